@@ -1,0 +1,92 @@
+// Shared device helpers for libclv_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/clv_b200.h"
+
+#define CLV_EPS 1e-7f  // keras _EPSILON [K2-recall]
+
+#define CLV_CHECK_LAUNCH()                                  \
+  do {                                                      \
+    cudaError_t e__ = cudaGetLastError();                   \
+    if (e__ != cudaSuccess) return CLV_E_CUDA;              \
+  } while (0)
+
+#define CLV_CUDA(call)                                      \
+  do {                                                      \
+    if ((call) != cudaSuccess) return CLV_E_CUDA;           \
+  } while (0)
+
+static inline int clv_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of one value per thread, result valid in thread 0.  `red` >= 32 floats of smem.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (wid == 0) v = warp_sum(v);
+  return v;
+}
+
+// ---- Philox4x32-10 (counter-based RNG; Salmon et al. 2011), keyed by (seed), counter (ctr, idx).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0; k.y += W1;
+  }
+  return c;
+}
+
+__device__ __forceinline__ float u32_to_unit(uint32_t x) {  // (0,1]
+  return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+}
+
+// Two independent N(0,1) draws for element `idx` of stream `stream_id` at call counter `ctr`.
+__device__ __forceinline__ float2 philox_normal2(uint64_t seed, uint64_t ctr, uint32_t stream_id,
+                                                 uint64_t idx) {
+  uint4 c = make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)ctr,
+                       (uint32_t)(ctr >> 32) ^ (stream_id * 0x9E3779B9u));
+  uint2 k = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  uint4 r = philox4x32_10(c, k);
+  const float u1 = u32_to_unit(r.x), u2 = u32_to_unit(r.y);
+  const float rad = sqrtf(-2.0f * logf(u1));
+  float s, co;
+  sincospif(2.0f * u2, &s, &co);
+  return make_float2(rad * co, rad * s);
+}
+
+__device__ __forceinline__ uint4 philox_u32x4(uint64_t seed, uint64_t ctr, uint32_t stream_id,
+                                              uint64_t idx) {
+  uint4 c = make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)ctr,
+                       (uint32_t)(ctr >> 32) ^ (stream_id * 0x9E3779B9u));
+  uint2 k = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  return philox4x32_10(c, k);
+}
+
+__device__ __forceinline__ float hard_sigmoid_f(float a) {  // keras hard_sigmoid [K2-recall]
+  return fminf(fmaxf(0.2f * a + 0.5f, 0.f), 1.f);
+}
+__device__ __forceinline__ float sigmoid_f(float a) { return 1.0f / (1.0f + expf(-a)); }

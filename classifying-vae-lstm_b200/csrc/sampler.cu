@@ -1,0 +1,349 @@
+// K5: persistent autoregressive samplers.  One CTA carries BT songs through ALL timesteps of
+// generate_sample (cl_vrnn/model.py:47-60 / cl_vae/model.py:27-42): the two stateful LSTM steps,
+// the Z heads + z draw, the sigmoid head, the Bernoulli threshold and the x_prev feedback never
+// leave the SM -- state lives in shared memory ([unit][song], so one LDS.128 feeds 4 songs) and
+// registers (cell states, the per-song W-column bias), weights stream from L2 (1 MB, resident) and
+// every weight load is reused for all BT songs.  The reference does 2 session.run per step at
+// batch 1; here a step costs no launch at all.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SH = 88;        // LSTM units the VRNN sampler is built for
+constexpr int SG = 4 * SH;    // gate columns = threads per CTA
+constexpr int BT = 16;        // songs per CTA
+
+struct VrnnSampArgs {
+  const float *Ke, *Ue, *be, *Kzm, *bzm, *Kzv, *bzv, *Kd, *Ud, *bd, *Kx, *bx;
+  const uint8_t* seed_roll;  // [S, T_seed, D]
+  const float* w;            // [S, C]
+  const float* eps_z;        // [S, T, Z] or null
+  const float* u;            // [S, T, D] or null
+  uint8_t* out;              // [S, T, D]
+  float* probs;              // [S, T, D] or null
+  uint64_t seed; int64_t song0;
+  int S, T_seed, T, D, Z, C, use_x_prev;
+};
+
+template <int NQ>
+__device__ __forceinline__ void fma_row(float (&acc)[4 * NQ], const float wgt, const float* srow) {
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(srow + 4 * q);
+    acc[4 * q + 0] = fmaf(wgt, v.x, acc[4 * q + 0]);
+    acc[4 * q + 1] = fmaf(wgt, v.y, acc[4 * q + 1]);
+    acc[4 * q + 2] = fmaf(wgt, v.z, acc[4 * q + 2]);
+    acc[4 * q + 3] = fmaf(wgt, v.w, acc[4 * q + 3]);
+  }
+}
+
+__global__ void __launch_bounds__(SG, 1) vrnn_sample_kernel(const VrnnSampArgs a) {
+  constexpr int H = SH, G = SG, NQ = BT / 4;
+  __shared__ __align__(16) float xT[128][BT];   // x_prev, [key][song]
+  __shared__ __align__(16) float heT[H][BT];
+  __shared__ __align__(16) float hdT[H][BT];
+  __shared__ __align__(16) float zT[16][BT];
+  __shared__ __align__(16) float za_s[32][BT];  // [mu | lv][song]
+  __shared__ __align__(16) float a_s[G][BT];
+  __shared__ __align__(16) float w_s[16][BT];
+  const int tid = threadIdx.x, n = tid;
+  const int D = a.D, Z = a.Z, C = a.C, T = a.T;
+  const int s0 = blockIdx.x * BT;
+  const int xo = a.use_x_prev ? D : 0;
+
+  for (int i = tid; i < 16 * BT; i += G) {
+    const int c = i / BT, s = i - c * BT;
+    w_s[c][s] = (c < C && s0 + s < a.S) ? a.w[(size_t)(s0 + s) * C + c] : 0.f;
+  }
+  for (int i = tid; i < H * BT; i += G) { (&heT[0][0])[i] = 0.f; (&hdT[0][0])[i] = 0.f; }
+  for (int i = tid; i < 128 * BT; i += G) {
+    const int d = i / BT, s = i - d * BT;
+    float v = 0.f;
+    if (d < D && s0 + s < a.S && a.T_seed > 0)
+      v = (float)a.seed_roll[((size_t)(s0 + s) * a.T_seed) * D + d];
+    xT[d][s] = v;
+  }
+  __syncthreads();
+  // per-song constant part of both input projections: bias + w @ K[W rows]  (RepeatVector(W))
+  float cbe[BT], cbd[BT];
+  {
+    const float b_e = __ldg(a.be + n), b_d = __ldg(a.bd + n);
+#pragma unroll
+    for (int s = 0; s < BT; ++s) { cbe[s] = b_e; cbd[s] = b_d; }
+    for (int c = 0; c < C; ++c) {
+      fma_row<NQ>(cbe, __ldg(a.Ke + (size_t)(D + c) * G + n), &w_s[c][0]);
+      fma_row<NQ>(cbd, __ldg(a.Kd + (size_t)(xo + Z + c) * G + n), &w_s[c][0]);
+    }
+  }
+  const int cj = tid % H, cq = tid / H;  // cell-update / output mapping: unit cj, songs 4cq..4cq+3
+  float c_e[4] = {0.f, 0.f, 0.f, 0.f}, c_d[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (int t = 0; t < T; ++t) {
+    float acc[BT];
+    // ---- z-encoder LSTM step on [x_prev | w]
+#pragma unroll
+    for (int s = 0; s < BT; ++s) acc[s] = cbe[s];
+#pragma unroll 8
+    for (int k = 0; k < D; ++k) fma_row<NQ>(acc, __ldg(a.Ke + (size_t)k * G + n), &xT[k][0]);
+#pragma unroll 8
+    for (int k = 0; k < H; ++k) fma_row<NQ>(acc, __ldg(a.Ue + (size_t)k * G + n), &heT[k][0]);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+      *reinterpret_cast<float4*>(&a_s[n][4 * q]) =
+          make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int s = 4 * cq + i;
+      const float ig = hard_sigmoid_f(a_s[cj][s]), fg = hard_sigmoid_f(a_s[H + cj][s]);
+      const float gg = tanhf(a_s[2 * H + cj][s]), og = hard_sigmoid_f(a_s[3 * H + cj][s]);
+      c_e[i] = fmaf(fg, c_e[i], ig * gg);
+      heT[cj][s] = og * tanhf(c_e[i]);
+    }
+    __syncthreads();
+    // ---- Z heads and z draw (sample_z, model.py:90-96)
+    for (int i = tid; i < BT * 2 * Z; i += G) {
+      const int s = i % BT, jz = i / BT;
+      const float* K = (jz < Z) ? (a.Kzm + jz) : (a.Kzv + (jz - Z));
+      float p = (jz < Z) ? __ldg(a.bzm + jz) : __ldg(a.bzv + (jz - Z));
+      for (int k = 0; k < H; ++k) p = fmaf(heT[k][s], __ldg(K + (size_t)k * Z), p);
+      za_s[jz][s] = p;
+    }
+    __syncthreads();
+    for (int i = tid; i < BT * Z; i += G) {
+      const int s = i % BT, j = i / BT;
+      const int64_t song = s0 + s;
+      float e = 0.f;
+      if (song < a.S) {
+        if (a.eps_z) e = __ldg(a.eps_z + ((size_t)song * T + t) * Z + j);
+        else e = philox_normal2(a.seed, 0, 3u, ((uint64_t)(a.song0 + song) * T + t) * Z + j).x;
+      }
+      zT[j][s] = za_s[j][s] + expf(za_s[Z + j][s] * 0.5f) * e;
+    }
+    __syncthreads();
+    // ---- decoder LSTM step on [x_prev | z | w]
+#pragma unroll
+    for (int s = 0; s < BT; ++s) acc[s] = cbd[s];
+    if (a.use_x_prev) {
+#pragma unroll 8
+      for (int k = 0; k < D; ++k) fma_row<NQ>(acc, __ldg(a.Kd + (size_t)k * G + n), &xT[k][0]);
+    }
+    for (int j = 0; j < Z; ++j) fma_row<NQ>(acc, __ldg(a.Kd + (size_t)(xo + j) * G + n), &zT[j][0]);
+#pragma unroll 8
+    for (int k = 0; k < H; ++k) fma_row<NQ>(acc, __ldg(a.Ud + (size_t)k * G + n), &hdT[k][0]);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+      *reinterpret_cast<float4*>(&a_s[n][4 * q]) =
+          make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int s = 4 * cq + i;
+      const float ig = hard_sigmoid_f(a_s[cj][s]), fg = hard_sigmoid_f(a_s[H + cj][s]);
+      const float gg = tanhf(a_s[2 * H + cj][s]), og = hard_sigmoid_f(a_s[3 * H + cj][s]);
+      c_d[i] = fmaf(fg, c_d[i], ig * gg);
+      hdT[cj][s] = og * tanhf(c_d[i]);
+    }
+    __syncthreads();
+    // ---- sigmoid head, Bernoulli threshold (sample_x, model.py:62-63), feedback
+    for (int d = cj; d < D; d += H) {
+      float lo[4];
+      const float b = __ldg(a.bx + d);
+      lo[0] = lo[1] = lo[2] = lo[3] = b;
+#pragma unroll 8
+      for (int k = 0; k < H; ++k) fma_row<1>(lo, __ldg(a.Kx + (size_t)k * D + d), &hdT[k][4 * cq]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int s = 4 * cq + i;
+        const int64_t song = s0 + s;
+        if (song >= a.S) continue;
+        const float p = sigmoid_f(lo[i]);
+        const size_t o = ((size_t)song * T + t) * D + d;
+        float uu;
+        if (a.u) uu = __ldg(a.u + o);
+        else uu = u32_to_unit(philox_u32x4(a.seed, 0, 4u, ((uint64_t)(a.song0 + song) * T + t) * D + d).x);
+        const float x = (uu <= p) ? 1.f : 0.f;
+        a.out[o] = (uint8_t)x;
+        if (a.probs) a.probs[o] = p;
+        // next x_prev: teacher-forced from the seed while t+1 < T_seed (model.py:48-49)
+        xT[d][s] = (t + 1 < a.T_seed)
+                       ? (float)a.seed_roll[((size_t)song * a.T_seed + (t + 1)) * D + d] : x;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------ CL-VAE sampler
+struct VaeSampArgs {
+  const float *Kh, *bh, *Kzm, *bzm, *Kzv, *bzv, *Kdh, *bdh, *Kx, *bx;
+  const uint8_t* x_seed;  // [S, D]
+  const float *w, *eps_z, *u;
+  uint8_t* out; float* probs;
+  uint64_t seed; int64_t song0;
+  int S, T, D, H, Z, C, use_x_prev, use_z_prior;
+};
+
+constexpr int VT = 128;  // threads: one per hidden unit / key
+
+__global__ void __launch_bounds__(VT, 1) vae_sample_kernel(const VaeSampArgs a) {
+  constexpr int NQ = BT / 4;
+  __shared__ __align__(16) float xT[2][128][BT];  // x_prev and the one-further-lagged x_prev_t
+  __shared__ __align__(16) float hT[128][BT];
+  __shared__ __align__(16) float zT[16][BT];
+  __shared__ __align__(16) float za_s[32][BT];
+  __shared__ __align__(16) float w_s[16][BT];
+  const int tid = threadIdx.x, n = tid;
+  const int D = a.D, H = a.H, Z = a.Z, C = a.C, T = a.T;
+  const int s0 = blockIdx.x * BT;
+  const int xo = a.use_x_prev ? D : 0;
+  for (int i = tid; i < 16 * BT; i += VT) {
+    const int c = i / BT, s = i - c * BT;
+    w_s[c][s] = (c < C && s0 + s < a.S) ? a.w[(size_t)(s0 + s) * C + c] : 0.f;
+  }
+  for (int i = tid; i < 128 * BT; i += VT) {
+    const int d = i / BT, s = i - d * BT;
+    const float v = (d < D && s0 + s < a.S) ? (float)a.x_seed[(size_t)(s0 + s) * D + d] : 0.f;
+    xT[0][d][s] = v; xT[1][d][s] = v;
+  }
+  __syncthreads();
+  float cbh[BT], cbd[BT];
+#pragma unroll
+  for (int s = 0; s < BT; ++s) { cbh[s] = 0.f; cbd[s] = 0.f; }
+  if (n < H) {
+    const float b_h = __ldg(a.bh + n), b_d = __ldg(a.bdh + n);
+#pragma unroll
+    for (int s = 0; s < BT; ++s) { cbh[s] = b_h; cbd[s] = b_d; }
+    for (int c = 0; c < C; ++c) {
+      fma_row<NQ>(cbh, __ldg(a.Kh + (size_t)(D + c) * H + n), &w_s[c][0]);
+      fma_row<NQ>(cbd, __ldg(a.Kdh + (size_t)c * H + n), &w_s[c][0]);
+    }
+  }
+  int cur = 0;  // xT[cur] = x_prev, xT[cur^1] = x_prev_t
+  for (int t = 0; t < T; ++t) {
+    float acc[BT];
+    // ---- z encoder: h = relu([x_prev | w] @ Kh + bh)   (cl_vae/model.py:28, make_z_encoder)
+    if (n < H) {
+#pragma unroll
+      for (int s = 0; s < BT; ++s) acc[s] = cbh[s];
+#pragma unroll 8
+      for (int k = 0; k < D; ++k) fma_row<NQ>(acc, __ldg(a.Kh + (size_t)k * H + n), &xT[cur][k][0]);
+#pragma unroll
+      for (int s = 0; s < BT; ++s) hT[n][s] = fmaxf(acc[s], 0.f);
+    }
+    __syncthreads();
+    for (int i = tid; i < BT * 2 * Z; i += VT) {
+      const int s = i % BT, jz = i / BT;
+      const float* K = (jz < Z) ? (a.Kzm + jz) : (a.Kzv + (jz - Z));
+      float p = (jz < Z) ? __ldg(a.bzm + jz) : __ldg(a.bzv + (jz - Z));
+      for (int k = 0; k < H; ++k) p = fmaf(hT[k][s], __ldg(K + (size_t)k * Z), p);
+      za_s[jz][s] = a.use_z_prior ? 0.f : p;   // --use_z_prior: sample_z((0*mean, 0*log_var))
+    }
+    __syncthreads();
+    for (int i = tid; i < BT * Z; i += VT) {
+      const int s = i % BT, j = i / BT;
+      const int64_t song = s0 + s;
+      float e = 0.f;
+      if (song < a.S) {
+        if (a.eps_z) e = __ldg(a.eps_z + ((size_t)song * T + t) * Z + j);
+        else e = philox_normal2(a.seed, 0, 3u, ((uint64_t)(a.song0 + song) * T + t) * Z + j).x;
+      }
+      zT[j][s] = za_s[j][s] + expf(za_s[Z + j][s] * 0.5f) * e;
+    }
+    __syncthreads();
+    // ---- decoder hidden: relu([w | x_prev_t | z] @ Kdh + b)   (cl_vae/model.py:34-38)
+    if (n < H) {
+#pragma unroll
+      for (int s = 0; s < BT; ++s) acc[s] = cbd[s];
+      if (a.use_x_prev) {
+#pragma unroll 8
+        for (int k = 0; k < D; ++k)
+          fma_row<NQ>(acc, __ldg(a.Kdh + (size_t)(C + k) * H + n), &xT[cur ^ 1][k][0]);
+      }
+      for (int j = 0; j < Z; ++j)
+        fma_row<NQ>(acc, __ldg(a.Kdh + (size_t)(C + xo + j) * H + n), &zT[j][0]);
+    }
+    __syncthreads();  // everyone is done reading hT (heads) before it is overwritten
+    if (n < H) {
+#pragma unroll
+      for (int s = 0; s < BT; ++s) hT[n][s] = fmaxf(acc[s], 0.f);
+    }
+    __syncthreads();
+    // ---- sigmoid head + threshold; x_prev_t <- x_prev, x_prev <- x_t   (model.py:39-41)
+    if (n < D) {
+      const float b = __ldg(a.bx + n);
+#pragma unroll
+      for (int s = 0; s < BT; ++s) acc[s] = b;
+#pragma unroll 8
+      for (int k = 0; k < H; ++k) fma_row<NQ>(acc, __ldg(a.Kx + (size_t)k * D + n), &hT[k][0]);
+#pragma unroll
+      for (int s = 0; s < BT; ++s) {
+        const int64_t song = s0 + s;
+        if (song >= a.S) continue;
+        const float p = sigmoid_f(acc[s]);
+        const size_t o = ((size_t)song * T + t) * D + n;
+        float uu;
+        if (a.u) uu = __ldg(a.u + o);
+        else uu = u32_to_unit(philox_u32x4(a.seed, 0, 4u, ((uint64_t)(a.song0 + song) * T + t) * D + n).x);
+        const float x = (uu <= p) ? 1.f : 0.f;
+        a.out[o] = (uint8_t)x;
+        if (a.probs) a.probs[o] = p;
+        xT[cur ^ 1][n][s] = x;  // the older buffer becomes the new x_prev
+      }
+    }
+    cur ^= 1;
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+extern "C" int clv_vrnn_sample(const clv_cfg* cfg, const float* params, const float* enc_kernel,
+                               const float* enc_rkernel, const float* enc_bias,
+                               const uint8_t* seed_roll, int32_t T_seed, int32_t nsteps,
+                               const float* w, const float* eps_z, const float* u, uint64_t seed,
+                               int64_t song0, int32_t S, uint8_t* out, float* probs, void* stream) {
+  if (!cfg || !params || !seed_roll || !w || !out) return CLV_E_INVALID;
+  if (cfg->model != 0 || cfg->H != SH || cfg->D > 128 || cfg->Z > 16 || cfg->C > 16 || cfg->C < 2)
+    return CLV_E_UNSUPPORTED;
+  if (T_seed < 1 || nsteps < 0) return CLV_E_INVALID;
+  if (S <= 0) return CLV_OK;
+  int64_t po[CLV_N_TENSORS]; int32_t pr[CLV_N_TENSORS], pc[CLV_N_TENSORS];
+  if (clv_param_layout(cfg, po, pr, pc) < 0) return CLV_E_INVALID;
+  VrnnSampArgs a;
+  a.Ke = enc_kernel ? enc_kernel : params + po[4];
+  a.Ue = enc_rkernel ? enc_rkernel : params + po[5];
+  a.be = enc_bias ? enc_bias : params + po[6];
+  a.Kzm = params + po[7]; a.bzm = params + po[8]; a.Kzv = params + po[9]; a.bzv = params + po[10];
+  a.Kd = params + po[11]; a.Ud = params + po[12]; a.bd = params + po[13];
+  a.Kx = params + po[14]; a.bx = params + po[15];
+  a.seed_roll = seed_roll; a.w = w; a.eps_z = eps_z; a.u = u; a.out = out; a.probs = probs;
+  a.seed = seed; a.song0 = song0; a.S = S; a.T_seed = T_seed; a.T = T_seed + nsteps;
+  a.D = cfg->D; a.Z = cfg->Z; a.C = cfg->C; a.use_x_prev = cfg->use_x_prev;
+  vrnn_sample_kernel<<<(S + BT - 1) / BT, SG, 0, (cudaStream_t)stream>>>(a);
+  CLV_CHECK_LAUNCH();
+  return CLV_OK;
+}
+
+extern "C" int clv_vae_sample(const clv_cfg* cfg, const float* params, const uint8_t* x_seed,
+                              int32_t nsteps, const float* w, const float* eps_z, const float* u,
+                              uint64_t seed, int64_t song0, int32_t S, int32_t use_z_prior,
+                              uint8_t* out, float* probs, void* stream) {
+  if (!cfg || !params || !x_seed || !w || !out) return CLV_E_INVALID;
+  if (cfg->model != 1 || cfg->H > 128 || cfg->D > 128 || cfg->Z > 16 || cfg->C > 16 || cfg->C < 2)
+    return CLV_E_UNSUPPORTED;
+  if (nsteps < 0) return CLV_E_INVALID;
+  if (S <= 0 || nsteps == 0) return CLV_OK;
+  int64_t po[CLV_N_TENSORS]; int32_t pr[CLV_N_TENSORS], pc[CLV_N_TENSORS];
+  if (clv_param_layout(cfg, po, pr, pc) < 0) return CLV_E_INVALID;
+  VaeSampArgs a;
+  a.Kh = params + po[6]; a.bh = params + po[7]; a.Kzm = params + po[8]; a.bzm = params + po[9];
+  a.Kzv = params + po[10]; a.bzv = params + po[11]; a.Kdh = params + po[12]; a.bdh = params + po[13];
+  a.Kx = params + po[14]; a.bx = params + po[15];
+  a.x_seed = x_seed; a.w = w; a.eps_z = eps_z; a.u = u; a.out = out; a.probs = probs;
+  a.seed = seed; a.song0 = song0; a.S = S; a.T = nsteps; a.D = cfg->D; a.H = cfg->H; a.Z = cfg->Z;
+  a.C = cfg->C; a.use_x_prev = cfg->use_x_prev; a.use_z_prior = use_z_prior;
+  vae_sample_kernel<<<(S + BT - 1) / BT, VT, 0, (cudaStream_t)stream>>>(a);
+  CLV_CHECK_LAUNCH();
+  return CLV_OK;
+}

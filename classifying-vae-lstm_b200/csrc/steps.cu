@@ -1,0 +1,367 @@
+// Parameter layout, workspace carving and the fused training-step drivers: the sequence of kernel
+// launches that replaces ONE tf.Session.run of Keras' train_function (cl_vrnn/train.py:66-71 ->
+// graph of cl_vrnn/model.py:169-264; cl_vae/train.py:63-69 -> cl_vae/model.py:136-218).
+// Host code only: no allocation, no synchronisation, everything stream-ordered (graph-capturable).
+#include <string.h>
+#include "common.cuh"
+
+namespace {
+
+// tensor indices in the flat buffer (Keras weighted-layer order)
+enum { R_HW_K, R_HW_B, R_WA_K, R_WA_B, R_ENC_K, R_ENC_U, R_ENC_B, R_ZM_K, R_ZM_B, R_ZV_K, R_ZV_B,
+       R_DEC_K, R_DEC_U, R_DEC_B, R_X_K, R_X_B };
+enum { V_HW_K, V_HW_B, V_WM_K, V_WM_B, V_WV_K, V_WV_B, V_H_K, V_H_B, V_ZM_K, V_ZM_B, V_ZV_K, V_ZV_B,
+       V_DH_K, V_DH_B, V_X_K, V_X_B };
+
+int check_cfg(const clv_cfg* c) {
+  if (!c) return CLV_E_INVALID;
+  if (c->model != 0 && c->model != 1) return CLV_E_INVALID;
+  if (c->B < 0 || c->B_global < c->B || c->L < 1 || c->D < 1 || c->H < 1 || c->Z < 1 || c->C < 2)
+    return CLV_E_INVALID;
+  if (c->C > 16 || c->Z > 16 || c->D > 128) return CLV_E_UNSUPPORTED;
+  if (c->model == 0 && c->H != 88) return CLV_E_UNSUPPORTED;   // K3 register tiling is built for 88
+  if (c->model == 1 && (c->L != 1 || c->H > 128 || c->Hc < 1)) return CLV_E_UNSUPPORTED;
+  return CLV_OK;
+}
+
+struct WsItem { const char* name; int64_t off, n; };
+struct Ws {
+  WsItem it[32];
+  int n = 0;
+  int64_t total = 0;
+  int64_t add(const char* name, int64_t count) {
+    const int64_t off = total;
+    it[n++] = {name, off, count};
+    total += (count + 63) / 64 * 64;
+    return off;
+  }
+  int64_t find(const char* name) const {
+    for (int i = 0; i < n; ++i) if (!strcmp(it[i].name, name)) return it[i].off;
+    return -1;
+  }
+};
+
+Ws carve(const clv_cfg* c) {
+  Ws w;
+  const int64_t B = c->B, L = c->L, D = c->D, H = c->H, Z = c->Z, C = c->C, C1 = C - 1;
+  if (c->model == 0) {
+    const int64_t G = 4 * H, BL = B * L;
+    w.add("hW", B * D); w.add("Wargs", B * 2 * C1); w.add("W", B * C);
+    w.add("rb_e", B * G); w.add("gates_e", BL * G); w.add("h_e", BL * H); w.add("c_e", BL * H);
+    w.add("Zargs", BL * 2 * Z); w.add("Zs", BL * Z);
+    w.add("rb_d", B * G); w.add("gates_d", BL * G); w.add("h_d", BL * H); w.add("c_d", BL * H);
+    w.add("logits", BL * D); w.add("dh", BL * H);
+    w.add("dAsum_d", B * G); w.add("dAsum_e", B * G); w.add("dZ", BL * Z);
+    w.add("dW_ext", B * C); w.add("dWargs", B * 2 * C1); w.add("dhW", B * D);
+  } else {
+    const int64_t Hc = c->Hc;
+    w.add("h_w", B * Hc); w.add("Wargs", B * 2 * C1); w.add("W", B * C);
+    w.add("h", B * H); w.add("Zargs", B * 2 * Z); w.add("Zs", B * Z);
+    w.add("h_dec", B * H); w.add("logits", B * D);
+    w.add("dpre", B * H); w.add("dh", B * H); w.add("dZ", B * Z);
+    w.add("dW_ext", B * C); w.add("dWargs", B * 2 * C1); w.add("dh_w", B * Hc);
+  }
+  return w;
+}
+
+// ---- GEMM call helpers ---------------------------------------------------------------
+clv_gemm_args gz() { clv_gemm_args a; memset(&a, 0, sizeof(a)); a.a_kmajor = 1; a.b_nmajor = 1; a.split_k = 1; return a; }
+
+int pick_split(int M, int N, int K) {
+  const int tiles = ((M + 63) / 64) * ((N + 63) / 64);
+  int split = (2 * clv_num_sms() + tiles - 1) / tiles;
+  const int maxs = (K + 63) / 64;
+  if (split > maxs) split = maxs;
+  return split < 1 ? 1 : split;
+}
+
+// C[M,N] = act(A_f32[M,K] @ B[K,N] + bias + rowadd)            (forward Dense)
+int nn_f32(const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc, int M,
+           int N, int K, const float* bias, int relu, int accumulate, cudaStream_t st) {
+  clv_gemm_args a = gz();
+  a.M = M; a.N = N; a.K = K; a.A = A; a.lda = lda; a.Bm = Bm; a.ldb = ldb; a.C = C; a.ldc = ldc;
+  a.bias = bias; a.relu = relu; a.accumulate = accumulate;
+  return clv_gemm(&a, st);
+}
+// C[M,N] = act(roll_u8 gather @ B + bias + rowadd[m/grp])       (forward Dense on piano-roll rows)
+int nn_u8(const uint8_t* roll, const int32_t* off, int grp, int shift, int64_t lda, const float* Bm,
+          int64_t ldb, float* C, int64_t ldc, int M, int N, int K, const float* bias,
+          const float* rowadd, int64_t ldra, int ra_grp, int relu, int accumulate, cudaStream_t st) {
+  clv_gemm_args a = gz();
+  a.M = M; a.N = N; a.K = K; a.A = roll; a.lda = lda; a.a_u8 = 1; a.a_off = off; a.a_grp = grp;
+  a.a_shift = shift; a.Bm = Bm; a.ldb = ldb; a.C = C; a.ldc = ldc; a.bias = bias; a.rowadd = rowadd;
+  a.ldra = ldra; a.ra_grp = ra_grp; a.relu = relu; a.accumulate = accumulate;
+  return clv_gemm(&a, st);
+}
+// dA[M,N] = (dC[M,K] @ W[N,K]^T) (* mask)                        (dgrad)
+int nt_f32(const float* dC, int64_t ldd, const float* W, int64_t ldw, float* dA, int64_t lda, int M,
+           int N, int K, const float* mask, int64_t ldmask, int accumulate, cudaStream_t st) {
+  clv_gemm_args a = gz();
+  a.M = M; a.N = N; a.K = K; a.A = dC; a.lda = ldd; a.Bm = W; a.ldb = ldw; a.b_nmajor = 0; a.C = dA;
+  a.ldc = lda; a.relu_mask = mask; a.ldmask = ldmask; a.accumulate = accumulate;
+  return clv_gemm(&a, st);
+}
+// dW[M,N] += A[K,M]^T @ dC[K,N]                                   (wgrad, fp32 A)
+int tn_f32(const float* A, int64_t lda, const float* dC, int64_t ldd, float* dW, int64_t ldw, int M,
+           int N, int K, int row_delta, int skip_grp, cudaStream_t st) {
+  clv_gemm_args a = gz();
+  a.M = M; a.N = N; a.K = K; a.A = A; a.lda = lda; a.a_kmajor = 0; a.a_row_delta = row_delta;
+  a.a_skip_grp = skip_grp; a.Bm = dC; a.ldb = ldd; a.C = dW; a.ldc = ldw;
+  a.split_k = pick_split(M, N, K);
+  a.accumulate = 1;
+  return clv_gemm(&a, st);
+}
+// dW[M,N] += roll_u8[K rows gathered, M]^T @ dC[K,N]              (wgrad, piano-roll A)
+int tn_u8(const uint8_t* roll, const int32_t* off, int grp, int shift, int64_t lda, const float* dC,
+          int64_t ldd, float* dW, int64_t ldw, int M, int N, int K, cudaStream_t st) {
+  clv_gemm_args a = gz();
+  a.M = M; a.N = N; a.K = K; a.A = roll; a.lda = lda; a.a_u8 = 1; a.a_kmajor = 0; a.a_off = off;
+  a.a_grp = grp; a.a_shift = shift; a.Bm = dC; a.ldb = ldd; a.C = dW; a.ldc = ldw;
+  a.split_k = pick_split(M, N, K);
+  a.accumulate = 1;
+  return clv_gemm(&a, st);
+}
+
+#define TRY(x) do { int rc__ = (x); if (rc__ != CLV_OK) return rc__; } while (0)
+
+int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uint8_t* roll,
+              const int32_t* off, const int32_t* labels, float* eps_w, float* eps_z,
+              uint64_t* ctr, float* ws, cudaStream_t st) {
+  int64_t po[CLV_N_TENSORS]; int32_t pr[CLV_N_TENSORS], pc[CLV_N_TENSORS];
+  clv_param_layout(c, po, pr, pc);
+  const int B = c->B, L = c->L, D = c->D, H = c->H, Z = c->Z, C = c->C, C1 = C - 1, G = 4 * H;
+  const int BL = B * L, xo = c->use_x_prev ? D : 0, sx = c->use_x_prev ? 1 : 0;
+  const float sb = 1.0f / (float)c->B_global, sbl = 1.0f / ((float)c->B_global * (float)L);
+  const Ws w = carve(c);
+#define WSP(name) (ws + w.find(name))
+  float *hW = WSP("hW"), *Wargs = WSP("Wargs"), *W = WSP("W"), *rb_e = WSP("rb_e"),
+        *gates_e = WSP("gates_e"), *h_e = WSP("h_e"), *c_e = WSP("c_e"), *Zargs = WSP("Zargs"),
+        *Zs = WSP("Zs"), *rb_d = WSP("rb_d"), *gates_d = WSP("gates_d"), *h_d = WSP("h_d"),
+        *c_d = WSP("c_d"), *logits = WSP("logits"), *dh = WSP("dh"), *dAsum_d = WSP("dAsum_d"),
+        *dAsum_e = WSP("dAsum_e"), *dZ = WSP("dZ"), *dW_ext = WSP("dW_ext"),
+        *dWargs = WSP("dWargs"), *dhW = WSP("dhW");
+#undef WSP
+  const float *Khw = P + po[R_HW_K], *bhw = P + po[R_HW_B], *Kwa = P + po[R_WA_K],
+              *bwa = P + po[R_WA_B], *Ke = P + po[R_ENC_K], *Ue = P + po[R_ENC_U],
+              *be = P + po[R_ENC_B], *Kzm = P + po[R_ZM_K], *bzm = P + po[R_ZM_B],
+              *Kzv = P + po[R_ZV_K], *bzv = P + po[R_ZV_B], *Kd = P + po[R_DEC_K],
+              *Ud = P + po[R_DEC_U], *bd = P + po[R_DEC_B], *Kx = P + po[R_X_K], *bx = P + po[R_X_B];
+
+  TRY(clv_step_begin(loss, ctr, !c->accumulate, c->gen_noise, st));
+  if (c->do_backward && !c->accumulate)
+    CLV_CUDA(cudaMemsetAsync(Gr, 0, sizeof(float) * (po[R_X_B] + pc[R_X_B]), st));
+
+  // ---- forward: key encoder (model.py:174-191)
+  TRY(nn_u8(roll, off, 1, sx, D, Khw, D, hW, D, B, D, L * D, bhw, nullptr, 0, 0, 1, 0, st));
+  TRY(nn_f32(hW, D, Kwa, 2 * C1, Wargs, 2 * C1, B, 2 * C1, D, bwa, 0, 0, st));
+  TRY(clv_logitnormal_fwd(Wargs, 2 * C1, eps_w, labels, W, loss, B, C, c->w_log_var_prior, sb,
+                          c->gen_noise, c->seed, ctr, st));
+  // ---- encoder LSTM (model.py:193-199): input projection hoisted, W term is a per-sequence bias
+  TRY(nn_f32(W, C, Ke + (int64_t)D * G, G, rb_e, G, B, G, C, be, 0, 0, st));
+  TRY(nn_u8(roll, off, L, sx, D, Ke, G, gates_e, G, BL, G, D, nullptr, rb_e, G, L, 0, 0, st));
+  TRY(clv_lstm_fwd(gates_e, Ue, h_e, c_e, nullptr, nullptr, B, L, H, st));
+  // ---- Z heads + sample + kl (model.py:200-216,236-239)
+  TRY(clv_gauss_heads_fwd(h_e, Kzm, bzm, Kzv, bzv, eps_z, Zargs, Zs, loss, BL, H, Z, sbl,
+                          c->gen_noise, c->seed, ctr, st));
+  // ---- decoder LSTM (model.py:218-228): input [Xp | Z | W]
+  TRY(nn_f32(W, C, Kd + (int64_t)(xo + Z) * G, G, rb_d, G, B, G, C, bd, 0, 0, st));
+  if (c->use_x_prev) {
+    TRY(nn_u8(roll, off, L, 0, D, Kd, G, gates_d, G, BL, G, D, nullptr, rb_d, G, L, 0, 0, st));
+    TRY(nn_f32(Zs, Z, Kd + (int64_t)xo * G, G, gates_d, G, BL, G, Z, nullptr, 0, 1, st));
+  } else {
+    clv_gemm_args a = gz();
+    a.M = BL; a.N = G; a.K = Z; a.A = Zs; a.lda = Z; a.Bm = Kd; a.ldb = G; a.C = gates_d; a.ldc = G;
+    a.rowadd = rb_d; a.ldra = G; a.ra_grp = L;
+    TRY(clv_gemm(&a, st));
+  }
+  TRY(clv_lstm_fwd(gates_d, Ud, h_d, c_d, nullptr, nullptr, B, L, H, st));
+  // ---- X head + Bernoulli loss (+ dlogits) (model.py:229-234,241-242)
+  TRY(nn_f32(h_d, H, Kx, D, logits, D, BL, D, H, bx, 0, 0, st));
+  TRY(clv_bernoulli_ce_fwd_bwd(logits, roll, off, L, sx, loss, BL, D, sbl, c->do_backward, st));
+  if (!c->do_backward) return CLV_OK;
+
+  // ---- backward
+  float *gKhw = Gr + po[R_HW_K], *gbhw = Gr + po[R_HW_B], *gKwa = Gr + po[R_WA_K],
+        *gbwa = Gr + po[R_WA_B], *gKe = Gr + po[R_ENC_K], *gUe = Gr + po[R_ENC_U],
+        *gbe = Gr + po[R_ENC_B], *gKzm = Gr + po[R_ZM_K], *gbzm = Gr + po[R_ZM_B],
+        *gKzv = Gr + po[R_ZV_K], *gbzv = Gr + po[R_ZV_B], *gKd = Gr + po[R_DEC_K],
+        *gUd = Gr + po[R_DEC_U], *gbd = Gr + po[R_DEC_B], *gKx = Gr + po[R_X_K],
+        *gbx = Gr + po[R_X_B];
+  TRY(tn_f32(h_d, H, logits, D, gKx, D, H, D, BL, 0, 0, st));
+  TRY(clv_colsum(logits, D, BL, D, gbx, 1, st));
+  TRY(nt_f32(logits, D, Kx, D, dh, H, BL, H, D, nullptr, 0, 0, st));
+  TRY(clv_lstm_bwd(gates_d, Ud, h_d, c_d, dh, dAsum_d, B, L, H, st));
+  if (c->use_x_prev) TRY(tn_u8(roll, off, L, 0, D, gates_d, G, gKd, G, D, G, BL, st));
+  TRY(tn_f32(Zs, Z, gates_d, G, gKd + (int64_t)xo * G, G, Z, G, BL, 0, 0, st));
+  TRY(tn_f32(W, C, dAsum_d, G, gKd + (int64_t)(xo + Z) * G, G, C, G, B, 0, 0, st));
+  TRY(tn_f32(h_d, H, gates_d, G, gUd, G, H, G, BL, -1, L, st));
+  TRY(clv_colsum(dAsum_d, G, B, G, gbd, 1, st));
+  TRY(nt_f32(gates_d, G, Kd + (int64_t)xo * G, G, dZ, Z, BL, Z, G, nullptr, 0, 0, st));
+  TRY(nt_f32(dAsum_d, G, Kd + (int64_t)(xo + Z) * G, G, dW_ext, C, B, C, G, nullptr, 0, 0, st));
+  TRY(clv_gauss_heads_bwd(h_e, Kzm, Kzv, eps_z, Zargs, dZ, dh, gKzm, gbzm, gKzv, gbzv, BL, H, Z,
+                          c->kl_weight * sbl, 0, st));
+  TRY(clv_lstm_bwd(gates_e, Ue, h_e, c_e, dh, dAsum_e, B, L, H, st));
+  TRY(tn_u8(roll, off, L, sx, D, gates_e, G, gKe, G, D, G, BL, st));
+  TRY(tn_f32(W, C, dAsum_e, G, gKe + (int64_t)D * G, G, C, G, B, 0, 0, st));
+  TRY(tn_f32(h_e, H, gates_e, G, gUe, G, H, G, BL, -1, L, st));
+  TRY(clv_colsum(dAsum_e, G, B, G, gbe, 1, st));
+  TRY(nt_f32(dAsum_e, G, Ke + (int64_t)D * G, G, dW_ext, C, B, C, G, nullptr, 0, 1, st));
+  TRY(clv_logitnormal_bwd(Wargs, 2 * C1, eps_w, labels, W, dW_ext, dWargs, B, C,
+                          c->w_log_var_prior, c->class_weight * sb, c->w_kl_weight * sb, st));
+  TRY(tn_f32(hW, D, dWargs, 2 * C1, gKwa, 2 * C1, D, 2 * C1, B, 0, 0, st));
+  TRY(clv_colsum(dWargs, 2 * C1, B, 2 * C1, gbwa, 1, st));
+  TRY(nt_f32(dWargs, 2 * C1, Kwa, 2 * C1, dhW, D, B, D, 2 * C1, hW, D, 0, st));
+  TRY(tn_u8(roll, off, 1, sx, D, dhW, D, gKhw, D, L * D, D, B, st));
+  TRY(clv_colsum(dhW, D, B, D, gbhw, 1, st));
+  return CLV_OK;
+}
+
+int vae_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uint8_t* roll,
+             const int32_t* off, const int32_t* labels, float* eps_w, float* eps_z, uint64_t* ctr,
+             float* ws, cudaStream_t st) {
+  int64_t po[CLV_N_TENSORS]; int32_t pr[CLV_N_TENSORS], pc[CLV_N_TENSORS];
+  clv_param_layout(c, po, pr, pc);
+  const int B = c->B, D = c->D, H = c->H, Hc = c->Hc, Z = c->Z, C = c->C, C1 = C - 1;
+  const int xo = c->use_x_prev ? D : 0, sx = c->use_x_prev ? 1 : 0;
+  const float sb = 1.0f / (float)c->B_global;
+  const Ws w = carve(c);
+#define WSP(name) (ws + w.find(name))
+  float *h_w = WSP("h_w"), *Wargs = WSP("Wargs"), *W = WSP("W"), *h = WSP("h"),
+        *Zargs = WSP("Zargs"), *Zs = WSP("Zs"), *h_dec = WSP("h_dec"), *logits = WSP("logits"),
+        *dpre = WSP("dpre"), *dh = WSP("dh"), *dZ = WSP("dZ"), *dW_ext = WSP("dW_ext"),
+        *dWargs = WSP("dWargs"), *dh_w = WSP("dh_w");
+#undef WSP
+  const float *Khw = P + po[V_HW_K], *bhw = P + po[V_HW_B], *Kwm = P + po[V_WM_K],
+              *bwm = P + po[V_WM_B], *Kwv = P + po[V_WV_K], *bwv = P + po[V_WV_B],
+              *Kh = P + po[V_H_K], *bh = P + po[V_H_B], *Kzm = P + po[V_ZM_K], *bzm = P + po[V_ZM_B],
+              *Kzv = P + po[V_ZV_K], *bzv = P + po[V_ZV_B], *Kdh = P + po[V_DH_K],
+              *bdh = P + po[V_DH_B], *Kx = P + po[V_X_K], *bx = P + po[V_X_B];
+
+  TRY(clv_step_begin(loss, ctr, !c->accumulate, c->gen_noise, st));
+  if (c->do_backward && !c->accumulate)
+    CLV_CUDA(cudaMemsetAsync(Gr, 0, sizeof(float) * (po[V_X_B] + pc[V_X_B]), st));
+
+  // ---- forward (cl_vae/model.py:141-188)
+  TRY(nn_u8(roll, off, 1, sx, D, Khw, Hc, h_w, Hc, B, Hc, D, bhw, nullptr, 0, 0, 1, 0, st));
+  TRY(nn_f32(h_w, Hc, Kwm, C1, Wargs, 2 * C1, B, C1, Hc, bwm, 0, 0, st));
+  TRY(nn_f32(h_w, Hc, Kwv, C1, Wargs + C1, 2 * C1, B, C1, Hc, bwv, 0, 0, st));
+  TRY(clv_logitnormal_fwd(Wargs, 2 * C1, eps_w, labels, W, loss, B, C, c->w_log_var_prior, sb,
+                          c->gen_noise, c->seed, ctr, st));
+  TRY(nn_u8(roll, off, 1, sx, D, Kh, H, h, H, B, H, D, nullptr, nullptr, 0, 0, 0, 0, st));
+  TRY(nn_f32(W, C, Kh + (int64_t)D * H, H, h, H, B, H, C, bh, 1, 1, st));
+  TRY(clv_gauss_heads_fwd(h, Kzm, bzm, Kzv, bzv, eps_z, Zargs, Zs, loss, B, H, Z, sb, c->gen_noise,
+                          c->seed, ctr, st));
+  TRY(nn_f32(W, C, Kdh, H, h_dec, H, B, H, C, nullptr, 0, 0, st));
+  if (c->use_x_prev)
+    TRY(nn_u8(roll, off, 1, 0, D, Kdh + (int64_t)C * H, H, h_dec, H, B, H, D, nullptr, nullptr, 0, 0,
+              0, 1, st));
+  TRY(nn_f32(Zs, Z, Kdh + (int64_t)(C + xo) * H, H, h_dec, H, B, H, Z, bdh, 1, 1, st));
+  TRY(nn_f32(h_dec, H, Kx, D, logits, D, B, D, H, bx, 0, 0, st));
+  TRY(clv_bernoulli_ce_fwd_bwd(logits, roll, off, 1, sx, loss, B, D, sb, c->do_backward, st));
+  if (!c->do_backward) return CLV_OK;
+
+  // ---- backward
+  float *gKhw = Gr + po[V_HW_K], *gbhw = Gr + po[V_HW_B], *gKwm = Gr + po[V_WM_K],
+        *gbwm = Gr + po[V_WM_B], *gKwv = Gr + po[V_WV_K], *gbwv = Gr + po[V_WV_B],
+        *gKh = Gr + po[V_H_K], *gbh = Gr + po[V_H_B], *gKzm = Gr + po[V_ZM_K],
+        *gbzm = Gr + po[V_ZM_B], *gKzv = Gr + po[V_ZV_K], *gbzv = Gr + po[V_ZV_B],
+        *gKdh = Gr + po[V_DH_K], *gbdh = Gr + po[V_DH_B], *gKx = Gr + po[V_X_K],
+        *gbx = Gr + po[V_X_B];
+  TRY(tn_f32(h_dec, H, logits, D, gKx, D, H, D, B, 0, 0, st));
+  TRY(clv_colsum(logits, D, B, D, gbx, 1, st));
+  TRY(nt_f32(logits, D, Kx, D, dpre, H, B, H, D, h_dec, H, 0, st));
+  TRY(tn_f32(W, C, dpre, H, gKdh, H, C, H, B, 0, 0, st));
+  if (c->use_x_prev) TRY(tn_u8(roll, off, 1, 0, D, dpre, H, gKdh + (int64_t)C * H, H, D, H, B, st));
+  TRY(tn_f32(Zs, Z, dpre, H, gKdh + (int64_t)(C + xo) * H, H, Z, H, B, 0, 0, st));
+  TRY(clv_colsum(dpre, H, B, H, gbdh, 1, st));
+  TRY(nt_f32(dpre, H, Kdh, H, dW_ext, C, B, C, H, nullptr, 0, 0, st));
+  TRY(nt_f32(dpre, H, Kdh + (int64_t)(C + xo) * H, H, dZ, Z, B, Z, H, nullptr, 0, 0, st));
+  TRY(clv_gauss_heads_bwd(h, Kzm, Kzv, eps_z, Zargs, dZ, dh, gKzm, gbzm, gKzv, gbzv, B, H, Z,
+                          c->kl_weight * sb, 1, st));
+  TRY(tn_u8(roll, off, 1, sx, D, dh, H, gKh, H, D, H, B, st));
+  TRY(tn_f32(W, C, dh, H, gKh + (int64_t)D * H, H, C, H, B, 0, 0, st));
+  TRY(clv_colsum(dh, H, B, H, gbh, 1, st));
+  TRY(nt_f32(dh, H, Kh + (int64_t)D * H, H, dW_ext, C, B, C, H, nullptr, 0, 1, st));
+  TRY(clv_logitnormal_bwd(Wargs, 2 * C1, eps_w, labels, W, dW_ext, dWargs, B, C,
+                          c->w_log_var_prior, c->class_weight * sb, c->w_kl_weight * sb, st));
+  TRY(tn_f32(h_w, Hc, dWargs, 2 * C1, gKwm, C1, Hc, C1, B, 0, 0, st));
+  TRY(tn_f32(h_w, Hc, dWargs + C1, 2 * C1, gKwv, C1, Hc, C1, B, 0, 0, st));
+  TRY(clv_colsum(dWargs, 2 * C1, B, C1, gbwm, 1, st));
+  TRY(clv_colsum(dWargs + C1, 2 * C1, B, C1, gbwv, 1, st));
+  TRY(nt_f32(dWargs, 2 * C1, Kwm, C1, dh_w, Hc, B, Hc, C1, nullptr, 0, 0, st));
+  TRY(nt_f32(dWargs + C1, 2 * C1, Kwv, C1, dh_w, Hc, B, Hc, C1, h_w, Hc, 1, st));
+  TRY(tn_u8(roll, off, 1, sx, D, dh_w, Hc, gKhw, Hc, D, Hc, B, st));
+  TRY(clv_colsum(dh_w, Hc, B, Hc, gbhw, 1, st));
+  return CLV_OK;
+}
+
+}  // namespace
+
+extern "C" int clv_version(void) { return 100; }
+
+extern "C" const char* clv_error_string(int code) {
+  switch (code) {
+    case CLV_OK: return "ok";
+    case CLV_E_INVALID: return "invalid argument";
+    case CLV_E_UNSUPPORTED: return "unsupported shape (H must be 88 for the LSTM; C<=16, Z<=16, D<=128)";
+    case CLV_E_CUDA: return "CUDA error (launch or runtime call failed; no CPU fallback exists)";
+    case CLV_E_WORKSPACE: return "workspace too small";
+    default: return "unknown error";
+  }
+}
+
+extern "C" int64_t clv_param_layout(const clv_cfg* c, int64_t* offs, int32_t* rows, int32_t* cols) {
+  if (!c || !offs || !rows || !cols) return CLV_E_INVALID;
+  const int D = c->D, H = c->H, Z = c->Z, C = c->C, L = c->L;
+  int r[CLV_N_TENSORS], k[CLV_N_TENSORS];
+  if (c->model == 0) {
+    const int G = 4 * H, in_d = (c->use_x_prev ? D : 0) + Z + C;
+    const int rr[] = {L * D, 0, D, 0, D + C, H, 0, H, 0, H, 0, in_d, H, 0, H, 0};
+    const int cc[] = {D, D, 2 * (C - 1), 2 * (C - 1), G, G, G, Z, Z, Z, Z, G, G, G, D, D};
+    memcpy(r, rr, sizeof(rr)); memcpy(k, cc, sizeof(cc));
+  } else if (c->model == 1) {
+    const int Hc = c->Hc, in_dec = C + (c->use_x_prev ? D : 0) + Z;
+    const int rr[] = {D, 0, Hc, 0, Hc, 0, D + C, 0, H, 0, H, 0, in_dec, 0, H, 0};
+    const int cc[] = {Hc, Hc, C - 1, C - 1, C - 1, C - 1, H, H, Z, Z, Z, Z, H, H, D, D};
+    memcpy(r, rr, sizeof(rr)); memcpy(k, cc, sizeof(cc));
+  } else {
+    return CLV_E_INVALID;
+  }
+  int64_t o = 0;
+  for (int i = 0; i < CLV_N_TENSORS; ++i) {
+    offs[i] = o; rows[i] = r[i]; cols[i] = k[i];
+    o += (r[i] > 0 ? (int64_t)r[i] : 1) * k[i];
+  }
+  return o;
+}
+
+extern "C" int64_t clv_workspace_bytes(const clv_cfg* cfg) {
+  int rc = check_cfg(cfg);
+  if (rc != CLV_OK) return rc;
+  return carve(cfg).total * (int64_t)sizeof(float);
+}
+
+extern "C" int64_t clv_workspace_offset(const clv_cfg* cfg, const char* name) {
+  if (check_cfg(cfg) != CLV_OK || !name) return -1;
+  return carve(cfg).find(name);
+}
+
+extern "C" int clv_train_step(const clv_cfg* cfg, const float* params, float* grads,
+                              float* loss_acc, const uint8_t* roll, const int32_t* win_off,
+                              const int32_t* labels, float* eps_w, float* eps_z, uint64_t* rng_ctr,
+                              void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc != CLV_OK) return rc;
+  if (!params || !loss_acc || !roll || !win_off || !labels || !eps_w || !eps_z || !workspace)
+    return CLV_E_INVALID;
+  if (cfg->do_backward && !grads) return CLV_E_INVALID;
+  if (cfg->gen_noise && !rng_ctr) return CLV_E_INVALID;
+  if (workspace_bytes < carve(cfg).total * (int64_t)sizeof(float)) return CLV_E_WORKSPACE;
+  if (cfg->B == 0) return CLV_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cfg->model == 0)
+    return vrnn_step(cfg, params, grads, loss_acc, roll, win_off, labels, eps_w, eps_z, rng_ctr,
+                     (float*)workspace, st);
+  return vae_step(cfg, params, grads, loss_acc, roll, win_off, labels, eps_w, eps_z, rng_ctr,
+                  (float*)workspace, st);
+}

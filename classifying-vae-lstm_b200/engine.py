@@ -1,0 +1,218 @@
+"""
+Device-side engine behind the Keras-like model objects: owns the flat parameter / gradient /
+optimizer-state / workspace buffers (PyTorch is only the allocator and the stream/NCCL plumbing) and
+drives libclv_b200's fused train step, the NCCL gradient all-reduce and the Adam-WN update, optionally
+replayed as one CUDA graph.  One process per GPU; data parallel = batch sharded across ranks.
+
+Replaces what Keras' `train_function` / `test_function` do for the reference (cl_vrnn/train.py:66-71;
+graph cl_vrnn/model.py:169-264; optimizer utils/weightnorm.py:75-143).
+"""
+import ctypes as C
+import math
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr
+
+VRNN_TENSORS = ["hW.kernel", "hW.bias", "Wargs.kernel", "Wargs.bias",
+                "encoder_h.kernel", "encoder_h.recurrent_kernel", "encoder_h.bias",
+                "Z_mean.kernel", "Z_mean.bias", "Z_log_var.kernel", "Z_log_var.bias",
+                "decoder_h.kernel", "decoder_h.recurrent_kernel", "decoder_h.bias",
+                "X_decoded_mean.kernel", "X_decoded_mean.bias"]
+VAE_TENSORS = ["h_w.kernel", "h_w.bias", "w_mean.kernel", "w_mean.bias", "w_log_var.kernel",
+               "w_log_var.bias", "h.kernel", "h.bias", "z_mean.kernel", "z_mean.bias",
+               "z_log_var.kernel", "z_log_var.bias", "decoder_h.kernel", "decoder_h.bias",
+               "x_decoded_mean.kernel", "x_decoded_mean.bias"]
+LOSS_NAMES = ["vae", "w_kl", "w_rec", "z_kl", "acc"]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.ClvError("no CUDA device: the CL-VAE/CL-VRNN hot path has no CPU fallback")
+
+
+class Engine:
+    def __init__(self, model, B, L=1, D=88, H=88, Z=2, n_classes=2, use_x_prev=False, Hc=88,
+                 class_weight=1.0, kl_weight=1.0, w_kl_weight=1.0, w_log_var_prior=0.0,
+                 optimizer="adam-wn", lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-8,
+                 seed=0, device=None, world_size=1, rank=0, process_group=None, use_graph=True):
+        _require_cuda()
+        lib()
+        if optimizer not in ("adam-wn", "adam"):
+            raise NotImplementedError("optimizer %r: only 'adam-wn' (reference default) and 'adam' "
+                                      "are built" % (optimizer,))
+        self.model = {"vrnn": 0, "vae": 1}[model] if isinstance(model, str) else int(model)
+        self.dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.B, self.L, self.D, self.H, self.Z, self.C = B, (L if self.model == 0 else 1), D, H, Z, n_classes
+        self.Hc = Hc
+        self.use_x_prev = bool(use_x_prev)
+        self.W = self.L + 1 if self.use_x_prev else self.L            # frames per window
+        self.hyper = dict(class_weight=class_weight, kl_weight=kl_weight, w_kl_weight=w_kl_weight,
+                          w_log_var_prior=w_log_var_prior)
+        self.optimizer, self.lr, self.b1, self.b2, self.eps = optimizer, lr, beta_1, beta_2, epsilon
+        self.world_size, self.rank, self.pg = world_size, rank, process_group
+        self.seed = (int(seed) * 1000003 + rank * 7919 + 1) & 0xFFFFFFFFFFFFFFFF
+        self.use_graph = use_graph
+        self.names = VRNN_TENSORS if self.model == 0 else VAE_TENSORS
+        cfg = self.cfg()
+        self.P, self.offs, self.rows, self.cols = _lib.param_layout(cfg)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.params = torch.zeros(self.P, **f32)
+        self.gradbuf = torch.zeros(self.P + 8, **f32)                  # [grads | 8 loss scalars]
+        self.grads, self.loss_acc = self.gradbuf[:self.P], self.gradbuf[self.P:]
+        n_state = check(lib().clv_adamwn_state_floats(C.byref(cfg)), "clv_adamwn_state_floats")
+        self.opt_state = torch.zeros(n_state, **f32)
+        check(lib().clv_adamwn_init(C.byref(cfg), ptr(self.opt_state), _stream()), "clv_adamwn_init")
+        ws_bytes = check(lib().clv_workspace_bytes(C.byref(cfg)), "clv_workspace_bytes")
+        self.workspace = torch.zeros(ws_bytes // 4 + 64, **f32)
+        self.eps_w = torch.zeros(B * (self.C - 1), **f32)
+        self.eps_z = torch.zeros(B * self.L * Z, **f32)
+        self.rng_ctr = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.labels = torch.zeros(B, dtype=torch.int32, device=self.dev)
+        self.win_off = (torch.arange(B, dtype=torch.int32, device=self.dev) * self.W).contiguous()
+        self.win_buf = torch.zeros(B * self.W * D, dtype=torch.uint8, device=self.dev)
+        self.roll = self.win_buf                                       # or a resident dataset roll
+        self.loss_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self._graphs = {}
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------ configuration
+    def cfg(self, **over):
+        kw = dict(model=self.model, B=self.B, L=self.L, D=self.D, H=self.H, Z=self.Z, C_=self.C,
+                  use_x_prev=self.use_x_prev, Hc=self.Hc, B_global=self.B * self.world_size,
+                  seed=self.seed, **self.hyper)
+        kw.update(over)
+        return _lib.make_cfg(**kw)
+
+    def set_loss_weights(self, **kw):
+        """kl_weight / w_kl_weight annealing (utils/model_utils.py:41-49): graphs are re-captured."""
+        changed = any(self.hyper.get(k) != v for k, v in kw.items())
+        self.hyper.update(kw)
+        if changed:
+            self._graphs.clear()
+
+    # ------------------------------------------------------------------ parameters
+    def view(self, name):
+        i = self.names.index(name)
+        n = (self.rows[i] if self.rows[i] > 0 else 1) * self.cols[i]
+        t = self.params[self.offs[i]:self.offs[i] + n]
+        return t.view(self.rows[i], self.cols[i]) if self.rows[i] > 0 else t
+
+    def grad_view(self, name):
+        i = self.names.index(name)
+        n = (self.rows[i] if self.rows[i] > 0 else 1) * self.cols[i]
+        t = self.grads[self.offs[i]:self.offs[i] + n]
+        return t.view(self.rows[i], self.cols[i]) if self.rows[i] > 0 else t
+
+    def set_params(self, d):
+        for k in self.names:
+            self.view(k).copy_(torch.as_tensor(np.asarray(d[k]), dtype=torch.float32).to(self.dev))
+
+    def get_params(self):
+        return {k: self.view(k).detach().cpu().numpy().copy() for k in self.names}
+
+    def init_params(self, rng):
+        """Keras-2.0.0 default initialisers [K2-recall]: Dense glorot_uniform / zeros; LSTM kernel
+        glorot_uniform, recurrent orthogonal, unit_forget_bias; VRNN Z heads and X head
+        RandomNormal(0, 0.1) (cl_vrnn/model.py:200-207,229-233)."""
+        out = {}
+        for i, k in enumerate(self.names):
+            r, c = self.rows[i], self.cols[i]
+            layer = k.split(".")[0]
+            if r == 0:
+                v = np.zeros(c, np.float32)
+                if self.model == 0 and layer in ("encoder_h", "decoder_h"):
+                    v[self.H:2 * self.H] = 1.0
+            elif k.endswith("recurrent_kernel"):
+                a = rng.standard_normal((r, c))
+                u, _, vt = np.linalg.svd(a, full_matrices=False)
+                v = (u if u.shape == (r, c) else vt).astype(np.float32)
+            elif self.model == 0 and layer in ("Z_mean", "Z_log_var", "X_decoded_mean"):
+                v = rng.normal(0.0, 0.1, (r, c)).astype(np.float32)
+            else:
+                lim = math.sqrt(6.0 / (r + c))
+                v = rng.uniform(-lim, lim, (r, c)).astype(np.float32)
+            out[k] = v
+        self.set_params(out)
+        if self.world_size > 1:
+            torch.distributed.broadcast(self.params, src=0, group=self.pg)
+        return out
+
+    # ------------------------------------------------------------------ data staging
+    def set_resident_roll(self, roll_u8):
+        """Keep a whole split on the device: uint8 [n_frames, D]; batches are then just window
+        offsets (utils.pianoroll.DeviceRolls)."""
+        self.roll = torch.as_tensor(roll_u8, dtype=torch.uint8).to(self.dev).contiguous().view(-1)
+
+    def stage_windows(self, win_u8, labels_i32, non_blocking=True):
+        """H2D of one batch given as materialised windows [B, W, D] uint8 + int32 labels."""
+        self.roll = self.win_buf
+        self.win_buf.copy_(win_u8.reshape(-1), non_blocking=non_blocking)
+        self.labels.copy_(labels_i32, non_blocking=non_blocking)
+
+    def stage_offsets(self, off_i32, labels_i32, non_blocking=True):
+        self.win_off.copy_(off_i32, non_blocking=non_blocking)
+        self.labels.copy_(labels_i32, non_blocking=non_blocking)
+
+    # ------------------------------------------------------------------ one step
+    def _launch_step(self, train, gen_noise):
+        cfg = self.cfg(gen_noise=int(gen_noise), do_backward=int(train))
+        check(lib().clv_train_step(C.byref(cfg), ptr(self.params), ptr(self.grads), ptr(self.loss_acc),
+                                   ptr(self.roll), ptr(self.win_off), ptr(self.labels),
+                                   ptr(self.eps_w), ptr(self.eps_z), ptr(self.rng_ctr),
+                                   ptr(self.workspace), self.workspace.numel() * 4, _stream()),
+              "clv_train_step")
+        if self.world_size > 1:
+            buf = self.gradbuf if train else self.loss_acc
+            torch.distributed.all_reduce(buf, group=self.pg)
+        if train:
+            check(lib().clv_adamwn_step(C.byref(cfg), ptr(self.params), ptr(self.grads),
+                                        ptr(self.opt_state), self.lr, self.b1, self.b2, self.eps, 1.0,
+                                        int(self.optimizer == "adam-wn"), _stream()), "clv_adamwn_step")
+
+    def run(self, train=True, gen_noise=True):
+        """Launch one step on the current stream using the staged batch.  With use_graph the launch
+        sequence (fwd+bwd kernels, NCCL all-reduce, Adam-WN) is captured once per
+        (train, gen_noise, roll buffer) and replayed."""
+        if not self.use_graph:
+            self._launch_step(train, gen_noise)
+            return
+        key = (bool(train), bool(gen_noise), self.roll.data_ptr())
+        g = self._graphs.get(key)
+        if g is None:
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    self._launch_step(train, gen_noise)
+            torch.cuda.current_stream().wait_stream(s)
+            self._graphs[key] = g
+            # capture does not execute: fall through to replay
+        g.replay()
+
+    def read_losses(self):
+        """D2H of the 5 scalars (already global means) -> dict incl. Keras' weighted total."""
+        self.loss_host.copy_(self.loss_acc, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        v = self.loss_host.tolist()
+        d = dict(zip(LOSS_NAMES, v[:5]))
+        d["loss"] = (d["vae"] + self.hyper["w_kl_weight"] * d["w_kl"]
+                     + self.hyper["class_weight"] * d["w_rec"] + self.hyper["kl_weight"] * d["z_kl"])
+        return d
+
+    def ws_view(self, name, shape):
+        off = lib().clv_workspace_offset(C.byref(self.cfg()), name.encode())
+        if off < 0:
+            raise KeyError(name)
+        n = int(np.prod(shape))
+        return self.workspace[off:off + n].view(*shape)
+
+    @property
+    def iterations(self):
+        return int(self.opt_state[-2:-1].view(torch.int32).item())

@@ -1,0 +1,205 @@
+/*
+ * clv_b200.h -- C-ABI of the B200-native CL-VAE / CL-VRNN hot path (libclv_b200.so).
+ *
+ * The reference (mobeets/classifying-vae-lstm) has NO plugin / FFI interface: its hot path is the
+ * Keras graph built by get_model (code/cl_vrnn/model.py:164-267, code/cl_vae/model.py:130-224),
+ * executed by model.fit / model.predict inside TensorFlow, the optimizer update of
+ * code/utils/weightnorm.py:75-178 and the Python sampling loops generate_sample
+ * (code/cl_vrnn/model.py:9-60, code/cl_vae/model.py:9-42).  This header is the seam a maintainer
+ * binds instead (ctypes stub in INTEGRATION.md); each entry point names the reference lines it
+ * replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *     the library never allocates or frees device memory, has no globals and never synchronises;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered (graph-capturable);
+ *   - return value: 0 = CLV_OK, negative = CLV_E_*; clv_error_string() names it;
+ *   - matrices are row-major fp32 in Keras [in,out] layout; piano-rolls are uint8 {0,1}
+ *     [n_frames, D] with per-sequence first-frame offsets (int32) -- windows are gathered, never
+ *     materialised;
+ *   - there is no CPU fallback anywhere: without a CUDA device every compute call fails.
+ */
+#ifndef CLV_B200_H
+#define CLV_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLV_OK 0
+#define CLV_E_INVALID (-1)      /* bad argument (null pointer, size out of range)            */
+#define CLV_E_UNSUPPORTED (-2)  /* shape outside what the kernels are built for              */
+#define CLV_E_CUDA (-3)         /* a CUDA runtime call / launch failed (see cudaGetLastError) */
+#define CLV_E_WORKSPACE (-4)    /* workspace too small                                       */
+
+int clv_version(void);
+const char* clv_error_string(int code);
+
+/* ---------------------------------------------------------------- model description ------- */
+/* Mirrors the arguments of get_model (cl_vrnn/model.py:164; cl_vae/model.py:130-134). */
+typedef struct clv_cfg {
+  int32_t model;        /* 0 = CL-VRNN, 1 = CL-VAE                                            */
+  int32_t B;            /* sequences (VRNN) / frames (VAE) in THIS call (local batch)         */
+  int32_t B_global;     /* batch the means are taken over (== B on one GPU; sum over ranks)    */
+  int32_t L;            /* seq_length (VRNN); 1 for VAE                                       */
+  int32_t D;            /* original_dim (88)                                                  */
+  int32_t H;            /* intermediate_dim: LSTM units (VRNN) / latent_dim_0 (VAE)           */
+  int32_t Hc;           /* VAE only: class_dim_0 (intermediate_class_dim)                     */
+  int32_t Z;            /* latent_dim                                                         */
+  int32_t C;            /* n_classes                                                          */
+  int32_t use_x_prev;   /* --use_x_prev                                                       */
+  float class_weight, kl_weight, w_kl_weight, w_log_var_prior;
+  int32_t gen_noise;    /* 1: draw eps_w/eps_z in-kernel (Philox) ; 0: read the eps buffers   */
+  int32_t do_backward;  /* 0: forward + losses only (validation pass)                         */
+  int32_t accumulate;   /* 1: add into grads/losses (micro-batching) instead of zeroing first */
+  int32_t gemm_algo;    /* 0: exact fp32 SIMT GEMMs ; 1: tcgen05 tensor-core GEMMs where built */
+  uint64_t seed;        /* Philox key for gen_noise (make it rank-dependent)                  */
+} clv_cfg;
+
+/* Flat parameter buffer layout = Keras weighted-layer order, so RUN.h5 I/O is one memcpy per
+ * tensor (cl_vrnn: hW, Wargs, encoder_h{kernel,recurrent_kernel,bias}, Z_mean, Z_log_var,
+ * decoder_h{..}, X_decoded_mean -- 16 tensors; cl_vae: h_w, w_mean, w_log_var, h, z_mean,
+ * z_log_var, decoder_h, x_decoded_mean -- 16 tensors).  offs/rows/cols have 16 entries; a bias
+ * has rows == 0.  Returns the parameter count P (or a negative error). */
+#define CLV_N_TENSORS 16
+int64_t clv_param_layout(const clv_cfg* cfg, int64_t* offs, int32_t* rows, int32_t* cols);
+
+/* ---------------------------------------------------------------- K1: GEMM ---------------- */
+/* C[M,N] = act( (accumulate? C : 0) + op(A)[M,K] @ op(B)[K,N] + bias[N] + rowadd[m/ra_grp, N] ) * mask
+ * Replaces every Dense / TimeDistributed(Dense) / LSTM input projection MatMul and, through the
+ * transposed forms, their TF-autodiff dgrad / wgrad (cl_vrnn/model.py:174-175,196-209,225-234;
+ * cl_vae/model.py:141-143,162-167,182-186).  A may be fp32 or a uint8 piano-roll gathered by
+ * per-sequence frame offsets. */
+typedef struct clv_gemm_args {
+  int32_t M, N, K;
+  const void* A; int64_t lda;   /* A(m,k): a_kmajor ? A[row(m)*lda + k] : A[row(k)*lda + m]   */
+  int32_t a_u8;                 /* A elements are uint8                                        */
+  int32_t a_kmajor;             /* 1: rows indexed by m (NN / NT); 0: rows indexed by k (TN)    */
+  const int32_t* a_off;         /* optional gather: row(r) = a_off[r / a_grp] + a_shift + r % a_grp */
+  int32_t a_grp, a_shift;
+  int32_t a_row_delta, a_skip_grp; /* TN only: use row r + delta; rows with r % skip_grp == 0 are zero */
+  const float* Bm; int64_t ldb; /* B(k,n): b_nmajor ? B[k*ldb + n] : B[n*ldb + k]              */
+  int32_t b_nmajor;
+  float* C; int64_t ldc;
+  const float* bias;            /* [N] or null                                                 */
+  const float* rowadd; int64_t ldra; int32_t ra_grp; /* [M/ra_grp, N] or null                  */
+  const float* relu_mask; int64_t ldmask; /* multiply by (mask[m,n] > 0) (ReLU backward) or null */
+  int32_t relu;                 /* apply max(.,0)                                              */
+  int32_t accumulate;           /* C += ...                                                    */
+  int32_t split_k;              /* >1: split the K range over grid.z, atomicAdd into C (C must
+                                   already hold the value to add to; no bias/act allowed)       */
+} clv_gemm_args;
+int clv_gemm(const clv_gemm_args* args, void* stream);
+/* out[N] (+)= sum_m A[m,N]  (bias gradients) */
+int clv_colsum(const float* A, int64_t lda, int32_t M, int32_t N, float* out, int32_t accumulate,
+               void* stream);
+
+/* ---------------------------------------------------------------- K2: logistic-normal ----- */
+/* sampling_w + W2 + w_kl_loss + w_rec_loss + accuracy (cl_vrnn/model.py:183-191,244-255,264;
+ * cl_vae/model.py:146-157,198-208).  Wargs[B,2(C-1)] = [W_mean | W_log_var] (ld = ldwa; the VAE
+ * keeps the two heads in one buffer too), eps_w[B,C-1], labels[B] (argmax of the one-hot key).
+ * Writes W[B,C]; adds scale_b * sum_b {w_kl, w_rec, correct} into loss_acc[1], [2], [4]. */
+int clv_logitnormal_fwd(const float* Wargs, int64_t ldwa, float* eps_w, const int32_t* labels,
+                        float* W, float* loss_acc, int32_t B, int32_t C, float w_log_var_prior,
+                        float scale_b, int32_t gen_noise, uint64_t seed, const uint64_t* ctr,
+                        void* stream);
+/* dWargs[B,2(C-1)] from dW_ext[B,C] (gradient reaching W from its consumers) plus the w_rec and
+ * w_kl terms; cw_over_B = class_weight/B_global, wkl_over_B = w_kl_weight/B_global. */
+int clv_logitnormal_bwd(const float* Wargs, int64_t ldwa, const float* eps_w, const int32_t* labels,
+                        const float* W, const float* dW_ext, float* dWargs, int32_t B, int32_t C,
+                        float w_log_var_prior, float cw_over_B, float wkl_over_B, void* stream);
+
+/* ---------------------------------------------------------------- K2b: Gaussian heads ----- */
+/* Z_mean / Z_log_var Dense heads + sampling + kl_loss in one pass over h (cl_vrnn/model.py:200-216,
+ * 236-239; cl_vae/model.py:165-174,193-196).  h[R,H]; Km,Kv[H,Z]; bm,bv[Z]; eps[R,Z].
+ * Writes Zargs[R,2Z] = [mu | log_var], Zs[R,Z]; adds scale * sum_r kl into loss_acc[3]. */
+int clv_gauss_heads_fwd(const float* h, const float* Km, const float* bm, const float* Kv,
+                        const float* bv, float* eps, float* Zargs, float* Zs, float* loss_acc,
+                        int64_t R, int32_t H, int32_t Z, float scale, int32_t gen_noise,
+                        uint64_t seed, const uint64_t* ctr, void* stream);
+/* Backward: dZ[R,Z] -> dh[R,H] (overwritten; multiplied by [h>0] when relu_input, the CL-VAE case
+ * where h is a ReLU output) and atomically accumulated dKm,dbm,dKv,dbv.
+ * klw_scale = kl_weight / (B_global*L). */
+int clv_gauss_heads_bwd(const float* h, const float* Km, const float* Kv, const float* eps,
+                        const float* Zargs, const float* dZ, float* dh, float* dKm, float* dbm,
+                        float* dKv, float* dbv, int64_t R, int32_t H, int32_t Z, float klw_scale,
+                        int32_t relu_input, void* stream);
+
+/* ---------------------------------------------------------------- K3: persistent LSTM ----- */
+/* Keras-2.0.0 LSTM recurrence (cl_vrnn/model.py:196-199,225-228): hard-sigmoid gates i,f,o, tanh
+ * candidate, gate order i,f,c,o.  `gates` holds the hoisted input projection x@kernel+bias
+ * [B,L,4H] on entry and the ACTIVATED gates on exit (the stash for BPTT).  U = recurrent_kernel
+ * [H,4H] stays in registers for all L steps.  h0/c0 may be null (zeros). */
+int clv_lstm_fwd(float* gates, const float* U, float* h, float* c, const float* h0,
+                 const float* c0, int32_t B, int32_t L, int32_t H, void* stream);
+/* BPTT: dh_out[B,L,H] is dLoss/dh_t from the layers above.  `gates` holds the activated gates on
+ * entry and dLoss/d(pre-activation) [B,L,4H] on exit; dAsum[B,4H] = its sum over t. */
+int clv_lstm_bwd(float* gates, const float* U, const float* h, const float* c, const float* dh_out,
+                 float* dAsum, int32_t B, int32_t L, int32_t H, void* stream);
+
+/* ---------------------------------------------------------------- K4: Bernoulli loss ------ */
+/* vae_loss = 88*mean_k Keras-BCE with clip->logit semantics, fused with its backward
+ * (cl_vrnn/model.py:241-242; cl_vae/model.py:190-191).  logits[R,D] are overwritten with
+ * dLoss/dlogits = scale*(p-x)*[eps<=p<=1-eps] when do_backward; x is row (x_off[r/x_grp] +
+ * x_shift + r%x_grp) of the uint8 roll.  Adds scale * sum_r loss_r into loss_acc[0]. */
+int clv_bernoulli_ce_fwd_bwd(float* logits, const uint8_t* roll, const int32_t* x_off,
+                             int32_t x_grp, int32_t x_shift, float* loss_acc, int64_t R, int32_t D,
+                             float scale, int32_t do_backward, void* stream);
+
+/* ---------------------------------------------------------------- K6: Adam + weight-norm -- */
+/* AdamWithWeightnorm.get_updates (utils/weightnorm.py:75-143,146-178) on the flat buffers.
+ * state = [ m (P) | v (P) | V_scaler (ncols) | m_g (ncols) | v_g (ncols) | iterations (1) ], ncols =
+ * total number of matrix columns; clv_adamwn_state_floats gives its size, clv_adamwn_init fills
+ * V_scaler with ones and the rest with zeros.  grad_scale multiplies the gradient (1/N after a
+ * sum-allreduce is already folded into B_global, so normally 1). */
+int64_t clv_adamwn_state_floats(const clv_cfg* cfg);
+int clv_adamwn_init(const clv_cfg* cfg, float* state, void* stream);
+int clv_adamwn_step(const clv_cfg* cfg, float* params, const float* grads, float* state, double lr,
+                    double beta_1, double beta_2, double epsilon, double grad_scale, int32_t weightnorm,
+                    void* stream);
+
+/* ---------------------------------------------------------------- fused training step ----- */
+/* zero loss_acc[8] (zero_losses) and advance the device RNG call counter (bump). */
+int clv_step_begin(float* loss_acc, uint64_t* rng_ctr, int32_t zero_losses, int32_t bump,
+                   void* stream);
+/* One train (or validation) step of model.fit's train_function (cl_vrnn/train.py:66-71):
+ * forward, the four losses + accuracy, backward into grads[P].  loss_acc[8] =
+ * {vae, w_kl, w_rec, z_kl, acc, -, -, -} already divided by B_global (sum over ranks gives the
+ * Keras means).  roll / win_off describe the batch: window b starts at frame win_off[b]; with
+ * use_x_prev the window is L+1 frames (history = frames 0..L-1, current = 1..L), otherwise L.
+ * eps_w[B,C-1], eps_z[B*L,Z] are read (gen_noise=0) or written (gen_noise=1).
+ * rng_ctr: device uint64 incremented once per call when gen_noise=1. */
+int64_t clv_workspace_bytes(const clv_cfg* cfg);
+int clv_train_step(const clv_cfg* cfg, const float* params, float* grads, float* loss_acc,
+                   const uint8_t* roll, const int32_t* win_off, const int32_t* labels,
+                   float* eps_w, float* eps_z, uint64_t* rng_ctr, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+/* Named views into the workspace after a step (for parity tests): returns the float offset of
+ * e.g. "W", "Zargs", "h_e", "h_d", "logits" or -1. */
+int64_t clv_workspace_offset(const clv_cfg* cfg, const char* name);
+
+/* ---------------------------------------------------------------- K5: samplers ------------ */
+/* generate_sample (cl_vrnn/model.py:9-60) for S independent songs in one persistent kernel.
+ * seed[S,T_seed,D] uint8 teacher-forces the first T_seed steps; w[S,C] is the key simplex (given
+ * one-hot or inferred); enc_lstm = {kernel,recurrent_kernel,bias} of the z-encoder LSTM (quirk Q1:
+ * pass params' encoder_h for the documented fix, or fresh weights for reference behaviour).
+ * Noise: eps_z[S,T,Z], u[S,T,D] tapes (parity mode) or null => Philox(seed, song0+s, t).
+ * out[S,T,D] uint8 (T = T_seed + nsteps; the host slices [T_seed:]); probs[S,T,D] optional. */
+int clv_vrnn_sample(const clv_cfg* cfg, const float* params, const float* enc_kernel,
+                    const float* enc_rkernel, const float* enc_bias, const uint8_t* seed_roll,
+                    int32_t T_seed, int32_t nsteps, const float* w, const float* eps_z,
+                    const float* u, uint64_t seed, int64_t song0, int32_t S, uint8_t* out,
+                    float* probs, void* stream);
+/* generate_sample (cl_vae/model.py:9-42): x_seed[S,D]; optional use_z_prior. */
+int clv_vae_sample(const clv_cfg* cfg, const float* params, const uint8_t* x_seed, int32_t nsteps,
+                   const float* w, const float* eps_z, const float* u, uint64_t seed, int64_t song0,
+                   int32_t S, int32_t use_z_prior, uint8_t* out, float* probs, void* stream);
+/* mean over n_chunks consecutive rows: out[S,C] = mean_j in[s*n_chunks + j, C]
+ * (key inference over seed chunks, cl_vrnn/model.py:34-41). */
+int clv_chunk_mean(const float* in, float* out, int32_t S, int32_t n_chunks, int32_t C,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,269 @@
+"""Per-kernel parity through the C-ABI against the oracle (float64 CPU) on seeded inputs.
+Tolerance: 1e-4 relative (north_star: fp32 losses/gradients within 1e-4)."""
+import ctypes as C
+import numpy as np
+import pytest
+import torch
+
+import util
+from oracle import clv_oracle as O, manual_bwd as M
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _env():
+    from clvae_b200 import _lib
+    from clvae_b200._lib import lib, check, ptr
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return _lib, lib(), check, ptr, st
+
+
+def dev(a, dtype=torch.float32):
+    return torch.tensor(np.ascontiguousarray(a), dtype=dtype).cuda()
+
+
+def gemm(**kw):
+    _lib, L, check, ptr, st = _env()
+    a = _lib.clv_gemm_args(a_kmajor=1, b_nmajor=1, split_k=1)
+    keep = []
+    for k, v in kw.items():
+        if torch.is_tensor(v):
+            keep.append(v)
+            v = v.data_ptr()
+        setattr(a, k, v)
+    check(L.clv_gemm(C.byref(a), st), "clv_gemm")
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("M_,N,K", [(200, 88, 1408), (3200, 352, 88), (37, 18, 88), (1, 4, 5),
+                                    (130, 65, 17)])
+def test_gemm_nn_bias_relu_rowadd(M_, N, K):
+    rng = np.random.default_rng(M_ + N + K)
+    A = rng.normal(size=(M_, K)); B = rng.normal(size=(K, N)); bias = rng.normal(size=N)
+    grp = 1 if M_ % 8 else 8
+    ra = rng.normal(size=((M_ + grp - 1) // grp, N))
+    ref = np.maximum(A @ B + bias + np.repeat(ra, grp, axis=0)[:M_], 0)
+    Cd = torch.zeros(M_, N, device="cuda")
+    gemm(M=M_, N=N, K=K, A=dev(A), lda=K, Bm=dev(B), ldb=N, C=Cd, ldc=N, bias=dev(bias),
+         rowadd=dev(ra), ldra=N, ra_grp=grp, relu=1)
+    assert util.rel_err(Cd.cpu().numpy(), ref) < TOL
+    # accumulate on top
+    Cd2 = Cd.clone()
+    gemm(M=M_, N=N, K=K, A=dev(A), lda=K, Bm=dev(B), ldb=N, C=Cd2, ldc=N, accumulate=1)
+    assert util.rel_err(Cd2.cpu().numpy(), ref + A @ B) < TOL
+
+
+def test_gemm_u8_gather_nn_and_tn():
+    rng = np.random.default_rng(7)
+    B_, L, D, N = 9, 5, 88, 40
+    roll = (rng.random((200, D)) < 0.1).astype(np.uint8)
+    off = rng.integers(0, 200 - L - 1, B_).astype(np.int32)
+    Wt = rng.normal(size=(D, N))
+    X = np.stack([roll[o + 1:o + 1 + L] for o in off]).astype(np.float64)       # shift 1
+    Cd = torch.zeros(B_ * L, N, device="cuda")
+    gemm(M=B_ * L, N=N, K=D, A=dev(roll, torch.uint8), lda=D, a_u8=1, a_off=dev(off, torch.int32),
+         a_grp=L, a_shift=1, Bm=dev(Wt), ldb=N, C=Cd, ldc=N)
+    assert util.rel_err(Cd.cpu().numpy(), X.reshape(-1, D) @ Wt) < TOL
+    # flat rows (hW): K = L*D contiguous
+    Wf = rng.normal(size=(L * D, 16))
+    Cd = torch.zeros(B_, 16, device="cuda")
+    gemm(M=B_, N=16, K=L * D, A=dev(roll, torch.uint8), lda=D, a_u8=1, a_off=dev(off, torch.int32),
+         a_grp=1, a_shift=1, Bm=dev(Wf), ldb=16, C=Cd, ldc=16)
+    assert util.rel_err(Cd.cpu().numpy(), X.reshape(B_, -1) @ Wf) < TOL
+    # TN (wgrad) with split-K atomics into a pre-filled buffer
+    dC = rng.normal(size=(B_ * L, N))
+    base = rng.normal(size=(D, N))
+    Gd = dev(base)
+    gemm(M=D, N=N, K=B_ * L, A=dev(roll, torch.uint8), lda=D, a_u8=1, a_kmajor=0,
+         a_off=dev(off, torch.int32), a_grp=L, a_shift=1, Bm=dev(dC), ldb=N, C=Gd, ldc=N, split_k=3)
+    assert util.rel_err(Gd.cpu().numpy(), base + X.reshape(-1, D).T @ dC) < TOL
+
+
+def test_gemm_nt_mask_and_tn_shift():
+    rng = np.random.default_rng(8)
+    M_, N, K = 77, 88, 18
+    dC = rng.normal(size=(M_, K)); Wt = rng.normal(size=(N, K)); mask = rng.normal(size=(M_, N))
+    Cd = torch.zeros(M_, N, device="cuda")
+    gemm(M=M_, N=N, K=K, A=dev(dC), lda=K, Bm=dev(Wt), ldb=K, b_nmajor=0, C=Cd, ldc=N,
+         relu_mask=dev(mask), ldmask=N)
+    assert util.rel_err(Cd.cpu().numpy(), (dC @ Wt.T) * (mask > 0)) < TOL
+    # TN with the one-step shift used for dU = Hprev^T @ dA
+    B_, L, H, G = 6, 7, 88, 352
+    h = rng.normal(size=(B_, L, H)); dA = rng.normal(size=(B_, L, G))
+    hprev = np.concatenate([np.zeros((B_, 1, H)), h[:, :-1]], axis=1)
+    Gd = torch.zeros(H, G, device="cuda")
+    gemm(M=H, N=G, K=B_ * L, A=dev(h), lda=H, a_kmajor=0, a_row_delta=-1, a_skip_grp=L, Bm=dev(dA),
+         ldb=G, C=Gd, ldc=G, split_k=4)
+    assert util.rel_err(Gd.cpu().numpy(), hprev.reshape(-1, H).T @ dA.reshape(-1, G)) < TOL
+
+
+def test_colsum():
+    _lib, L, check, ptr, st = _env()
+    rng = np.random.default_rng(9)
+    A = rng.normal(size=(1000, 352))
+    out = dev(np.ones(352))
+    check(L.clv_colsum(ptr(dev(A)), 352, 1000, 352, ptr(out), 1, st))
+    torch.cuda.synchronize()
+    assert util.rel_err(out.cpu().numpy(), 1 + A.sum(0)) < TOL
+
+
+@pytest.mark.parametrize("B_,Cc", [(200, 10), (33, 2), (5, 16)])
+def test_logitnormal_fwd_bwd(B_, Cc):
+    _lib, L, check, ptr, st = _env()
+    rng = np.random.default_rng(B_)
+    C1 = Cc - 1
+    Wargs = rng.normal(0, 0.7, size=(B_, 2 * C1)); eps = rng.standard_normal((B_, C1))
+    labels = rng.integers(0, Cc, B_).astype(np.int32)
+    wt = O.one_hot(labels, Cc).numpy()
+    prior = 0.3
+    W, wkl, wrec, corr = M.logitnormal_fwd(Wargs[:, :C1], Wargs[:, C1:], eps, wt, Cc, prior)
+    Wd = torch.zeros(B_, Cc, device="cuda"); loss = torch.zeros(8, device="cuda")
+    epsd = dev(eps)
+    check(L.clv_logitnormal_fwd(ptr(dev(Wargs)), 2 * C1, ptr(epsd), ptr(dev(labels, torch.int32)),
+                                ptr(Wd), ptr(loss), B_, Cc, prior, 1.0 / B_, 0, 0, None, st))
+    torch.cuda.synchronize()
+    assert util.rel_err(Wd.cpu().numpy(), W) < TOL
+    lo = loss.cpu().numpy()
+    assert abs(lo[1] - wkl.mean()) < TOL * abs(wkl.mean())
+    assert abs(lo[2] - wrec.mean()) < TOL * abs(wrec.mean())
+    assert abs(lo[4] - corr.mean()) < 1e-6
+    dW_ext = rng.normal(size=(B_, Cc))
+    dWm, dWlv = M.logitnormal_bwd(Wargs[:, :C1], Wargs[:, C1:], eps, wt, W, dW_ext, Cc, prior,
+                                  0.7 / B_, 0.9 / B_)
+    dWa = torch.zeros(B_, 2 * C1, device="cuda")
+    check(L.clv_logitnormal_bwd(ptr(dev(Wargs)), 2 * C1, ptr(epsd), ptr(dev(labels, torch.int32)),
+                                ptr(dev(W)), ptr(dev(dW_ext)), ptr(dWa), B_, Cc, prior, 0.7 / B_,
+                                0.9 / B_, st))
+    torch.cuda.synchronize()
+    assert util.rel_err(dWa.cpu().numpy(), np.concatenate([dWm, dWlv], -1)) < TOL
+
+
+@pytest.mark.parametrize("R,Z,relu_in", [(3200, 2, 0), (100, 4, 1), (17, 16, 0)])
+def test_gauss_heads_fwd_bwd(R, Z, relu_in):
+    _lib, L, check, ptr, st = _env()
+    rng = np.random.default_rng(R + Z)
+    H = 88
+    h = rng.normal(size=(R, H))
+    if relu_in:
+        h = np.maximum(h, 0)
+    Km = rng.normal(0, 0.1, (H, Z)); Kv = rng.normal(0, 0.1, (H, Z))
+    bm = rng.normal(0, 0.1, Z); bv = rng.normal(0, 0.1, Z); eps = rng.standard_normal((R, Z))
+    mu = h @ Km + bm; lv = h @ Kv + bv
+    Zs = mu + np.exp(lv / 2) * eps
+    kl = -0.5 * (1 + lv - mu ** 2 - np.exp(lv)).sum(-1)
+    Za = torch.zeros(R, 2 * Z, device="cuda"); Zd = torch.zeros(R, Z, device="cuda")
+    loss = torch.zeros(8, device="cuda"); epsd = dev(eps); hd = dev(h); Kmd = dev(Km); Kvd = dev(Kv)
+    check(L.clv_gauss_heads_fwd(ptr(hd), ptr(Kmd), ptr(dev(bm)), ptr(Kvd), ptr(dev(bv)), ptr(epsd),
+                                ptr(Za), ptr(Zd), ptr(loss), R, H, Z, 1.0 / R, 0, 0, None, st))
+    torch.cuda.synchronize()
+    assert util.rel_err(Za.cpu().numpy(), np.concatenate([mu, lv], -1)) < TOL
+    assert util.rel_err(Zd.cpu().numpy(), Zs) < TOL
+    assert abs(loss.cpu().numpy()[3] - kl.mean()) < TOL * abs(kl.mean())
+    dZ = rng.normal(size=(R, Z)); klw = 0.3 / R
+    dmu = dZ + klw * mu
+    dlv = dZ * eps * 0.5 * np.exp(lv / 2) + klw * 0.5 * (np.exp(lv) - 1)
+    dh = dmu @ Km.T + dlv @ Kv.T
+    if relu_in:
+        dh = dh * (h > 0)
+    dhd = torch.zeros(R, H, device="cuda")
+    gKm = torch.zeros(H, Z, device="cuda"); gKv = torch.zeros(H, Z, device="cuda")
+    gbm = torch.zeros(Z, device="cuda"); gbv = torch.zeros(Z, device="cuda")
+    check(L.clv_gauss_heads_bwd(ptr(hd), ptr(Kmd), ptr(Kvd), ptr(epsd), ptr(Za), ptr(dev(dZ)), ptr(dhd),
+                                ptr(gKm), ptr(gbm), ptr(gKv), ptr(gbv), R, H, Z, klw, relu_in, st))
+    torch.cuda.synchronize()
+    assert util.rel_err(dhd.cpu().numpy(), dh) < TOL
+    assert util.rel_err(gKm.cpu().numpy(), h.T @ dmu) < TOL
+    assert util.rel_err(gKv.cpu().numpy(), h.T @ dlv) < TOL
+    assert util.rel_err(gbm.cpu().numpy(), dmu.sum(0)) < TOL
+    assert util.rel_err(gbv.cpu().numpy(), dlv.sum(0)) < TOL
+
+
+@pytest.mark.parametrize("B_,L", [(200, 16), (3, 5), (1, 1), (19, 33), (1200, 4)])
+def test_lstm_fwd_bwd(B_, L):
+    _lib, Lb, check, ptr, st = _env()
+    rng = np.random.default_rng(B_ * 100 + L)
+    H, G = 88, 352
+    xproj = rng.normal(0, 1.2, size=(B_, L, G)); U = rng.normal(0, 0.15, size=(H, G))
+    hs, cs, a_all = M.lstm_fwd(xproj, U)
+    gates = dev(xproj); Ud = dev(U)
+    hd = torch.zeros(B_, L, H, device="cuda"); cd = torch.zeros(B_, L, H, device="cuda")
+    check(Lb.clv_lstm_fwd(ptr(gates), ptr(Ud), ptr(hd), ptr(cd), None, None, B_, L, H, st))
+    torch.cuda.synchronize()
+    assert util.rel_err(hd.cpu().numpy(), hs) < TOL
+    assert util.rel_err(cd.cpu().numpy(), cs) < TOL
+    g_ref = np.concatenate([M._hard_sigmoid(a_all[..., :2 * H]), np.tanh(a_all[..., 2 * H:3 * H]),
+                            M._hard_sigmoid(a_all[..., 3 * H:])], -1)
+    assert util.rel_err(gates.cpu().numpy(), g_ref) < TOL
+    dh_out = rng.normal(size=(B_, L, H))
+    dA = M.lstm_bwd(dh_out, hs, cs, a_all, U)
+    dAsum = torch.zeros(B_, G, device="cuda")
+    check(Lb.clv_lstm_bwd(ptr(gates), ptr(Ud), ptr(hd), ptr(cd), ptr(dev(dh_out)), ptr(dAsum), B_, L,
+                          H, st))
+    torch.cuda.synchronize()
+    assert util.rel_err(gates.cpu().numpy(), dA) < TOL
+    assert util.rel_err(dAsum.cpu().numpy(), dA.sum(1)) < TOL
+
+
+def test_lstm_saturated_gates_have_zero_gradient():
+    _lib, Lb, check, ptr, st = _env()
+    H, G, B_, L = 88, 352, 2, 3
+    xproj = np.zeros((B_, L, G)); xproj[..., :H] = 9.0; xproj[..., 3 * H:] = -9.0   # i clipped to 1, o to 0
+    gates = dev(xproj); Ud = dev(np.zeros((H, G)))
+    hd = torch.zeros(B_, L, H, device="cuda"); cd = torch.zeros(B_, L, H, device="cuda")
+    check(Lb.clv_lstm_fwd(ptr(gates), ptr(Ud), ptr(hd), ptr(cd), None, None, B_, L, H, st))
+    dAsum = torch.zeros(B_, G, device="cuda")
+    check(Lb.clv_lstm_bwd(ptr(gates), ptr(Ud), ptr(hd), ptr(cd), ptr(dev(np.ones((B_, L, H)))),
+                          ptr(dAsum), B_, L, H, st))
+    torch.cuda.synchronize()
+    g = gates.cpu().numpy()
+    assert np.all(g[..., :H] == 0) and np.all(g[..., 3 * H:] == 0)
+    assert np.all(hd.cpu().numpy() == 0)
+
+
+@pytest.mark.parametrize("R", [3200, 7])
+def test_bernoulli_ce(R):
+    _lib, L, check, ptr, st = _env()
+    rng = np.random.default_rng(R)
+    D = 88
+    logits = rng.normal(0, 3, size=(R, D)); logits[0, :4] = [30, -30, 17.5, -17.5]   # clip region
+    roll = (rng.random((R + 5, D)) < 0.1).astype(np.uint8)
+    off = np.arange(R, dtype=np.int32) + 2
+    x = roll[off + 1].astype(np.float64)
+    loss_ref, dl_ref = M.bernoulli_fwd_bwd(logits, x, 1.0 / R)
+    lg = dev(logits); loss = torch.zeros(8, device="cuda")
+    check(L.clv_bernoulli_ce_fwd_bwd(ptr(lg), ptr(dev(roll, torch.uint8)), ptr(dev(off, torch.int32)),
+                                     1, 1, ptr(loss), R, D, 1.0 / R, 1, st))
+    torch.cuda.synchronize()
+    assert abs(loss.cpu().numpy()[0] - loss_ref.mean()) < TOL * loss_ref.mean()
+    assert util.rel_err(lg.cpu().numpy(), dl_ref) < TOL
+    assert lg.cpu().numpy()[0, 0] == 0.0 and lg.cpu().numpy()[0, 1] == 0.0
+
+
+@pytest.mark.parametrize("weightnorm", [1, 0])
+def test_adamwn_matches_oracle_trajectory(weightnorm):
+    from clvae_b200.engine import Engine
+    rng = np.random.default_rng(11)
+    e = Engine("vrnn", 4, L=3, D=88, H=88, Z=2, n_classes=5, use_x_prev=True,
+               optimizer="adam-wn" if weightnorm else "adam", use_graph=False)
+    p0 = e.init_params(rng)
+    params = {k: torch.tensor(v, dtype=torch.float64) for k, v in p0.items()}
+    if weightnorm:
+        opt = O.AdamWN(params)
+    else:
+        opt = O.AdamWN({k: v.reshape(-1) for k, v in params.items()})
+        params = {k: v.reshape(-1) for k, v in params.items()}
+    _lib, L, check, ptr, st = _env()
+    for step in range(4):
+        g = {k: rng.normal(0, 10.0 ** rng.integers(-3, 1), size=tuple(v.shape)) for k, v in params.items()}
+        for k in e.names:
+            e.grad_view(k).copy_(dev(g[k]).view_as(e.grad_view(k)))
+        cfg = e.cfg()
+        check(L.clv_adamwn_step(C.byref(cfg), ptr(e.params), ptr(e.grads), ptr(e.opt_state), 1e-3, 0.9,
+                                0.999, 1e-8, 1.0, weightnorm, st))
+        torch.cuda.synchronize()
+        params = opt.step(params, {k: torch.tensor(v) for k, v in g.items()})
+        got = e.get_params()
+        for k in e.names:
+            assert util.rel_err(got[k].reshape(-1), params[k].numpy().reshape(-1)) < TOL, (step, k)
+    assert e.iterations == 4

@@ -1,0 +1,110 @@
+"""Whole training step (fwd + 4 losses + accuracy + bwd + Adam-WN) through clv_train_step against the
+oracle on identical weights, inputs and injected noise.  1e-4 relative (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+import util
+from oracle import clv_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+KW = dict(class_weight=0.7, kl_weight=0.3, w_kl_weight=0.9, w_log_var_prior=0.2)
+
+
+def check_step(e, out, g):
+    e.run(train=True, gen_noise=False)
+    lo = e.read_losses()
+    for k in ("vae", "w_kl", "w_rec", "z_kl", "loss"):
+        assert abs(lo[k] - float(out[k])) <= TOL * abs(float(out[k])), (k, lo[k], float(out[k]))
+    assert abs(lo["acc"] - float(out["acc"])) < 1e-6
+    for k in e.names:
+        got = e.grad_view(k).cpu().numpy()
+        assert util.rel_err(got, g[k].numpy().reshape(got.shape)) < TOL, k
+
+
+@pytest.mark.parametrize("B,L,C,Z,xp", [(200, 16, 10, 2, True), (200, 16, 10, 2, False),
+                                        (7, 3, 2, 4, True), (1, 1, 3, 1, True), (33, 40, 12, 2, True)])
+def test_vrnn_step_matches_oracle(B, L, C, Z, xp):
+    case = util.make_vrnn_case(B * 7 + L, B, L, C=C, Z=Z, use_x_prev=xp)
+    out, g = util.oracle_vrnn(case, **KW)
+    e = util.engine_for(case, "vrnn", use_graph=False, **KW)
+    check_step(e, out, g)
+    # intermediates the sampler sub-models expose
+    assert util.rel_err(e.ws_view("W", (B, C)).cpu().numpy(), out["W"].numpy()) < TOL
+    assert util.rel_err(e.ws_view("h_e", (B, L, 88)).cpu().numpy(), out["h_e"].numpy()) < TOL
+    assert util.rel_err(e.ws_view("h_d", (B, L, 88)).cpu().numpy(), out["h_d"].numpy()) < TOL
+
+
+@pytest.mark.parametrize("B,C,Z,xp", [(100, 2, 4, True), (100, 10, 2, False), (5, 3, 16, True)])
+def test_vae_step_matches_oracle(B, C, Z, xp):
+    case = util.make_vae_case(B + C, B, C=C, Z=Z, use_x_prev=xp)
+    out, g = util.oracle_vae(case, **KW)
+    e = util.engine_for(case, "vae", use_graph=False, **KW)
+    check_step(e, out, g)
+
+
+def test_vrnn_training_trajectory_and_graph_replay():
+    """5 optimizer steps (Adam-WN) on a fixed batch: eager launches, CUDA-graph replay and the oracle
+    stay together; validation pass leaves parameters untouched."""
+    case = util.make_vrnn_case(99, 24, 6, C=4, Z=2, use_x_prev=True)
+    engines = [util.engine_for(case, "vrnn", use_graph=ug) for ug in (False, True)]
+    p = {k: v.clone() for k, v in case["p"].items()}
+    opt = O.AdamWN(p)
+    for step in range(5):
+        c2 = dict(case, p=p)
+        out, g = util.oracle_vrnn(c2)
+        for e in engines:
+            e.run(train=True, gen_noise=False)
+            lo = e.read_losses()
+            assert abs(lo["loss"] - float(out["loss"])) <= 2e-4 * abs(float(out["loss"])), step
+        p = opt.step(p, g)
+    for e in engines:
+        got = e.get_params()
+        for k in e.names:
+            assert util.rel_err(got[k], p[k].numpy()) < 5e-4, k
+        before = e.params.clone()
+        e.run(train=False, gen_noise=False)
+        assert torch.equal(before, e.params)
+    a, b = engines[0].get_params(), engines[1].get_params()
+    for k in a:
+        assert util.rel_err(a[k], b[k]) < 1e-5
+
+
+def test_in_kernel_noise_is_standard_normal_and_fresh():
+    case = util.make_vrnn_case(5, 256, 8, C=10, Z=2)
+    e = util.engine_for(case, "vrnn", use_graph=True)
+    e.run(train=False, gen_noise=True)
+    z1 = e.eps_z.cpu().numpy().copy(); w1 = e.eps_w.cpu().numpy().copy()
+    e.run(train=False, gen_noise=True)
+    z2 = e.eps_z.cpu().numpy()
+    assert abs(z1.mean()) < 0.1 and abs(z1.std() - 1) < 0.1 and abs(w1.std() - 1) < 0.1
+    assert not np.array_equal(z1, z2)
+    lo = e.read_losses()
+    assert np.isfinite(lo["loss"])
+
+
+def test_microbatch_accumulation_equals_full_batch():
+    """accumulate=1 adds a second micro-batch into grads/losses (how the host fits the top of the
+    sweep into HBM); B_global makes the means global."""
+    import ctypes as C
+    from clvae_b200._lib import lib, check, ptr
+    case = util.make_vrnn_case(3, 16, 5, C=4, Z=2)
+    out, g = util.oracle_vrnn(case)
+    full = util.engine_for(case, "vrnn", use_graph=False)
+    full.run(train=True, gen_noise=False)
+    half = {}
+    for i, sl in enumerate((slice(0, 8), slice(8, 16))):
+        c = dict(case, B=8, win=case["win"][sl], labels=case["labels"][sl], eps_w=case["eps_w"][sl],
+                 eps_z=case["eps_z"][sl])
+        half[i] = util.engine_for(c, "vrnn", use_graph=False)
+    e0, e1 = half[0], half[1]
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for i, e in enumerate((e0, e1)):
+        cfg = e.cfg(B_global=16, gen_noise=0, do_backward=1, accumulate=i)
+        check(lib().clv_train_step(C.byref(cfg), ptr(e.params), ptr(e0.grads), ptr(e0.loss_acc),
+                                   ptr(e.roll), ptr(e.win_off), ptr(e.labels), ptr(e.eps_w),
+                                   ptr(e.eps_z), None, ptr(e.workspace), e.workspace.numel() * 4, st))
+    torch.cuda.synchronize()
+    assert util.rel_err(e0.grads.cpu().numpy(), full.grads.cpu().numpy()) < 1e-5
+    assert util.rel_err(e0.loss_acc.cpu().numpy()[:5], full.loss_acc.cpu().numpy()[:5]) < 1e-5
