@@ -23,7 +23,7 @@ class clv_cfg(C.Structure):
                 ("class_weight", C.c_float), ("kl_weight", C.c_float), ("w_kl_weight", C.c_float),
                 ("w_log_var_prior", C.c_float),
                 ("gen_noise", C.c_int32), ("do_backward", C.c_int32), ("accumulate", C.c_int32),
-                ("gemm_algo", C.c_int32), ("seed", C.c_uint64)]
+                ("gemm_algo", C.c_int32), ("x_shift", C.c_int32), ("seed", C.c_uint64)]
 
 
 class clv_gemm_args(C.Structure):
@@ -45,6 +45,7 @@ _CFG = C.POINTER(clv_cfg)
 # name -> (restype, argtypes); every symbol declared in include/clv_b200.h
 PROTOTYPES = {
     "clv_version": (C.c_int, []),
+    "clv_launch_count": (_I64, []),
     "clv_error_string": (C.c_char_p, [C.c_int]),
     "clv_param_layout": (_I64, [_CFG, C.POINTER(_I64), C.POINTER(_I32), C.POINTER(_I32)]),
     "clv_gemm": (C.c_int, [C.POINTER(clv_gemm_args), _P]),
@@ -102,12 +103,12 @@ def ptr(t):
 
 def make_cfg(model, B, L, D, H, Z, C_, use_x_prev, Hc=0, B_global=None, class_weight=1.0,
              kl_weight=1.0, w_kl_weight=1.0, w_log_var_prior=0.0, gen_noise=0, do_backward=1,
-             accumulate=0, gemm_algo=0, seed=0):
+             accumulate=0, gemm_algo=0, seed=0, x_shift=0):
     return clv_cfg(model=model, B=B, B_global=B if B_global is None else B_global, L=L, D=D, H=H,
                    Hc=Hc, Z=Z, C=C_, use_x_prev=int(bool(use_x_prev)), class_weight=class_weight,
                    kl_weight=kl_weight, w_kl_weight=w_kl_weight, w_log_var_prior=w_log_var_prior,
                    gen_noise=gen_noise, do_backward=do_backward, accumulate=accumulate,
-                   gemm_algo=gemm_algo, seed=seed)
+                   gemm_algo=gemm_algo, x_shift=x_shift, seed=seed)
 
 
 def param_layout(cfg):

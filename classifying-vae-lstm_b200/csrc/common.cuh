@@ -6,10 +6,15 @@
 
 #define CLV_EPS 1e-7f  // keras _EPSILON [K2-recall]
 
+// diagnostic only: number of kernels this library has launched in this process (bench.py's
+// gpu_launches); not used by any compute path.
+extern unsigned long long g_clv_launches;
+
 #define CLV_CHECK_LAUNCH()                                  \
   do {                                                      \
     cudaError_t e__ = cudaGetLastError();                   \
     if (e__ != cudaSuccess) return CLV_E_CUDA;              \
+    ++g_clv_launches;                                       \
   } while (0)
 
 #define CLV_CUDA(call)                                      \

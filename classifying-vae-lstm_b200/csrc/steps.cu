@@ -130,7 +130,8 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   int64_t po[CLV_N_TENSORS]; int32_t pr[CLV_N_TENSORS], pc[CLV_N_TENSORS];
   clv_param_layout(c, po, pr, pc);
   const int B = c->B, L = c->L, D = c->D, H = c->H, Z = c->Z, C = c->C, C1 = C - 1, G = 4 * H;
-  const int BL = B * L, xo = c->use_x_prev ? D : 0, sx = c->use_x_prev ? 1 : 0;
+  const int BL = B * L, xo = c->use_x_prev ? D : 0;
+  const int sx = c->x_shift > 0 ? c->x_shift : (c->use_x_prev ? 1 : 0);
   const float sb = 1.0f / (float)c->B_global, sbl = 1.0f / ((float)c->B_global * (float)L);
   const Ws w = carve(c);
 #define WSP(name) (ws + w.find(name))
@@ -222,7 +223,8 @@ int vae_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uin
   int64_t po[CLV_N_TENSORS]; int32_t pr[CLV_N_TENSORS], pc[CLV_N_TENSORS];
   clv_param_layout(c, po, pr, pc);
   const int B = c->B, D = c->D, H = c->H, Hc = c->Hc, Z = c->Z, C = c->C, C1 = C - 1;
-  const int xo = c->use_x_prev ? D : 0, sx = c->use_x_prev ? 1 : 0;
+  const int xo = c->use_x_prev ? D : 0;
+  const int sx = c->x_shift > 0 ? c->x_shift : (c->use_x_prev ? 1 : 0);
   const float sb = 1.0f / (float)c->B_global;
   const Ws w = carve(c);
 #define WSP(name) (ws + w.find(name))
@@ -297,7 +299,9 @@ int vae_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uin
 
 }  // namespace
 
+unsigned long long g_clv_launches = 0;
 extern "C" int clv_version(void) { return 100; }
+extern "C" int64_t clv_launch_count(void) { return (int64_t)g_clv_launches; }
 
 extern "C" const char* clv_error_string(int code) {
   switch (code) {

@@ -52,6 +52,7 @@ class Engine:
         self.Hc = Hc
         self.use_x_prev = bool(use_x_prev)
         self.W = self.L + 1 if self.use_x_prev else self.L            # frames per window
+        self.x_shift = 0                                               # 0 = default placement
         self.hyper = dict(class_weight=class_weight, kl_weight=kl_weight, w_kl_weight=w_kl_weight,
                           w_log_var_prior=w_log_var_prior)
         self.optimizer, self.lr, self.b1, self.b2, self.eps = optimizer, lr, beta_1, beta_2, epsilon
@@ -85,7 +86,7 @@ class Engine:
     def cfg(self, **over):
         kw = dict(model=self.model, B=self.B, L=self.L, D=self.D, H=self.H, Z=self.Z, C_=self.C,
                   use_x_prev=self.use_x_prev, Hc=self.Hc, B_global=self.B * self.world_size,
-                  seed=self.seed, **self.hyper)
+                  seed=self.seed, x_shift=self.x_shift, **self.hyper)
         kw.update(over)
         return _lib.make_cfg(**kw)
 
@@ -95,6 +96,15 @@ class Engine:
         self.hyper.update(kw)
         if changed:
             self._graphs.clear()
+
+    def set_window(self, frames, x_shift):
+        """Window geometry: `frames` per window, `current` starts at frame x_shift (0 = default:
+        1 with use_x_prev).  Used when current/history are independent arrays ([history | current])."""
+        self.W, self.x_shift = frames, x_shift
+        self.win_off = (torch.arange(self.B, dtype=torch.int32, device=self.dev) * self.W).contiguous()
+        self.win_buf = torch.zeros(self.B * self.W * self.D, dtype=torch.uint8, device=self.dev)
+        self.roll = self.win_buf
+        self._graphs.clear()
 
     # ------------------------------------------------------------------ parameters
     def view(self, name):
@@ -180,7 +190,10 @@ class Engine:
         sequence (fwd+bwd kernels, NCCL all-reduce, Adam-WN) is captured once per
         (train, gen_noise, roll buffer) and replayed."""
         if not self.use_graph:
+            n0 = lib().clv_launch_count()
             self._launch_step(train, gen_noise)
+            if train:
+                self.launches_per_step = lib().clv_launch_count() - n0
             return
         key = (bool(train), bool(gen_noise), self.roll.data_ptr())
         g = self._graphs.get(key)
@@ -189,8 +202,11 @@ class Engine:
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 g = torch.cuda.CUDAGraph()
+                n0 = lib().clv_launch_count()
                 with torch.cuda.graph(g, stream=s):
                     self._launch_step(train, gen_noise)
+                if train:
+                    self.launches_per_step = lib().clv_launch_count() - n0
             torch.cuda.current_stream().wait_stream(s)
             self._graphs[key] = g
             # capture does not execute: fall through to replay

@@ -33,6 +33,7 @@ extern "C" {
 #define CLV_E_WORKSPACE (-4)    /* workspace too small                                       */
 
 int clv_version(void);
+int64_t clv_launch_count(void); /* diagnostic: kernels launched by this library so far */
 const char* clv_error_string(int code);
 
 /* ---------------------------------------------------------------- model description ------- */
@@ -53,6 +54,9 @@ typedef struct clv_cfg {
   int32_t do_backward;  /* 0: forward + losses only (validation pass)                         */
   int32_t accumulate;   /* 1: add into grads/losses (micro-batching) instead of zeroing first */
   int32_t gemm_algo;    /* 0: exact fp32 SIMT GEMMs ; 1: tcgen05 tensor-core GEMMs where built */
+  int32_t x_shift;      /* frame of `current` inside a window; 0 = default (1 with use_x_prev
+                           [history = frames 0..L-1, current = 1..L], else 0).  L for windows
+                           stored as [history | current] when the two inputs do not overlap     */
   uint64_t seed;        /* Philox key for gen_noise (make it rank-dependent)                  */
 } clv_cfg;
 
