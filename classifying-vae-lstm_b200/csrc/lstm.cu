@@ -110,11 +110,9 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
   const int nrows = min(R, B - b0);
 
   float Ureg[NSZ];
+  // scalar loads: U sits at an arbitrary float offset of the flat parameter buffer (not 16B-aligned)
 #pragma unroll
-  for (int i4 = 0; i4 < NSZ / 4; ++i4) {
-    const float4 u = __ldg(reinterpret_cast<const float4*>(U + (size_t)k * G + ns * NSZ) + i4);
-    Ureg[4 * i4] = u.x; Ureg[4 * i4 + 1] = u.y; Ureg[4 * i4 + 2] = u.z; Ureg[4 * i4 + 3] = u.w;
-  }
+  for (int i = 0; i < NSZ; ++i) Ureg[i] = __ldg(U + (size_t)k * G + ns * NSZ + i);
   for (int i = tid; i < RMAX * H; i += NT) {
     dhrec_s[i / H][i % H] = 0.f;
     dc_s[i / H][i % H] = 0.f;

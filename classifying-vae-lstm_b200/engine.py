@@ -75,7 +75,8 @@ class Engine:
         self.eps_z = torch.zeros(B * self.L * Z, **f32)
         self.rng_ctr = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.labels = torch.zeros(B, dtype=torch.int32, device=self.dev)
-        self.win_off = (torch.arange(B, dtype=torch.int32, device=self.dev) * self.W).contiguous()
+        self._win_off_seq = (torch.arange(B, dtype=torch.int32, device=self.dev) * self.W).contiguous()
+        self.win_off = self._win_off_seq.clone()
         self.win_buf = torch.zeros(B * self.W * D, dtype=torch.uint8, device=self.dev)
         self.roll = self.win_buf                                       # or a resident dataset roll
         self.loss_host = torch.zeros(8, dtype=torch.float32).pin_memory()
@@ -101,7 +102,8 @@ class Engine:
         """Window geometry: `frames` per window, `current` starts at frame x_shift (0 = default:
         1 with use_x_prev).  Used when current/history are independent arrays ([history | current])."""
         self.W, self.x_shift = frames, x_shift
-        self.win_off = (torch.arange(self.B, dtype=torch.int32, device=self.dev) * self.W).contiguous()
+        self._win_off_seq = (torch.arange(self.B, dtype=torch.int32, device=self.dev) * self.W).contiguous()
+        self.win_off.copy_(self._win_off_seq)
         self.win_buf = torch.zeros(self.B * self.W * self.D, dtype=torch.uint8, device=self.dev)
         self.roll = self.win_buf
         self._graphs.clear()
@@ -162,6 +164,7 @@ class Engine:
     def stage_windows(self, win_u8, labels_i32, non_blocking=True):
         """H2D of one batch given as materialised windows [B, W, D] uint8 + int32 labels."""
         self.roll = self.win_buf
+        self.win_off.copy_(self._win_off_seq)                          # window b = frames [b*W, (b+1)*W)
         self.win_buf.copy_(win_u8.reshape(-1), non_blocking=non_blocking)
         self.labels.copy_(labels_i32, non_blocking=non_blocking)
 

@@ -1,6 +1,6 @@
 """Persistent samplers vs the oracle's restatement of generate_sample on recorded noise tapes:
 bit-exact piano rolls wherever |p - u| > 1e-6 (north_star)."""
-import ctypes as C
+import ctypes as CT
 import numpy as np
 import pytest
 import torch
@@ -11,8 +11,21 @@ from oracle import clv_oracle as O
 pytestmark = pytest.mark.gpu
 
 
+_KEEP = []   # device tensors must outlive the asynchronous launches that read them
+
+
+@pytest.fixture(autouse=True)
+def _clear_keep():
+    _KEEP.clear()
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
+
+
 def dev(a, dtype=torch.float32):
-    return torch.tensor(np.ascontiguousarray(a), dtype=dtype).cuda()
+    t = torch.tensor(np.ascontiguousarray(a), dtype=dtype).cuda()
+    _KEEP.append(t)
+    return t
 
 
 @pytest.mark.parametrize("S,T_seed,nsteps,C,Z,xp", [(3, 4, 12, 10, 2, True), (17, 1, 6, 3, 4, False),
@@ -35,8 +48,8 @@ def test_vrnn_sampler_bit_exact_away_from_threshold(S, T_seed, nsteps, C, Z, xp)
     out = torch.zeros(S, T, D, dtype=torch.uint8, device="cuda")
     probs = torch.zeros(S, T, D, device="cuda")
     cfg = e.cfg()
-    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    check(lib().clv_vrnn_sample(C.byref(cfg), ptr(e.params), None, None, None,
+    st = CT.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib().clv_vrnn_sample(CT.byref(cfg), ptr(e.params), None, None, None,
                                 ptr(dev(seeds, torch.uint8)), T_seed, nsteps, ptr(dev(w)),
                                 ptr(dev(eps_z)), ptr(dev(u)), 0, 0, S, ptr(out), ptr(probs), st))
     torch.cuda.synchronize()
@@ -77,8 +90,8 @@ def test_vae_sampler_bit_exact_away_from_threshold(S, nsteps, C, Z, xp, prior):
     out = torch.zeros(S, nsteps, D, dtype=torch.uint8, device="cuda")
     probs = torch.zeros(S, nsteps, D, device="cuda")
     cfg = e.cfg()
-    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    check(lib().clv_vae_sample(C.byref(cfg), ptr(e.params), ptr(dev(seeds, torch.uint8)), nsteps,
+    st = CT.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib().clv_vae_sample(CT.byref(cfg), ptr(e.params), ptr(dev(seeds, torch.uint8)), nsteps,
                                ptr(dev(w)), ptr(dev(eps_z)), ptr(dev(u)), 0, 0, S, int(prior),
                                ptr(out), ptr(probs), st))
     torch.cuda.synchronize()
@@ -109,13 +122,13 @@ def test_sampler_philox_mode_is_deterministic_and_song_indexed():
     T = T_seed + nsteps
     seeds = dev(O.synth_rolls(rng, S, T_seed, D, 0.1), torch.uint8)
     w = dev(rng.dirichlet(np.ones(C), S))
-    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    st = CT.c_void_p(torch.cuda.current_stream().cuda_stream)
     cfg = e.cfg()
     full = torch.zeros(S, T, D, dtype=torch.uint8, device="cuda")
-    check(lib().clv_vrnn_sample(C.byref(cfg), ptr(e.params), None, None, None, ptr(seeds), T_seed, nsteps,
+    check(lib().clv_vrnn_sample(CT.byref(cfg), ptr(e.params), None, None, None, ptr(seeds), T_seed, nsteps,
                                 ptr(w), None, None, 1234, 0, S, ptr(full), None, st))
     part = torch.zeros(S - 24, T, D, dtype=torch.uint8, device="cuda")
-    check(lib().clv_vrnn_sample(C.byref(cfg), ptr(e.params), None, None, None, ptr(seeds[24:].contiguous()),
+    check(lib().clv_vrnn_sample(CT.byref(cfg), ptr(e.params), None, None, None, ptr(seeds[24:].contiguous()),
                                 T_seed, nsteps, ptr(w[24:].contiguous()), None, None, 1234, 24, S - 24,
                                 ptr(part), None, st))
     torch.cuda.synchronize()
