@@ -17,7 +17,7 @@ struct AdamPlan {
   int32_t NC;
 };
 
-constexpr int CT = 8, RL = 32, NTH = CT * RL;
+constexpr int CT = 8, RL = 64, NTH = CT * RL;
 
 __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* __restrict__ W,
                                                      const float* __restrict__ G,
@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
     // pass 1: ||V||^2 and <G, V> per column
     float svv = 0.f, sgv = 0.f;
     if (cv)
+#pragma unroll 4
       for (int r = ry; r < rows; r += RL) {
         const int64_t e = off + (int64_t)r * cols + c;
         const float V = W[e] / vs, g = G[e] * gscale;
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
     // pass 2: Adam on V; new V parked in W
     float snn = 0.f;
     if (cv)
+#pragma unroll 4
       for (int r = ry; r < rows; r += RL) {
         const int64_t e = off + (int64_t)r * cols + c;
         const float V = W[e] / vs, g = G[e] * gscale;
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
     // pass 3: W = V_scaler' * V'
     const float ns = col[2][cx];
     if (cv)
+#pragma unroll 4
       for (int r = ry; r < rows; r += RL) {
         const int64_t e = off + (int64_t)r * cols + c;
         W[e] *= ns;

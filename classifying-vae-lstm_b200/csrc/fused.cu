@@ -1,0 +1,319 @@
+// Fused kernels that take the small-M Dense stacks off the launch-latency critical path:
+//   clv_xhead_fwd_bwd : X_decoded_mean Dense + sigmoid + 88-key Bernoulli loss + dlogits + dgrad to
+//                       h_dec, one pass over h_dec with the 88x88 head kernel resident in smem
+//                       (cl_vrnn/model.py:229-234,241-242 and their TF-autodiff backward)
+//   clv_keyenc_fwd    : key encoder hW (ReLU Dense over the flattened window) + Wargs Dense +
+//                       logistic-normal sample/softmax + w_kl/w_rec/accuracy, one CTA per sequence.
+//                       The window is a sparse binary roll, so the [L*D] x [L*D, D] product is a
+//                       gather-sum of the active rows of the kernel (exact fp32, ~5% of the dense work)
+//                       (cl_vrnn/model.py:174-191,244-255,264)
+//   clv_keyenc_bwd    : logistic-normal backward + dgrad through Wargs and the ReLU of hW
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float seg16_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------ X head
+constexpr int XR = 32;         // rows per CTA
+constexpr int XT = 352;        // threads: (column/unit, row-quarter)
+constexpr int XD = 88;         // D == H == 88 specialisation
+
+__global__ void __launch_bounds__(XT, 1)
+xhead_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const float* __restrict__ bx,
+             const uint8_t* __restrict__ roll, const int32_t* __restrict__ x_off, const int x_grp,
+             const int x_shift, float* __restrict__ loss_acc, float* __restrict__ dlogits,
+             float* __restrict__ dh, const int64_t R, const float scale, const int do_backward) {
+  extern __shared__ __align__(16) float sm[];
+  float* K_s = sm;                    // [k][d]   (forward: lanes over d)
+  float* KT_s = K_s + XD * XD;        // [d][k]   (dgrad: lanes over k)
+  float* h_s = KT_s + XD * XD;        // [XR][XD] h tile, later the dlogits tile
+  __shared__ float red[32];
+  const int tid = threadIdx.x, j = tid % XD, rq = tid / XD;   // rq in 0..3 -> rows 8rq..8rq+7
+  const int64_t row0 = (int64_t)blockIdx.x * XR;
+  for (int i = tid; i < XD * XD; i += XT) {
+    const float v = __ldg(Kx + i);
+    K_s[i] = v;
+    KT_s[(i % XD) * XD + (i / XD)] = v;
+  }
+  for (int i = tid; i < XR * XD; i += XT) {
+    const int64_t r = row0 + i / XD;
+    h_s[i] = (r < R) ? __ldg(h + r * XD + (i % XD)) : 0.f;
+  }
+  __syncthreads();
+  float acc[8];
+  const float b = __ldg(bx + j);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = b;
+#pragma unroll 4
+  for (int k = 0; k < XD; ++k) {
+    const float w = K_s[k * XD + j];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(h_s[(rq * 8 + i) * XD + k], w, acc[i]);
+  }
+  __syncthreads();   // all reads of the h tile done; it becomes the dlogits tile
+  float lsum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t r = row0 + rq * 8 + i;
+    float dl = 0.f;
+    if (r < R) {
+      const int64_t g = r / x_grp;
+      const int64_t xrow = (int64_t)__ldg(x_off + g) + x_shift + (r - g * x_grp);
+      const float x = (float)__ldg(roll + xrow * XD + j);
+      const float p = sigmoid_f(acc[i]);
+      const float pc = fminf(fmaxf(p, CLV_EPS), 1.0f - CLV_EPS);
+      const float l = logf(pc / (1.0f - pc));
+      lsum += fmaxf(l, 0.f) - l * x + log1pf(expf(-fabsf(l)));
+      const bool pass = (p >= CLV_EPS) && (p <= 1.0f - CLV_EPS);
+      dl = pass ? scale * (pc - x) : 0.f;
+      if (do_backward) dlogits[r * XD + j] = dl;
+    }
+    h_s[(rq * 8 + i) * XD + j] = dl;
+  }
+  const float t = block_sum(lsum, red);   // contains __syncthreads: the dlogits tile is complete
+  if (tid == 0) atomicAdd(loss_acc + 0, t * scale);
+  if (!do_backward) return;
+  // dh[r][k] = sum_d dlogits[r][d] * Kx[k][d]
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 4
+  for (int d = 0; d < XD; ++d) {
+    const float w = KT_s[d * XD + j];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(h_s[(rq * 8 + i) * XD + d], w, acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t r = row0 + rq * 8 + i;
+    if (r < R) dh[r * XD + j] = acc[i];
+  }
+}
+
+// ------------------------------------------------------------------------------ key encoder fwd
+constexpr int KT = 128;   // threads per sequence
+
+__global__ void __launch_bounds__(KT)
+keyenc_fwd_kernel(const uint8_t* __restrict__ roll, const int32_t* __restrict__ off, const int shift,
+                  const int L, const int D, const float* __restrict__ Khw,
+                  const float* __restrict__ bhw, const float* __restrict__ Kwa,
+                  const float* __restrict__ bwa, float* __restrict__ eps_w,
+                  const int32_t* __restrict__ labels, float* __restrict__ hW,
+                  float* __restrict__ Wargs, float* __restrict__ W, float* __restrict__ loss_acc,
+                  const int C, const float prior, const float scale_b, const int gen_noise,
+                  const uint64_t seed, const uint64_t* ctr) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  const int n = L * D;                                   // window bytes (D % 4 == 0)
+  const int nwords = n >> 2;
+  uint32_t* win_s = reinterpret_cast<uint32_t*>(dyn);    // [nwords]
+  uint16_t* list_s = reinterpret_cast<uint16_t*>(dyn + (size_t)nwords * 4);   // active positions
+  __shared__ int cnt_s[KT + 1];
+  __shared__ float hw_s[128];
+  __shared__ float wa_s[32];
+  const int tid = threadIdx.x, b = blockIdx.x;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(roll + ((size_t)__ldg(off + b) + shift) * D);
+  for (int i = tid; i < nwords; i += KT) win_s[i] = __ldg(src + i);
+  __syncthreads();
+  // ---- ordered compaction of the set bytes (deterministic summation order)
+  const int chunk = (nwords + KT - 1) / KT;
+  const int w0 = tid * chunk, w1 = min(nwords, w0 + chunk);
+  int cnt = 0;
+  for (int i = w0; i < w1; ++i) {
+    const uint32_t v = win_s[i];
+    cnt += (v & 0xffu ? 1 : 0) + (v & 0xff00u ? 1 : 0) + (v & 0xff0000u ? 1 : 0) + (v & 0xff000000u ? 1 : 0);
+  }
+  cnt_s[tid + 1] = cnt;
+  if (tid == 0) cnt_s[0] = 0;
+  __syncthreads();
+  if (tid == 0)
+    for (int i = 1; i <= KT; ++i) cnt_s[i] += cnt_s[i - 1];
+  __syncthreads();
+  int pos = cnt_s[tid];
+  for (int i = w0; i < w1; ++i) {
+    const uint32_t v = win_s[i];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if ((v >> (8 * q)) & 0xffu) list_s[pos++] = (uint16_t)(4 * i + q);
+  }
+  const int nact = cnt_s[KT];
+  __syncthreads();
+  // ---- hW = relu(b + sum of active kernel rows)
+  if (tid < D) {
+    float a0 = __ldg(bhw + tid), a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int i = 0;
+    for (; i + 4 <= nact; i += 4) {
+      a0 += __ldg(Khw + (size_t)list_s[i] * D + tid);
+      a1 += __ldg(Khw + (size_t)list_s[i + 1] * D + tid);
+      a2 += __ldg(Khw + (size_t)list_s[i + 2] * D + tid);
+      a3 += __ldg(Khw + (size_t)list_s[i + 3] * D + tid);
+    }
+    for (; i < nact; ++i) a0 += __ldg(Khw + (size_t)list_s[i] * D + tid);
+    const float v = fmaxf((a0 + a1) + (a2 + a3), 0.f);
+    hw_s[tid] = v;
+    hW[(size_t)b * D + tid] = v;
+  }
+  __syncthreads();
+  // ---- Wargs = hW @ Kwa + b
+  const int C1 = C - 1, NW = 2 * C1;
+  if (tid < NW) {
+    float a = __ldg(bwa + tid);
+    for (int k = 0; k < D; ++k) a = fmaf(hw_s[k], __ldg(Kwa + (size_t)k * NW + tid), a);
+    wa_s[tid] = a;
+    Wargs[(size_t)b * NW + tid] = a;
+  }
+  __syncthreads();
+  // ---- logistic-normal sample + losses (same maths as logitnormal_fwd_kernel), lanes 0..15
+  if (tid < 32) {
+    const int j = tid & 15;
+    float mu = 0.f, lv = 0.f, eps = 0.f;
+    if (j < C1) {
+      mu = wa_s[j]; lv = wa_s[C1 + j];
+      if (tid < 16) {
+        if (gen_noise) {
+          eps = philox_normal2(seed, *ctr, 1u, (uint64_t)b * C1 + j).x;
+          eps_w[(size_t)b * C1 + j] = eps;
+        } else {
+          eps = eps_w[(size_t)b * C1 + j];
+        }
+      }
+    }
+    eps = __shfl_sync(0xffffffffu, eps, j);   // both half-warps compute the same row
+    const float s = mu + expf(lv * 0.5f) * eps;
+    const float e = (j < C1) ? expf(s) : (j == C1 ? 1.0f : 0.0f);
+    const float w = e / seg16_sum(e);
+    if (tid < C) W[(size_t)b * C + tid] = w;
+    const float ep = expf(prior);
+    const float wkl = -0.5f * seg16_sum((j < C1) ? (1.0f - prior + lv - expf(lv) / ep - mu * mu / ep) : 0.f);
+    const float w2 = (j < C) ? (w + 1e-10f) : 0.f;
+    const float S = seg16_sum(w2);
+    const float qc = fminf(fmaxf(w2 / S, CLV_EPS), 1.0f - CLV_EPS);
+    const int lab = __ldg(labels + b);
+    const float wrec = seg16_sum((j == lab) ? -(float)C1 * logf(qc) : 0.f);
+    float bv = (j < C) ? w : -INFINITY;
+    int bi = j;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (tid == 0) {
+      atomicAdd(loss_acc + 1, wkl * scale_b);
+      atomicAdd(loss_acc + 2, wrec * scale_b);
+      atomicAdd(loss_acc + 4, (bi == lab ? 1.f : 0.f) * scale_b);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ key encoder bwd
+// one warp per sequence: logistic-normal backward -> dWargs -> dhW = (dWargs @ Kwa^T) * [hW > 0]
+__global__ void __launch_bounds__(256)
+keyenc_bwd_kernel(const float* __restrict__ Wargs, const float* __restrict__ eps_w,
+                  const int32_t* __restrict__ labels, const float* __restrict__ W,
+                  const float* __restrict__ dW_ext, const float* __restrict__ Kwa,
+                  const float* __restrict__ hW, float* __restrict__ dWargs, float* __restrict__ dhW,
+                  const int B, const int C, const int D, const float prior, const float cw_over_B,
+                  const float wkl_over_B) {
+  __shared__ float dwa_s[8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.x * 8 + wid;
+  const bool rv = b < B;
+  const int j = lane & 15, C1 = C - 1, NW = 2 * C1;
+  float w = 0.f, dwe = 0.f;
+  if (rv && j < C) { w = __ldg(W + (size_t)b * C + j); dwe = __ldg(dW_ext + (size_t)b * C + j); }
+  const int lab = rv ? __ldg(labels + b) : 0;
+  const float w2 = (j < C) ? (w + 1e-10f) : 0.f;
+  const float S = seg16_sum(w2);
+  const float q = w2 / S;
+  const bool pass = (q >= CLV_EPS) && (q <= 1.0f - CLV_EPS);
+  const float qc = fminf(fmaxf(q, CLV_EPS), 1.0f - CLV_EPS);
+  const float dq = (j == lab && j < C && pass) ? (-(float)C1 / qc) * cw_over_B : 0.f;
+  const float dqw = seg16_sum(dq * w2);
+  const float dWv = (j < C) ? (dwe + dq / S - dqw / (S * S)) : 0.f;
+  const float dot = seg16_sum(dWv * w);
+  const float ds = w * (dWv - dot);
+  if (rv && j < C1 && lane < 16) {
+    const float mu = __ldg(Wargs + (size_t)b * NW + j), lv = __ldg(Wargs + (size_t)b * NW + C1 + j);
+    const float eps = __ldg(eps_w + (size_t)b * C1 + j);
+    const float ep = expf(prior);
+    const float dm = ds + wkl_over_B * mu / ep;
+    const float dv = ds * eps * 0.5f * expf(lv * 0.5f) + wkl_over_B * (-0.5f) * (1.0f - expf(lv) / ep);
+    dWargs[(size_t)b * NW + j] = dm;
+    dWargs[(size_t)b * NW + C1 + j] = dv;
+    dwa_s[wid][j] = dm;
+    dwa_s[wid][C1 + j] = dv;
+  }
+  __syncwarp();
+  if (rv)
+    for (int k = lane; k < D; k += 32) {
+      float a = 0.f;
+      for (int o = 0; o < NW; ++o) a = fmaf(dwa_s[wid][o], __ldg(Kwa + (size_t)k * NW + o), a);
+      dhW[(size_t)b * D + k] = (__ldg(hW + (size_t)b * D + k) > 0.f) ? a : 0.f;
+    }
+}
+
+}  // namespace
+
+extern "C" int clv_xhead_fwd_bwd(const float* h, const float* Kx, const float* bx,
+                                 const uint8_t* roll, const int32_t* x_off, int32_t x_grp,
+                                 int32_t x_shift, float* loss_acc, float* dlogits, float* dh, int64_t R,
+                                 int32_t H, int32_t D, float scale, int32_t do_backward, void* stream) {
+  if (!h || !Kx || !bx || !roll || !x_off || !loss_acc || x_grp <= 0) return CLV_E_INVALID;
+  if (do_backward && (!dlogits || !dh)) return CLV_E_INVALID;
+  if (H != XD || D != XD) return CLV_E_UNSUPPORTED;
+  if (R <= 0) return CLV_OK;
+  const size_t smem = sizeof(float) * (2 * XD * XD + XR * XD);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CLV_CUDA(cudaFuncSetAttribute(xhead_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  xhead_kernel<<<(unsigned)((R + XR - 1) / XR), XT, smem, (cudaStream_t)stream>>>(
+      h, Kx, bx, roll, x_off, x_grp, x_shift, loss_acc, dlogits, dh, R, scale, do_backward);
+  CLV_CHECK_LAUNCH();
+  return CLV_OK;
+}
+
+extern "C" int clv_keyenc_fwd(const uint8_t* roll, const int32_t* win_off, int32_t shift, int32_t L,
+                              int32_t D, const float* Khw, const float* bhw, const float* Kwa,
+                              const float* bwa, float* eps_w, const int32_t* labels, float* hW,
+                              float* Wargs, float* W, float* loss_acc, int32_t B, int32_t C,
+                              float w_log_var_prior, float scale_b, int32_t gen_noise, uint64_t seed,
+                              const uint64_t* ctr, void* stream) {
+  if (!roll || !win_off || !Khw || !bhw || !Kwa || !bwa || !eps_w || !labels || !hW || !Wargs || !W ||
+      !loss_acc)
+    return CLV_E_INVALID;
+  if (C < 2 || C > 16 || D > 128 || (D & 3) || (int64_t)L * D > 65535) return CLV_E_UNSUPPORTED;
+  if (gen_noise && !ctr) return CLV_E_INVALID;
+  if (B <= 0) return CLV_OK;
+  const size_t smem = (size_t)L * D + 2 * (size_t)L * D + 16;
+  static size_t attr_smem = 48 * 1024;
+  if (smem > attr_smem) {
+    if (smem > 227 * 1024) return CLV_E_UNSUPPORTED;
+    CLV_CUDA(cudaFuncSetAttribute(keyenc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  keyenc_fwd_kernel<<<B, KT, smem, (cudaStream_t)stream>>>(
+      roll, win_off, shift, L, D, Khw, bhw, Kwa, bwa, eps_w, labels, hW, Wargs, W, loss_acc, C,
+      w_log_var_prior, scale_b, gen_noise, seed, ctr);
+  CLV_CHECK_LAUNCH();
+  return CLV_OK;
+}
+
+extern "C" int clv_keyenc_bwd(const float* Wargs, const float* eps_w, const int32_t* labels,
+                              const float* W, const float* dW_ext, const float* Kwa, const float* hW,
+                              float* dWargs, float* dhW, int32_t B, int32_t C, int32_t D,
+                              float w_log_var_prior, float cw_over_B, float wkl_over_B, void* stream) {
+  if (!Wargs || !eps_w || !labels || !W || !dW_ext || !Kwa || !hW || !dWargs || !dhW) return CLV_E_INVALID;
+  if (C < 2 || C > 16) return CLV_E_UNSUPPORTED;
+  if (B <= 0) return CLV_OK;
+  keyenc_bwd_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+      Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, B, C, D, w_log_var_prior, cw_over_B,
+      wkl_over_B);
+  CLV_CHECK_LAUNCH();
+  return CLV_OK;
+}

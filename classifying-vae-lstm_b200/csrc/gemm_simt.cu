@@ -7,7 +7,7 @@
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, PAD = 4, NT = 256;
+constexpr int BK = 16, PAD = 4;
 
 template <bool A_U8>
 __device__ __forceinline__ float load_a(const void* A, int64_t idx) {
@@ -17,19 +17,27 @@ __device__ __forceinline__ float load_a(const void* A, int64_t idx) {
 
 __device__ __forceinline__ int64_t gather_row(const clv_gemm_args& a, int64_t r) {
   if (a.a_off) {
-    const int64_t g = r / a.a_grp;
-    return (int64_t)__ldg(a.a_off + g) + a.a_shift + (r - g * a.a_grp);
+    const uint32_t ru = (uint32_t)r, grp = (uint32_t)a.a_grp;   // rows < 2^31: 32-bit division
+    const uint32_t g = ru / grp;
+    return (int64_t)__ldg(a.a_off + g) + a.a_shift + (int64_t)(ru - g * grp);
   }
   return r;
 }
 
-template <bool A_U8, bool A_KM, bool B_NM>
-__global__ void __launch_bounds__(NT) gemm_kernel(const clv_gemm_args a, const int kchunk) {
-  __shared__ __align__(16) float As[BK][BM + PAD];
-  __shared__ __align__(16) float Bs[BK][BN + PAD];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int64_t m0 = (int64_t)blockIdx.x * BM;
-  const int n0 = blockIdx.y * BN;
+// Tile BMxBN (square), 4x4 outputs per thread, BK=16.  BT=64 (256 threads) for large problems,
+// BT=32 (64 threads, up to 32 CTAs/SM) when the 64-tile grid would leave most SMs idle.
+template <int BT, bool A_U8, bool A_KM, bool B_NM>
+__global__ void __launch_bounds__((BT / 4) * (BT / 4)) gemm_kernel(const clv_gemm_args a,
+                                                                   const int kchunk) {
+  constexpr int NT = (BT / 4) * (BT / 4);      // threads
+  constexpr int LPT = BT * BK / NT;            // loads per thread per operand tile (4 or 8)
+  constexpr int TPR = BK / LPT;                // threads per K-major row
+  constexpr int KSTEP = NT / BT;               // k rows covered per pass for M/N-major operands
+  __shared__ __align__(16) float As[BK][BT + PAD];
+  __shared__ __align__(16) float Bs[BK][BT + PAD];
+  const int tid = threadIdx.x, tx = tid % (BT / 4), ty = tid / (BT / 4);
+  const int64_t m0 = (int64_t)blockIdx.x * BT;
+  const int n0 = blockIdx.y * BT;
   const int64_t kbeg = (int64_t)blockIdx.z * kchunk;
   const int64_t kend = min((int64_t)a.K, kbeg + kchunk);
 
@@ -39,44 +47,47 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const clv_gemm_args a, const i
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  float ra[4], rb[4];
+  // K-major operands: a thread owns ONE row and LPT consecutive k (row address computed once);
+  // M/N-major operands: a thread owns one m (n) and LPT k rows, coalesced along m (n).
+  const int am = A_KM ? (tid / TPR) : (tid % BT);
+  const int ak = A_KM ? ((tid % TPR) * LPT) : (tid / BT);
+  const int bn = B_NM ? (tid % BT) : (tid / TPR);
+  const int bk = B_NM ? (tid / BT) : ((tid % TPR) * LPT);
+  const bool a_ok = (m0 + am) < a.M, b_ok = (n0 + bn) < a.N;
+  int64_t a_base = 0;
+  if (A_KM && a_ok) a_base = gather_row(a, m0 + am) * a.lda;
+  const int64_t b_base = B_NM ? (int64_t)(n0 + bn) : (int64_t)(n0 + bn) * a.ldb;
+
+  float ra[LPT], rb[LPT];
   auto fetch = [&](int64_t k0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + i * NT;
-      // ---- A element
-      int mm, kk;
-      if (A_KM) { kk = idx & (BK - 1); mm = idx >> 4; } else { mm = idx & (BM - 1); kk = idx >> 6; }
-      const int64_t m = m0 + mm, k = k0 + kk;
+    for (int i = 0; i < LPT; ++i) {
       float v = 0.f;
-      if (m < a.M && k < kend) {
-        if (A_KM) {
-          v = load_a<A_U8>(a.A, gather_row(a, m) * a.lda + k);
-        } else {
-          bool skip = a.a_skip_grp > 0 && (k % a.a_skip_grp) == 0;
-          if (!skip) v = load_a<A_U8>(a.A, gather_row(a, k + a.a_row_delta) * a.lda + m);
-        }
+      if (A_KM) {
+        const int64_t k = k0 + ak + i;
+        if (a_ok && k < kend) v = load_a<A_U8>(a.A, a_base + k);
+      } else {
+        const int64_t k = k0 + ak + KSTEP * i;
+        if (a_ok && k < kend && !(a.a_skip_grp > 0 && ((uint32_t)k % (uint32_t)a.a_skip_grp) == 0))
+          v = load_a<A_U8>(a.A, gather_row(a, k + a.a_row_delta) * a.lda + (m0 + am));
       }
       ra[i] = v;
-      // ---- B element
-      int nn, kb;
-      if (B_NM) { nn = idx & (BN - 1); kb = idx >> 6; } else { kb = idx & (BK - 1); nn = idx >> 4; }
-      const int n = n0 + nn;
-      const int64_t k2 = k0 + kb;
       float w = 0.f;
-      if (n < a.N && k2 < kend) w = B_NM ? __ldg(a.Bm + k2 * a.ldb + n) : __ldg(a.Bm + (int64_t)n * a.ldb + k2);
+      if (B_NM) {
+        const int64_t k = k0 + bk + KSTEP * i;
+        if (b_ok && k < kend) w = __ldg(a.Bm + k * a.ldb + b_base);
+      } else {
+        const int64_t k = k0 + bk + i;
+        if (b_ok && k < kend) w = __ldg(a.Bm + b_base + k);
+      }
       rb[i] = w;
     }
   };
   auto stash = [&]() {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + i * NT;
-      int mm, kk, nn, kb;
-      if (A_KM) { kk = idx & (BK - 1); mm = idx >> 4; } else { mm = idx & (BM - 1); kk = idx >> 6; }
-      if (B_NM) { nn = idx & (BN - 1); kb = idx >> 6; } else { kb = idx & (BK - 1); nn = idx >> 4; }
-      As[kk][mm] = ra[i];
-      Bs[kb][nn] = rb[i];
+    for (int i = 0; i < LPT; ++i) {
+      if (A_KM) As[ak + i][am] = ra[i]; else As[ak + KSTEP * i][am] = ra[i];
+      if (B_NM) Bs[bk + KSTEP * i][bn] = rb[i]; else Bs[bk + i][bn] = rb[i];
     }
   };
 
@@ -125,12 +136,23 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const clv_gemm_args a, const i
   }
 }
 
-template <bool A_U8, bool A_KM>
+template <int BT, bool A_U8, bool A_KM>
 int launch2(const clv_gemm_args& a, dim3 grid, int kchunk, cudaStream_t st) {
-  if (a.b_nmajor) gemm_kernel<A_U8, A_KM, true><<<grid, NT, 0, st>>>(a, kchunk);
-  else gemm_kernel<A_U8, A_KM, false><<<grid, NT, 0, st>>>(a, kchunk);
+  constexpr int NT = (BT / 4) * (BT / 4);
+  if (a.b_nmajor) gemm_kernel<BT, A_U8, A_KM, true><<<grid, NT, 0, st>>>(a, kchunk);
+  else gemm_kernel<BT, A_U8, A_KM, false><<<grid, NT, 0, st>>>(a, kchunk);
   CLV_CHECK_LAUNCH();
   return CLV_OK;
+}
+
+template <int BT>
+int launch1(const clv_gemm_args& a, int kchunk, cudaStream_t st) {
+  const int64_t gm = ((int64_t)a.M + BT - 1) / BT;
+  const int gn = (a.N + BT - 1) / BT;
+  if (gn > 65535 || a.split_k > 65535) return CLV_E_UNSUPPORTED;
+  dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)a.split_k);
+  if (a.a_u8) return a.a_kmajor ? launch2<BT, true, true>(a, grid, kchunk, st) : launch2<BT, true, false>(a, grid, kchunk, st);
+  return a.a_kmajor ? launch2<BT, false, true>(a, grid, kchunk, st) : launch2<BT, false, false>(a, grid, kchunk, st);
 }
 
 __global__ void colsum_kernel(const float* __restrict__ A, int64_t lda, int M, int N,
@@ -153,7 +175,27 @@ __global__ void colsum_kernel(const float* __restrict__ A, int64_t lda, int M, i
   }
 }
 
+__global__ void bias_act_kernel(float* __restrict__ C, int64_t ldc, int M, int N,
+                                const float* __restrict__ bias, int relu) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * N) return;
+  const int64_t m = i / N;
+  const int n = (int)(i - m * N);
+  float v = C[m * ldc + n] + (bias ? __ldg(bias + n) : 0.f);
+  C[m * ldc + n] = relu ? fmaxf(v, 0.f) : v;
+}
+
 }  // namespace
+
+extern "C" int clv_bias_act(float* C, int64_t ldc, int32_t M, int32_t N, const float* bias,
+                            int32_t relu, void* stream) {
+  if (!C) return CLV_E_INVALID;
+  if (M <= 0 || N <= 0) return CLV_OK;
+  const int64_t n = (int64_t)M * N;
+  bias_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(C, ldc, M, N, bias, relu);
+  CLV_CHECK_LAUNCH();
+  return CLV_OK;
+}
 
 extern "C" int clv_gemm(const clv_gemm_args* args, void* stream) {
   if (!args || !args->A || !args->Bm || !args->C) return CLV_E_INVALID;
@@ -166,13 +208,11 @@ extern "C" int clv_gemm(const clv_gemm_args* args, void* stream) {
   int kchunk = (int)(((int64_t)a.K + a.split_k - 1) / a.split_k);
   kchunk = ((kchunk + BK - 1) / BK) * BK;
   a.split_k = (a.K + kchunk - 1) / kchunk;
-  const int64_t gm = ((int64_t)a.M + BM - 1) / BM;
-  const int gn = (a.N + BN - 1) / BN;
-  if (gn > 65535 || a.split_k > 65535) return CLV_E_UNSUPPORTED;
-  dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)a.split_k);
   cudaStream_t st = (cudaStream_t)stream;
-  if (a.a_u8) return a.a_kmajor ? launch2<true, true>(a, grid, kchunk, st) : launch2<true, false>(a, grid, kchunk, st);
-  return a.a_kmajor ? launch2<false, true>(a, grid, kchunk, st) : launch2<false, false>(a, grid, kchunk, st);
+  // small problems: 32x32 tiles of 64 threads so the grid covers the chip and many CTAs share an SM
+  const int64_t ctas64 = (((int64_t)a.M + 63) / 64) * ((a.N + 63) / 64) * a.split_k;
+  if (ctas64 < 2LL * clv_num_sms()) return launch1<32>(a, kchunk, st);
+  return launch1<64>(a, kchunk, st);
 }
 
 extern "C" int clv_colsum(const float* A, int64_t lda, int32_t M, int32_t N, float* out,

@@ -14,16 +14,32 @@ namespace {
 
 constexpr int RMAX = 8;  // batch rows per CTA (smem tile)
 
+// Optional fused input terms (the parts of the Keras LSTM input projection that are not a GEMM over
+// the piano-roll): a = xproj + bias + Wv[b,:] @ Ww (RepeatVector(W) columns, constant over t)
+//                                   + Zs[b,t,:] @ Kz (the Z columns, rank-Z)      + h_{t-1} @ U
+struct LstmExtra {
+  const float* bias;   // [4H] or null
+  const float* Wv;     // [B,C] simplex W or null
+  const float* Ww;     // [C,4H] rows of the kernel that multiply W
+  const float* Zs;     // [B,L,Z] or null
+  const float* Kz;     // [Z,4H] rows of the kernel that multiply Z
+  float* dZ;           // bwd only: [B,L,Z] out (dLoss/dZ) or null
+  float* dW_ext;       // bwd only: [B,C] (+)= dAsum @ Ww^T or null
+  int C, Z, has_xproj, dW_accumulate;
+};
+constexpr int ZMAX = 16;
+
 template <int H, int RC>
 __global__ void __launch_bounds__(8 * H, 1)
 lstm_fwd_kernel(float* __restrict__ gates, const float* __restrict__ U, float* __restrict__ hout,
                 float* __restrict__ cout, const float* __restrict__ h0, const float* __restrict__ c0,
-                const int B, const int L, const int R) {
+                const int B, const int L, const int R, const LstmExtra ex) {
   constexpr int G = 4 * H, KSZ = H / 2, NT = 8 * H;
   static_assert(KSZ % 4 == 0, "H must be a multiple of 8");
   __shared__ __align__(16) float h_s[RMAX][H];
   __shared__ __align__(16) float a_s[RMAX][G];
   __shared__ float c_s[RMAX][H];
+  __shared__ float kz_s[ZMAX][G];
   const int tid = threadIdx.x, n = tid >> 1, ks = tid & 1;
   const int b0 = blockIdx.x * R;
   const int nrows = min(R, B - b0);
@@ -31,6 +47,19 @@ lstm_fwd_kernel(float* __restrict__ gates, const float* __restrict__ U, float* _
   float Ureg[KSZ];
 #pragma unroll
   for (int i = 0; i < KSZ; ++i) Ureg[i] = __ldg(U + (size_t)(ks * KSZ + i) * G + n);
+  // per-row constant: bias + W[b,:] @ Ww   (rows this lane finalises: r = 2q + ks)
+  float cb[RMAX / 2];
+#pragma unroll
+  for (int q = 0; q < RMAX / 2; ++q) {
+    const int r = 2 * q + ks;
+    float v = ex.bias ? __ldg(ex.bias + n) : 0.f;
+    if (ex.Wv && r < nrows)
+      for (int c = 0; c < ex.C; ++c)
+        v = fmaf(__ldg(ex.Wv + (size_t)(b0 + r) * ex.C + c), __ldg(ex.Ww + (size_t)c * G + n), v);
+    cb[q] = v;
+  }
+  const int Z = ex.Zs ? ex.Z : 0;
+  for (int i = tid; i < Z * G; i += NT) kz_s[i / G][i % G] = __ldg(ex.Kz + i);
 
   for (int i = tid; i < RMAX * H; i += NT) {
     const int r = i / H, j = i - r * H;
@@ -42,12 +71,22 @@ lstm_fwd_kernel(float* __restrict__ gates, const float* __restrict__ U, float* _
 
   for (int t = 0; t < L; ++t) {
     // ---- a = xproj_t + h_{t-1} @ U
-    for (int r0 = 0; r0 < nrows; r0 += RC) {
+#pragma unroll
+    for (int rr = 0; rr < RMAX / RC; ++rr) {
+      const int r0 = rr * RC;
+      if (r0 >= nrows) break;
       float xv[RC / 2];
 #pragma unroll
       for (int q = 0; q < RC / 2; ++q) {
         const int r = r0 + 2 * q + ks;
-        xv[q] = (r < nrows) ? gates[((size_t)(b0 + r) * L + t) * G + n] : 0.f;
+        float v = 0.f;
+        if (r < nrows) {
+          const size_t bt = (size_t)(b0 + r) * L + t;
+          v = cb[rr * (RC / 2) + q];
+          if (ex.has_xproj) v += gates[bt * G + n];
+          for (int j = 0; j < Z; ++j) v = fmaf(__ldg(ex.Zs + bt * Z + j), kz_s[j][n], v);
+        }
+        xv[q] = v;
       }
       float acc[RC];
 #pragma unroll
@@ -98,14 +137,18 @@ template <int H, int RC>
 __global__ void __launch_bounds__(8 * H, 1)
 lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const float* __restrict__ c,
                 const float* __restrict__ dh_out, float* __restrict__ dAsum, const int B,
-                const int L, const int R) {
+                const int L, const int R, const LstmExtra ex) {
   constexpr int G = 4 * H, NS = 8, NSZ = G / NS, NT = 8 * H;
   static_assert(NSZ % 4 == 0, "H must be a multiple of 8");
   constexpr int SLOTS = (RMAX * H + NT - 1) / NT;
   __shared__ __align__(16) float da_s[RMAX][G];
   __shared__ float dhrec_s[RMAX][H];
   __shared__ float dc_s[RMAX][H];
+  __shared__ float kz_s[ZMAX][G];
   const int tid = threadIdx.x, k = tid >> 3, ns = tid & 7;
+  const int lane = tid & 31, wid = tid >> 5;
+  const int Z = ex.dZ ? ex.Z : 0;
+  for (int i = tid; i < Z * G; i += NT) kz_s[i / G][i % G] = __ldg(ex.Kz + i);
   const int b0 = blockIdx.x * R;
   const int nrows = min(R, B - b0);
 
@@ -151,8 +194,17 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
         asum[s][0] += dai; asum[s][1] += daf; asum[s][2] += dag; asum[s][3] += dao;
       }
     }
-    if (t == 0) break;
+    if (t == 0 && Z == 0) break;
     __syncthreads();
+    // ---- dZ[b,t,:] = da @ Kz^T (rank-Z gradient to the latent; one warp per (row, j) pair)
+    for (int pz = wid; pz < nrows * Z; pz += NT / 32) {
+      const int r = pz / Z, j = pz - r * Z;
+      float p = 0.f;
+      for (int i = lane; i < G; i += 32) p = fmaf(da_s[r][i], kz_s[j][i], p);
+      p = warp_sum(p);
+      if (lane == 0) ex.dZ[((size_t)(b0 + r) * L + t) * Z + j] = p;
+    }
+    if (t == 0) break;
     // ---- dh_rec = da @ U^T
     for (int r0 = 0; r0 < nrows; r0 += RC) {
       float acc[RC];
@@ -181,6 +233,7 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
     }
     __syncthreads();
   }
+  __syncthreads();   // every warp is past its last read of da_s: reuse it for the per-row sums
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
     const int cell = tid + s * NT;
@@ -188,6 +241,21 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
       const int r = cell / H, j = cell - r * H;
       float* ap = dAsum + (size_t)(b0 + r) * G + j;
       ap[0] = asum[s][0]; ap[H] = asum[s][1]; ap[2 * H] = asum[s][2]; ap[3 * H] = asum[s][3];
+      da_s[r][j] = asum[s][0]; da_s[r][H + j] = asum[s][1];
+      da_s[r][2 * H + j] = asum[s][2]; da_s[r][3 * H + j] = asum[s][3];
+    }
+  }
+  if (ex.dW_ext) {   // dW[b,:] (+)= (sum_t da[b,t,:]) @ Ww^T : gradient to the simplex W
+    __syncthreads();
+    for (int pc = wid; pc < nrows * ex.C; pc += NT / 32) {
+      const int r = pc / ex.C, cc = pc - r * ex.C;
+      float p = 0.f;
+      for (int i = lane; i < G; i += 32) p = fmaf(da_s[r][i], __ldg(ex.Ww + (size_t)cc * G + i), p);
+      p = warp_sum(p);
+      if (lane == 0) {
+        float* o = ex.dW_ext + (size_t)(b0 + r) * ex.C + cc;
+        *o = ex.dW_accumulate ? (*o + p) : p;
+      }
     }
   }
 }
@@ -200,34 +268,67 @@ int pick_rows(int B) {
   return (r + 1) & ~1;  // multiple of 2
 }
 
+int lstm_fwd_launch(float* gates, const float* U, float* h, float* c, const float* h0,
+                    const float* c0, int B, int L, int H, const LstmExtra& ex, cudaStream_t st) {
+  if (!gates || !U || !h || !c) return CLV_E_INVALID;
+  if (H != 88 || ex.Z > ZMAX) return CLV_E_UNSUPPORTED;
+  if (B <= 0 || L <= 0) return CLV_OK;
+  const int R = pick_rows(B);
+  const int grid = (B + R - 1) / R;
+  if (R % 4 == 0) lstm_fwd_kernel<88, 4><<<grid, 8 * 88, 0, st>>>(gates, U, h, c, h0, c0, B, L, R, ex);
+  else lstm_fwd_kernel<88, 2><<<grid, 8 * 88, 0, st>>>(gates, U, h, c, h0, c0, B, L, R, ex);
+  CLV_CHECK_LAUNCH();
+  return CLV_OK;
+}
+
+int lstm_bwd_launch(float* gates, const float* U, const float* c, const float* dh_out, float* dAsum,
+                    int B, int L, int H, const LstmExtra& ex, cudaStream_t st) {
+  if (!gates || !U || !c || !dh_out || !dAsum) return CLV_E_INVALID;
+  if (H != 88 || ex.Z > ZMAX) return CLV_E_UNSUPPORTED;
+  if (B <= 0 || L <= 0) return CLV_OK;
+  const int R = pick_rows(B);
+  const int grid = (B + R - 1) / R;
+  if (R % 4 == 0) lstm_bwd_kernel<88, 4><<<grid, 8 * 88, 0, st>>>(gates, U, c, dh_out, dAsum, B, L, R, ex);
+  else lstm_bwd_kernel<88, 2><<<grid, 8 * 88, 0, st>>>(gates, U, c, dh_out, dAsum, B, L, R, ex);
+  CLV_CHECK_LAUNCH();
+  return CLV_OK;
+}
+
 }  // namespace
 
 extern "C" int clv_lstm_fwd(float* gates, const float* U, float* h, float* c, const float* h0,
                             const float* c0, int32_t B, int32_t L, int32_t H, void* stream) {
-  if (!gates || !U || !h || !c) return CLV_E_INVALID;
-  if (H != 88) return CLV_E_UNSUPPORTED;
-  if (B <= 0 || L <= 0) return CLV_OK;
-  const int R = pick_rows(B);
-  const int grid = (B + R - 1) / R;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (R % 4 == 0) lstm_fwd_kernel<88, 4><<<grid, 8 * 88, 0, st>>>(gates, U, h, c, h0, c0, B, L, R);
-  else lstm_fwd_kernel<88, 2><<<grid, 8 * 88, 0, st>>>(gates, U, h, c, h0, c0, B, L, R);
-  CLV_CHECK_LAUNCH();
-  return CLV_OK;
+  LstmExtra ex = {};
+  ex.has_xproj = 1;
+  return lstm_fwd_launch(gates, U, h, c, h0, c0, B, L, H, ex, (cudaStream_t)stream);
 }
 
 extern "C" int clv_lstm_bwd(float* gates, const float* U, const float* h, const float* c,
                             const float* dh_out, float* dAsum, int32_t B, int32_t L, int32_t H,
                             void* stream) {
   (void)h;
-  if (!gates || !U || !c || !dh_out || !dAsum) return CLV_E_INVALID;
-  if (H != 88) return CLV_E_UNSUPPORTED;
-  if (B <= 0 || L <= 0) return CLV_OK;
-  const int R = pick_rows(B);
-  const int grid = (B + R - 1) / R;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (R % 4 == 0) lstm_bwd_kernel<88, 4><<<grid, 8 * 88, 0, st>>>(gates, U, c, dh_out, dAsum, B, L, R);
-  else lstm_bwd_kernel<88, 2><<<grid, 8 * 88, 0, st>>>(gates, U, c, dh_out, dAsum, B, L, R);
-  CLV_CHECK_LAUNCH();
-  return CLV_OK;
+  LstmExtra ex = {};
+  return lstm_bwd_launch(gates, U, c, dh_out, dAsum, B, L, H, ex, (cudaStream_t)stream);
+}
+
+extern "C" int clv_lstm_fwd_fused(float* gates, int32_t has_xproj, const float* U, const float* bias,
+                                  const float* Wv, const float* Ww, int32_t C, const float* Zs,
+                                  const float* Kz, int32_t Z, float* h, float* c, int32_t B, int32_t L,
+                                  int32_t H, void* stream) {
+  LstmExtra ex = {};
+  ex.bias = bias; ex.Wv = Wv; ex.Ww = Ww; ex.C = C; ex.Zs = Zs; ex.Kz = Kz; ex.Z = Z;
+  ex.has_xproj = has_xproj;
+  if ((Wv && (!Ww || C < 1)) || (Zs && (!Kz || Z < 1))) return CLV_E_INVALID;
+  return lstm_fwd_launch(gates, U, h, c, nullptr, nullptr, B, L, H, ex, (cudaStream_t)stream);
+}
+
+extern "C" int clv_lstm_bwd_fused(float* gates, const float* U, const float* c, const float* dh_out,
+                                  float* dAsum, const float* Ww, int32_t C, float* dW_ext,
+                                  int32_t dW_accumulate, const float* Kz, int32_t Z, float* dZ,
+                                  int32_t B, int32_t L, int32_t H, void* stream) {
+  LstmExtra ex = {};
+  ex.Ww = Ww; ex.C = C; ex.dW_ext = dW_ext; ex.dW_accumulate = dW_accumulate;
+  ex.Kz = Kz; ex.Z = Z; ex.dZ = dZ;
+  if ((dW_ext && (!Ww || C < 1)) || (dZ && (!Kz || Z < 1))) return CLV_E_INVALID;
+  return lstm_bwd_launch(gates, U, c, dh_out, dAsum, B, L, H, ex, (cudaStream_t)stream);
 }

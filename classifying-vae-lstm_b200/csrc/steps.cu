@@ -5,6 +5,23 @@
 #include <string.h>
 #include "common.cuh"
 
+extern "C" int clv_lstm_fwd_fused(float*, int32_t, const float*, const float*, const float*, const float*,
+                                  int32_t, const float*, const float*, int32_t, float*, float*, int32_t,
+                                  int32_t, int32_t, void*);
+extern "C" int clv_lstm_bwd_fused(float*, const float*, const float*, const float*, float*, const float*,
+                                  int32_t, float*, int32_t, const float*, int32_t, float*, int32_t,
+                                  int32_t, int32_t, void*);
+extern "C" int clv_xhead_fwd_bwd(const float*, const float*, const float*, const uint8_t*, const int32_t*,
+                                 int32_t, int32_t, float*, float*, float*, int64_t, int32_t, int32_t,
+                                 float, int32_t, void*);
+extern "C" int clv_keyenc_fwd(const uint8_t*, const int32_t*, int32_t, int32_t, int32_t, const float*,
+                              const float*, const float*, const float*, float*, const int32_t*, float*,
+                              float*, float*, float*, int32_t, int32_t, float, float, int32_t, uint64_t,
+                              const uint64_t*, void*);
+extern "C" int clv_keyenc_bwd(const float*, const float*, const int32_t*, const float*, const float*,
+                              const float*, const float*, float*, float*, int32_t, int32_t, int32_t, float,
+                              float, float, void*);
+
 namespace {
 
 // tensor indices in the flat buffer (Keras weighted-layer order)
@@ -124,6 +141,43 @@ int tn_u8(const uint8_t* roll, const int32_t* off, int grp, int shift, int64_t l
 
 #define TRY(x) do { int rc__ = (x); if (rc__ != CLV_OK) return rc__; } while (0)
 
+// Auxiliary stream for the weight-gradient branch (off the critical path of the step).  Created by
+// clv_runtime_init() OUTSIDE any stream capture; forked from / joined back into the caller's stream
+// with events, so all work stays ordered on the caller's stream (and is captured with it).
+struct SideStream {
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev[8] = {};
+  bool ready = false;
+};
+SideStream g_side[16];
+
+struct Fork {
+  cudaStream_t main, side;
+  SideStream* s;
+  int n = 0, nj = 0;
+  bool on;
+  Fork(cudaStream_t st, bool want) : main(st), side(st), s(nullptr), on(false) {
+    int dev = 0;
+    if (want && cudaGetDevice(&dev) == cudaSuccess && dev < 16 && g_side[dev].ready) {
+      s = &g_side[dev]; side = s->aux; on = true;
+    }
+  }
+  int fork() {   // side branch may now consume everything enqueued on main so far
+    if (!on) return CLV_OK;
+    CLV_CUDA(cudaEventRecord(s->ev[n], main));
+    CLV_CUDA(cudaStreamWaitEvent(side, s->ev[n], 0));
+    n = (n + 1) % 5;
+    return CLV_OK;
+  }
+  int join() {   // main waits for everything enqueued on the side branch so far
+    if (!on) return CLV_OK;
+    CLV_CUDA(cudaEventRecord(s->ev[5 + nj], side));
+    CLV_CUDA(cudaStreamWaitEvent(main, s->ev[5 + nj], 0));
+    nj = (nj + 1) % 3;
+    return CLV_OK;
+  }
+};
+
 int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uint8_t* roll,
               const int32_t* off, const int32_t* labels, float* eps_w, float* eps_z,
               uint64_t* ctr, float* ws, cudaStream_t st) {
@@ -152,68 +206,94 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   if (c->do_backward && !c->accumulate)
     CLV_CUDA(cudaMemsetAsync(Gr, 0, sizeof(float) * (po[R_X_B] + pc[R_X_B]), st));
 
-  // ---- forward: key encoder (model.py:174-191)
-  TRY(nn_u8(roll, off, 1, sx, D, Khw, D, hW, D, B, D, L * D, bhw, nullptr, 0, 0, 1, 0, st));
-  TRY(nn_f32(hW, D, Kwa, 2 * C1, Wargs, 2 * C1, B, 2 * C1, D, bwa, 0, 0, st));
-  TRY(clv_logitnormal_fwd(Wargs, 2 * C1, eps_w, labels, W, loss, B, C, c->w_log_var_prior, sb,
-                          c->gen_noise, c->seed, ctr, st));
-  // ---- encoder LSTM (model.py:193-199): input projection hoisted, W term is a per-sequence bias
-  TRY(nn_f32(W, C, Ke + (int64_t)D * G, G, rb_e, G, B, G, C, be, 0, 0, st));
-  TRY(nn_u8(roll, off, L, sx, D, Ke, G, gates_e, G, BL, G, D, nullptr, rb_e, G, L, 0, 0, st));
-  TRY(clv_lstm_fwd(gates_e, Ue, h_e, c_e, nullptr, nullptr, B, L, H, st));
+  Fork fk(st, c->overlap_wgrad != 0);
+  cudaStream_t sw = fk.side;   // side branch: work that is off the critical path of the step
+  const bool fused_ke = (int64_t)L * D <= 65535 && (D % 4) == 0;
+  const float* Ke_w = Ke + (int64_t)D * G;            // rows of the kernels that multiply W
+  const float* Kd_z = Kd + (int64_t)xo * G;           //                               ... Z
+  const float* Kd_w = Kd + (int64_t)(xo + Z) * G;
+
+  // ---- decoder input projection of the history roll: depends on nothing but the batch -> side
+  if (c->use_x_prev) {
+    TRY(fk.fork());
+    TRY(nn_u8(roll, off, L, 0, D, Kd, G, gates_d, G, BL, G, D, nullptr, nullptr, 0, 0, 0, 0, sw));
+  }
+  // ---- key encoder: hW, Wargs, logistic-normal W + its losses (model.py:174-191,244-255,264)
+  if (fused_ke) {
+    TRY(clv_keyenc_fwd(roll, off, sx, L, D, Khw, bhw, Kwa, bwa, eps_w, labels, hW, Wargs, W, loss, B, C,
+                       c->w_log_var_prior, sb, c->gen_noise, c->seed, ctr, st));
+  } else {
+    clv_gemm_args a = gz();
+    a.M = B; a.N = D; a.K = L * D; a.A = roll; a.lda = D; a.a_u8 = 1; a.a_off = off; a.a_grp = 1;
+    a.a_shift = sx; a.Bm = Khw; a.ldb = D; a.C = hW; a.ldc = D;
+    a.split_k = pick_split(B, D, L * D);
+    if (a.split_k > 1) {
+      CLV_CUDA(cudaMemsetAsync(hW, 0, sizeof(float) * (size_t)B * D, st));
+      TRY(clv_gemm(&a, st));
+      TRY(clv_bias_act(hW, D, B, D, bhw, 1, st));
+    } else {
+      a.bias = bhw; a.relu = 1;
+      TRY(clv_gemm(&a, st));
+    }
+    TRY(nn_f32(hW, D, Kwa, 2 * C1, Wargs, 2 * C1, B, 2 * C1, D, bwa, 0, 0, st));
+    TRY(clv_logitnormal_fwd(Wargs, 2 * C1, eps_w, labels, W, loss, B, C, c->w_log_var_prior, sb,
+                            c->gen_noise, c->seed, ctr, st));
+  }
+  // ---- encoder LSTM (model.py:193-199): roll part hoisted as one GEMM; bias and the
+  //      RepeatVector(W) columns are folded into the recurrent kernel's per-sequence constant
+  TRY(nn_u8(roll, off, L, sx, D, Ke, G, gates_e, G, BL, G, D, nullptr, nullptr, 0, 0, 0, 0, st));
+  TRY(clv_lstm_fwd_fused(gates_e, 1, Ue, be, W, Ke_w, C, nullptr, nullptr, 0, h_e, c_e, B, L, H, st));
   // ---- Z heads + sample + kl (model.py:200-216,236-239)
   TRY(clv_gauss_heads_fwd(h_e, Kzm, bzm, Kzv, bzv, eps_z, Zargs, Zs, loss, BL, H, Z, sbl,
                           c->gen_noise, c->seed, ctr, st));
-  // ---- decoder LSTM (model.py:218-228): input [Xp | Z | W]
-  TRY(nn_f32(W, C, Kd + (int64_t)(xo + Z) * G, G, rb_d, G, B, G, C, bd, 0, 0, st));
-  if (c->use_x_prev) {
-    TRY(nn_u8(roll, off, L, 0, D, Kd, G, gates_d, G, BL, G, D, nullptr, rb_d, G, L, 0, 0, st));
-    TRY(nn_f32(Zs, Z, Kd + (int64_t)xo * G, G, gates_d, G, BL, G, Z, nullptr, 0, 1, st));
+  // ---- decoder LSTM (model.py:218-228) on [Xp | Z | W]: Z enters as a rank-Z term per step
+  if (c->use_x_prev) TRY(fk.join());
+  TRY(clv_lstm_fwd_fused(gates_d, c->use_x_prev, Ud, bd, W, Kd_w, C, Zs, Kd_z, Z, h_d, c_d, B, L, H, st));
+  // ---- X head + Bernoulli loss + dlogits + dgrad to h_d in one pass (model.py:229-234,241-242)
+  if (H == 88 && D == 88) {
+    TRY(clv_xhead_fwd_bwd(h_d, Kx, bx, roll, off, L, sx, loss, logits, dh, BL, H, D, sbl,
+                          c->do_backward, st));
   } else {
-    clv_gemm_args a = gz();
-    a.M = BL; a.N = G; a.K = Z; a.A = Zs; a.lda = Z; a.Bm = Kd; a.ldb = G; a.C = gates_d; a.ldc = G;
-    a.rowadd = rb_d; a.ldra = G; a.ra_grp = L;
-    TRY(clv_gemm(&a, st));
+    TRY(nn_f32(h_d, H, Kx, D, logits, D, BL, D, H, bx, 0, 0, st));
+    TRY(clv_bernoulli_ce_fwd_bwd(logits, roll, off, L, sx, loss, BL, D, sbl, c->do_backward, st));
+    if (c->do_backward) TRY(nt_f32(logits, D, Kx, D, dh, H, BL, H, D, nullptr, 0, 0, st));
   }
-  TRY(clv_lstm_fwd(gates_d, Ud, h_d, c_d, nullptr, nullptr, B, L, H, st));
-  // ---- X head + Bernoulli loss (+ dlogits) (model.py:229-234,241-242)
-  TRY(nn_f32(h_d, H, Kx, D, logits, D, BL, D, H, bx, 0, 0, st));
-  TRY(clv_bernoulli_ce_fwd_bwd(logits, roll, off, L, sx, loss, BL, D, sbl, c->do_backward, st));
   if (!c->do_backward) return CLV_OK;
 
-  // ---- backward
+  // ---- backward.  Critical path on `st`; every weight gradient on the side branch.
   float *gKhw = Gr + po[R_HW_K], *gbhw = Gr + po[R_HW_B], *gKwa = Gr + po[R_WA_K],
         *gbwa = Gr + po[R_WA_B], *gKe = Gr + po[R_ENC_K], *gUe = Gr + po[R_ENC_U],
         *gbe = Gr + po[R_ENC_B], *gKzm = Gr + po[R_ZM_K], *gbzm = Gr + po[R_ZM_B],
         *gKzv = Gr + po[R_ZV_K], *gbzv = Gr + po[R_ZV_B], *gKd = Gr + po[R_DEC_K],
         *gUd = Gr + po[R_DEC_U], *gbd = Gr + po[R_DEC_B], *gKx = Gr + po[R_X_K],
         *gbx = Gr + po[R_X_B];
-  TRY(tn_f32(h_d, H, logits, D, gKx, D, H, D, BL, 0, 0, st));
-  TRY(clv_colsum(logits, D, BL, D, gbx, 1, st));
-  TRY(nt_f32(logits, D, Kx, D, dh, H, BL, H, D, nullptr, 0, 0, st));
-  TRY(clv_lstm_bwd(gates_d, Ud, h_d, c_d, dh, dAsum_d, B, L, H, st));
-  if (c->use_x_prev) TRY(tn_u8(roll, off, L, 0, D, gates_d, G, gKd, G, D, G, BL, st));
-  TRY(tn_f32(Zs, Z, gates_d, G, gKd + (int64_t)xo * G, G, Z, G, BL, 0, 0, st));
-  TRY(tn_f32(W, C, dAsum_d, G, gKd + (int64_t)(xo + Z) * G, G, C, G, B, 0, 0, st));
-  TRY(tn_f32(h_d, H, gates_d, G, gUd, G, H, G, BL, -1, L, st));
-  TRY(clv_colsum(dAsum_d, G, B, G, gbd, 1, st));
-  TRY(nt_f32(gates_d, G, Kd + (int64_t)xo * G, G, dZ, Z, BL, Z, G, nullptr, 0, 0, st));
-  TRY(nt_f32(dAsum_d, G, Kd + (int64_t)(xo + Z) * G, G, dW_ext, C, B, C, G, nullptr, 0, 0, st));
+  TRY(fk.fork());
+  TRY(tn_f32(h_d, H, logits, D, gKx, D, H, D, BL, 0, 0, sw));
+  TRY(clv_colsum(logits, D, BL, D, gbx, 1, sw));
+  TRY(clv_lstm_bwd_fused(gates_d, Ud, c_d, dh, dAsum_d, Kd_w, C, dW_ext, 0, Kd_z, Z, dZ, B, L, H, st));
+  TRY(fk.fork());
+  if (c->use_x_prev) TRY(tn_u8(roll, off, L, 0, D, gates_d, G, gKd, G, D, G, BL, sw));
+  TRY(tn_f32(Zs, Z, gates_d, G, gKd + (int64_t)xo * G, G, Z, G, BL, 0, 0, sw));
+  TRY(tn_f32(W, C, dAsum_d, G, gKd + (int64_t)(xo + Z) * G, G, C, G, B, 0, 0, sw));
+  TRY(tn_f32(h_d, H, gates_d, G, gUd, G, H, G, BL, -1, L, sw));
+  TRY(clv_colsum(dAsum_d, G, B, G, gbd, 1, sw));
+  // K2b bwd overwrites dh: its only reader (decoder BPTT) is ordered before it on st
   TRY(clv_gauss_heads_bwd(h_e, Kzm, Kzv, eps_z, Zargs, dZ, dh, gKzm, gbzm, gKzv, gbzv, BL, H, Z,
                           c->kl_weight * sbl, 0, st));
-  TRY(clv_lstm_bwd(gates_e, Ue, h_e, c_e, dh, dAsum_e, B, L, H, st));
-  TRY(tn_u8(roll, off, L, sx, D, gates_e, G, gKe, G, D, G, BL, st));
-  TRY(tn_f32(W, C, dAsum_e, G, gKe + (int64_t)D * G, G, C, G, B, 0, 0, st));
-  TRY(tn_f32(h_e, H, gates_e, G, gUe, G, H, G, BL, -1, L, st));
-  TRY(clv_colsum(dAsum_e, G, B, G, gbe, 1, st));
-  TRY(nt_f32(dAsum_e, G, Ke + (int64_t)D * G, G, dW_ext, C, B, C, G, nullptr, 0, 1, st));
-  TRY(clv_logitnormal_bwd(Wargs, 2 * C1, eps_w, labels, W, dW_ext, dWargs, B, C,
-                          c->w_log_var_prior, c->class_weight * sb, c->w_kl_weight * sb, st));
-  TRY(tn_f32(hW, D, dWargs, 2 * C1, gKwa, 2 * C1, D, 2 * C1, B, 0, 0, st));
-  TRY(clv_colsum(dWargs, 2 * C1, B, 2 * C1, gbwa, 1, st));
-  TRY(nt_f32(dWargs, 2 * C1, Kwa, 2 * C1, dhW, D, B, D, 2 * C1, hW, D, 0, st));
-  TRY(tn_u8(roll, off, 1, sx, D, dhW, D, gKhw, D, L * D, D, B, st));
-  TRY(clv_colsum(dhW, D, B, D, gbhw, 1, st));
+  TRY(clv_lstm_bwd_fused(gates_e, Ue, c_e, dh, dAsum_e, Ke_w, C, dW_ext, 1, nullptr, 0, nullptr, B, L, H, st));
+  TRY(fk.fork());
+  TRY(tn_u8(roll, off, L, sx, D, gates_e, G, gKe, G, D, G, BL, sw));
+  TRY(tn_f32(W, C, dAsum_e, G, gKe + (int64_t)D * G, G, C, G, B, 0, 0, sw));
+  TRY(tn_f32(h_e, H, gates_e, G, gUe, G, H, G, BL, -1, L, sw));
+  TRY(clv_colsum(dAsum_e, G, B, G, gbe, 1, sw));
+  TRY(clv_keyenc_bwd(Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, B, C, D,
+                     c->w_log_var_prior, c->class_weight * sb, c->w_kl_weight * sb, st));
+  TRY(fk.fork());
+  TRY(tn_f32(hW, D, dWargs, 2 * C1, gKwa, 2 * C1, D, 2 * C1, B, 0, 0, sw));
+  TRY(clv_colsum(dWargs, 2 * C1, B, 2 * C1, gbwa, 1, sw));
+  TRY(tn_u8(roll, off, 1, sx, D, dhW, D, gKhw, D, L * D, D, B, sw));
+  TRY(clv_colsum(dhW, D, B, D, gbhw, 1, sw));
+  TRY(fk.join());
   return CLV_OK;
 }
 
@@ -302,6 +382,18 @@ int vae_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uin
 unsigned long long g_clv_launches = 0;
 extern "C" int clv_version(void) { return 100; }
 extern "C" int64_t clv_launch_count(void) { return (int64_t)g_clv_launches; }
+
+extern "C" int clv_runtime_init(void) {
+  int dev = 0;
+  CLV_CUDA(cudaGetDevice(&dev));
+  if (dev >= 16) return CLV_E_UNSUPPORTED;
+  SideStream& s = g_side[dev];
+  if (s.ready) return CLV_OK;
+  CLV_CUDA(cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; ++i) CLV_CUDA(cudaEventCreateWithFlags(&s.ev[i], cudaEventDisableTiming));
+  s.ready = true;
+  return CLV_OK;
+}
 
 extern "C" const char* clv_error_string(int code) {
   switch (code) {

@@ -40,7 +40,8 @@ class Engine:
     def __init__(self, model, B, L=1, D=88, H=88, Z=2, n_classes=2, use_x_prev=False, Hc=88,
                  class_weight=1.0, kl_weight=1.0, w_kl_weight=1.0, w_log_var_prior=0.0,
                  optimizer="adam-wn", lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-8,
-                 seed=0, device=None, world_size=1, rank=0, process_group=None, use_graph=True):
+                 seed=0, device=None, world_size=1, rank=0, process_group=None, use_graph=True,
+                 overlap_wgrad=True):
         _require_cuda()
         lib()
         if optimizer not in ("adam-wn", "adam"):
@@ -59,6 +60,10 @@ class Engine:
         self.world_size, self.rank, self.pg = world_size, rank, process_group
         self.seed = (int(seed) * 1000003 + rank * 7919 + 1) & 0xFFFFFFFFFFFFFFFF
         self.use_graph = use_graph
+        self.overlap_wgrad = bool(overlap_wgrad)
+        if self.overlap_wgrad:
+            with torch.cuda.device(self.dev):
+                check(lib().clv_runtime_init(), "clv_runtime_init")
         self.names = VRNN_TENSORS if self.model == 0 else VAE_TENSORS
         cfg = self.cfg()
         self.P, self.offs, self.rows, self.cols = _lib.param_layout(cfg)
@@ -87,7 +92,8 @@ class Engine:
     def cfg(self, **over):
         kw = dict(model=self.model, B=self.B, L=self.L, D=self.D, H=self.H, Z=self.Z, C_=self.C,
                   use_x_prev=self.use_x_prev, Hc=self.Hc, B_global=self.B * self.world_size,
-                  seed=self.seed, x_shift=self.x_shift, **self.hyper)
+                  seed=self.seed, x_shift=self.x_shift, overlap_wgrad=int(self.overlap_wgrad),
+                  **self.hyper)
         kw.update(over)
         return _lib.make_cfg(**kw)
 

@@ -34,6 +34,9 @@ extern "C" {
 
 int clv_version(void);
 int64_t clv_launch_count(void); /* diagnostic: kernels launched by this library so far */
+/* Once per process and device, OUTSIDE stream capture: creates the auxiliary stream + events used
+ * when clv_cfg.overlap_wgrad is set.  Optional: without it everything runs on `stream`. */
+int clv_runtime_init(void);
 const char* clv_error_string(int code);
 
 /* ---------------------------------------------------------------- model description ------- */
@@ -57,6 +60,8 @@ typedef struct clv_cfg {
   int32_t x_shift;      /* frame of `current` inside a window; 0 = default (1 with use_x_prev
                            [history = frames 0..L-1, current = 1..L], else 0).  L for windows
                            stored as [history | current] when the two inputs do not overlap     */
+  int32_t overlap_wgrad;/* 1: run the weight-gradient GEMMs on the library's auxiliary stream
+                           (needs clv_runtime_init()); forked from / joined into `stream`       */
   uint64_t seed;        /* Philox key for gen_noise (make it rank-dependent)                  */
 } clv_cfg;
 
@@ -94,6 +99,9 @@ typedef struct clv_gemm_args {
                                    already hold the value to add to; no bias/act allowed)       */
 } clv_gemm_args;
 int clv_gemm(const clv_gemm_args* args, void* stream);
+/* C[M,N] = act(C + bias[N])  -- epilogue of a split-K forward GEMM */
+int clv_bias_act(float* C, int64_t ldc, int32_t M, int32_t N, const float* bias, int32_t relu,
+                 void* stream);
 /* out[N] (+)= sum_m A[m,N]  (bias gradients) */
 int clv_colsum(const float* A, int64_t lda, int32_t M, int32_t N, float* out, int32_t accumulate,
                void* stream);
@@ -141,6 +149,19 @@ int clv_lstm_fwd(float* gates, const float* U, float* h, float* c, const float* 
 int clv_lstm_bwd(float* gates, const float* U, const float* h, const float* c, const float* dh_out,
                  float* dAsum, int32_t B, int32_t L, int32_t H, void* stream);
 
+/* Fused forms used by clv_train_step.  Forward: the input terms that are not a GEMM over the roll are
+ * folded into the recurrence: a_t = (has_xproj ? gates[b,t,:] : 0) + bias + Wv[b,:] @ Ww (the
+ * RepeatVector(W) columns; Ww = [C,4H] rows of the kernel) + Zs[b,t,:] @ Kz (the Z columns; Kz =
+ * [Z,4H]) + h_{t-1} @ U.  Any of bias / Wv / Zs may be null.  Backward additionally emits
+ * dZ[B,L,Z] = dA @ Kz^T and dW_ext[B,C] (+)= dAsum @ Ww^T (either may be null). */
+int clv_lstm_fwd_fused(float* gates, int32_t has_xproj, const float* U, const float* bias,
+                       const float* Wv, const float* Ww, int32_t C, const float* Zs, const float* Kz,
+                       int32_t Z, float* h, float* c, int32_t B, int32_t L, int32_t H, void* stream);
+int clv_lstm_bwd_fused(float* gates, const float* U, const float* c, const float* dh_out, float* dAsum,
+                       const float* Ww, int32_t C, float* dW_ext, int32_t dW_accumulate,
+                       const float* Kz, int32_t Z, float* dZ, int32_t B, int32_t L, int32_t H,
+                       void* stream);
+
 /* ---------------------------------------------------------------- K4: Bernoulli loss ------ */
 /* vae_loss = 88*mean_k Keras-BCE with clip->logit semantics, fused with its backward
  * (cl_vrnn/model.py:241-242; cl_vae/model.py:190-191).  logits[R,D] are overwritten with
@@ -149,6 +170,29 @@ int clv_lstm_bwd(float* gates, const float* U, const float* h, const float* c, c
 int clv_bernoulli_ce_fwd_bwd(float* logits, const uint8_t* roll, const int32_t* x_off,
                              int32_t x_grp, int32_t x_shift, float* loss_acc, int64_t R, int32_t D,
                              float scale, int32_t do_backward, void* stream);
+
+/* K1+K4 fused for the sigmoid head (H = D = 88): logits = h @ Kx + bx, the Bernoulli loss above,
+ * dlogits[R,D] and dh[R,H] = dlogits @ Kx^T in ONE pass over h with Kx resident in shared memory
+ * (cl_vrnn/model.py:229-234,241-242 and their backward). */
+int clv_xhead_fwd_bwd(const float* h, const float* Kx, const float* bx, const uint8_t* roll,
+                      const int32_t* x_off, int32_t x_grp, int32_t x_shift, float* loss_acc,
+                      float* dlogits, float* dh, int64_t R, int32_t H, int32_t D, float scale,
+                      int32_t do_backward, void* stream);
+
+/* ---------------------------------------------------------------- key encoder (fused) ------ */
+/* hW = relu(flat(window) @ Khw + b) as a gather-sum over the SET keys of the binary window (exact
+ * fp32), Wargs = hW @ Kwa + b, then K2 forward -- one CTA per sequence (cl_vrnn/model.py:174-191,
+ * 244-255,264).  Needs L*D <= 65535 and D % 4 == 0 (clv_train_step falls back to K1+K2 otherwise). */
+int clv_keyenc_fwd(const uint8_t* roll, const int32_t* win_off, int32_t shift, int32_t L, int32_t D,
+                   const float* Khw, const float* bhw, const float* Kwa, const float* bwa, float* eps_w,
+                   const int32_t* labels, float* hW, float* Wargs, float* W, float* loss_acc, int32_t B,
+                   int32_t C, float w_log_var_prior, float scale_b, int32_t gen_noise, uint64_t seed,
+                   const uint64_t* ctr, void* stream);
+/* K2 backward + dgrad through Wargs and the ReLU of hW: dWargs[B,2(C-1)], dhW[B,D]. */
+int clv_keyenc_bwd(const float* Wargs, const float* eps_w, const int32_t* labels, const float* W,
+                   const float* dW_ext, const float* Kwa, const float* hW, float* dWargs, float* dhW,
+                   int32_t B, int32_t C, int32_t D, float w_log_var_prior, float cw_over_B,
+                   float wkl_over_B, void* stream);
 
 /* ---------------------------------------------------------------- K6: Adam + weight-norm -- */
 /* AdamWithWeightnorm.get_updates (utils/weightnorm.py:75-143,146-178) on the flat buffers.

@@ -283,3 +283,97 @@ def test_adamwn_matches_oracle_trajectory(weightnorm):
         for k in e.names:
             assert util.rel_err(got[k].reshape(-1), params[k].numpy().reshape(-1)) < TOL, (step, k)
     assert e.iterations == 4
+
+
+# ---------------------------------------------------------------------------- fused kernels
+@pytest.mark.parametrize("R,grp", [(3200, 16), (45, 5)])
+def test_xhead_fused_matches_gemm_plus_bernoulli(R, grp):
+    _lib, L, check, ptr, st = _env()
+    rng = np.random.default_rng(R)
+    D = H = 88
+    h = rng.normal(0, 1.0, size=(R, H)); Kx = rng.normal(0, 0.3, size=(H, D)); bx = rng.normal(0, 0.3, D)
+    roll = (rng.random((R + 40, D)) < 0.1).astype(np.uint8)
+    nseq = R // grp
+    off = (np.arange(nseq) * (grp + 1)).astype(np.int32)
+    rows = (off[:, None] + 1 + np.arange(grp)[None, :]).reshape(-1)
+    x = roll[rows].astype(np.float32)
+    logits = (h @ Kx + bx)
+    loss_ref, dl_ref = M.bernoulli_fwd_bwd(logits.astype(np.float32), x, np.float32(1.0 / R))
+    dh_ref = dl_ref.astype(np.float64) @ Kx.T
+    dl = torch.zeros(R, D, device="cuda"); dh = torch.zeros(R, H, device="cuda")
+    loss = torch.zeros(8, device="cuda")
+    check(L.clv_xhead_fwd_bwd(ptr(dev(h)), ptr(dev(Kx)), ptr(dev(bx)), ptr(dev(roll, torch.uint8)),
+                              ptr(dev(off, torch.int32)), grp, 1, ptr(loss), ptr(dl), ptr(dh), R, H, D,
+                              1.0 / R, 1, st))
+    torch.cuda.synchronize()
+    assert abs(loss.cpu().numpy()[0] - loss_ref.astype(np.float64).mean()) < TOL * loss_ref.mean()
+    assert util.rel_err(dl.cpu().numpy(), dl_ref) < TOL
+    assert util.rel_err(dh.cpu().numpy(), dh_ref) < TOL
+
+
+@pytest.mark.parametrize("B_,Lq,Cc,dens", [(200, 16, 10, 0.05), (7, 3, 2, 0.5), (3, 64, 16, 0.0)])
+def test_keyenc_fused_fwd_bwd(B_, Lq, Cc, dens):
+    _lib, L, check, ptr, st = _env()
+    rng = np.random.default_rng(B_ + Lq)
+    D, C1 = 88, Cc - 1
+    roll = (rng.random((B_ * (Lq + 1) + 3, D)) < dens).astype(np.uint8)
+    off = (np.arange(B_) * (Lq + 1)).astype(np.int32)
+    X = np.stack([roll[o + 1:o + 1 + Lq] for o in off]).reshape(B_, -1).astype(np.float64)
+    Khw = rng.normal(0, 0.1, (Lq * D, D)); bhw = rng.normal(0, 0.1, D)
+    Kwa = rng.normal(0, 0.3, (D, 2 * C1)); bwa = rng.normal(0, 0.1, 2 * C1)
+    eps = rng.standard_normal((B_, C1)); labels = rng.integers(0, Cc, B_).astype(np.int32)
+    wt = O.one_hot(labels, Cc).numpy()
+    hW = np.maximum(X @ Khw + bhw, 0); Wa = hW @ Kwa + bwa
+    W, wkl, wrec, corr = M.logitnormal_fwd(Wa[:, :C1], Wa[:, C1:], eps, wt, Cc, 0.1)
+    hWd = torch.zeros(B_, D, device="cuda"); Wad = torch.zeros(B_, 2 * C1, device="cuda")
+    Wd = torch.zeros(B_, Cc, device="cuda"); loss = torch.zeros(8, device="cuda"); epsd = dev(eps)
+    Kwad, labd = dev(Kwa), dev(labels, torch.int32)
+    check(L.clv_keyenc_fwd(ptr(dev(roll, torch.uint8)), ptr(dev(off, torch.int32)), 1, Lq, D, ptr(dev(Khw)),
+                           ptr(dev(bhw)), ptr(Kwad), ptr(dev(bwa)), ptr(epsd), ptr(labd), ptr(hWd), ptr(Wad),
+                           ptr(Wd), ptr(loss), B_, Cc, 0.1, 1.0 / B_, 0, 0, None, st))
+    torch.cuda.synchronize()
+    assert util.rel_err(hWd.cpu().numpy(), hW) < TOL
+    assert util.rel_err(Wad.cpu().numpy(), Wa) < TOL
+    assert util.rel_err(Wd.cpu().numpy(), W) < TOL
+    lo = loss.cpu().numpy()
+    assert abs(lo[1] - wkl.mean()) < TOL * abs(wkl.mean()) and abs(lo[2] - wrec.mean()) < TOL * abs(wrec.mean())
+    assert abs(lo[4] - corr.mean()) < 1e-6
+    dW_ext = rng.normal(size=(B_, Cc))
+    dWm, dWlv = M.logitnormal_bwd(Wa[:, :C1], Wa[:, C1:], eps, wt, W, dW_ext, Cc, 0.1, 0.7 / B_, 0.9 / B_)
+    dWa_ref = np.concatenate([dWm, dWlv], -1)
+    dhW_ref = (dWa_ref @ Kwa.T) * (hW > 0)
+    dWa = torch.zeros(B_, 2 * C1, device="cuda"); dhW = torch.zeros(B_, D, device="cuda")
+    check(L.clv_keyenc_bwd(ptr(Wad), ptr(epsd), ptr(labd), ptr(Wd), ptr(dev(dW_ext)), ptr(Kwad), ptr(hWd),
+                           ptr(dWa), ptr(dhW), B_, Cc, D, 0.1, 0.7 / B_, 0.9 / B_, st))
+    torch.cuda.synchronize()
+    assert util.rel_err(dWa.cpu().numpy(), dWa_ref) < TOL
+    assert util.rel_err(dhW.cpu().numpy(), dhW_ref) < TOL
+
+
+@pytest.mark.parametrize("B_,L,Z,Cc,has_x", [(200, 16, 2, 10, 1), (5, 7, 4, 3, 0), (19, 3, 16, 16, 1)])
+def test_lstm_fused_input_terms_and_extra_gradients(B_, L, Z, Cc, has_x):
+    _lib, Lb, check, ptr, st = _env()
+    rng = np.random.default_rng(B_ * 10 + L)
+    H, G = 88, 352
+    xp = rng.normal(0, 1.0, size=(B_, L, G)) * has_x
+    U = rng.normal(0, 0.15, size=(H, G)); bias = rng.normal(0, 0.2, G)
+    Wv = rng.dirichlet(np.ones(Cc), B_); Ww = rng.normal(0, 0.4, (Cc, G))
+    Zs = rng.normal(size=(B_, L, Z)); Kz = rng.normal(0, 0.4, (Z, G))
+    xproj = xp + bias + (Wv @ Ww)[:, None, :] + Zs @ Kz
+    hs, cs, a_all = M.lstm_fwd(xproj, U)
+    gates = dev(xp); Ud = dev(U); Wwd, Kzd = dev(Ww), dev(Kz)
+    hd = torch.zeros(B_, L, H, device="cuda"); cd = torch.zeros(B_, L, H, device="cuda")
+    check(Lb.clv_lstm_fwd_fused(ptr(gates), has_x, ptr(Ud), ptr(dev(bias)), ptr(dev(Wv)), ptr(Wwd), Cc,
+                                ptr(dev(Zs)), ptr(Kzd), Z, ptr(hd), ptr(cd), B_, L, H, st))
+    torch.cuda.synchronize()
+    assert util.rel_err(hd.cpu().numpy(), hs) < TOL and util.rel_err(cd.cpu().numpy(), cs) < TOL
+    dh_out = rng.normal(size=(B_, L, H))
+    dA = M.lstm_bwd(dh_out, hs, cs, a_all, U)
+    dAsum = torch.zeros(B_, G, device="cuda"); dZ = torch.zeros(B_, L, Z, device="cuda")
+    base = rng.normal(size=(B_, Cc)); dWe = dev(base)
+    check(Lb.clv_lstm_bwd_fused(ptr(gates), ptr(Ud), ptr(cd), ptr(dev(dh_out)), ptr(dAsum), ptr(Wwd), Cc,
+                                ptr(dWe), 1, ptr(Kzd), Z, ptr(dZ), B_, L, H, st))
+    torch.cuda.synchronize()
+    assert util.rel_err(gates.cpu().numpy(), dA) < TOL
+    assert util.rel_err(dZ.cpu().numpy(), dA @ Kz.T) < TOL
+    assert util.rel_err(dWe.cpu().numpy(), base + dA.sum(1) @ Ww.T) < TOL
