@@ -69,8 +69,24 @@ lstm_fwd_kernel(float* __restrict__ gates, const float* __restrict__ U, float* _
   }
   __syncthreads();
 
+  // software pipeline: the hoisted projection of step t+1 is loaded while step t computes
+  float xpre[RMAX / 2];
+#pragma unroll
+  for (int q = 0; q < RMAX / 2; ++q) {
+    const int r = 2 * q + ks;
+    xpre[q] = (ex.has_xproj && r < nrows) ? gates[((size_t)(b0 + r) * L) * G + n] : 0.f;
+  }
+
   for (int t = 0; t < L; ++t) {
     // ---- a = xproj_t + h_{t-1} @ U
+    float xcur[RMAX / 2];
+#pragma unroll
+    for (int q = 0; q < RMAX / 2; ++q) {
+      xcur[q] = xpre[q];
+      const int r = 2 * q + ks;
+      if (ex.has_xproj && r < nrows && t + 1 < L)
+        xpre[q] = gates[((size_t)(b0 + r) * L + t + 1) * G + n];
+    }
 #pragma unroll
     for (int rr = 0; rr < RMAX / RC; ++rr) {
       const int r0 = rr * RC;
@@ -82,8 +98,7 @@ lstm_fwd_kernel(float* __restrict__ gates, const float* __restrict__ U, float* _
         float v = 0.f;
         if (r < nrows) {
           const size_t bt = (size_t)(b0 + r) * L + t;
-          v = cb[rr * (RC / 2) + q];
-          if (ex.has_xproj) v += gates[bt * G + n];
+          v = cb[rr * (RC / 2) + q] + xcur[rr * (RC / 2) + q];
           for (int j = 0; j < Z; ++j) v = fmaf(__ldg(ex.Zs + bt * Z + j), kz_s[j][n], v);
         }
         xv[q] = v;
@@ -166,6 +181,23 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
   for (int s = 0; s < SLOTS; ++s) asum[s][0] = asum[s][1] = asum[s][2] = asum[s][3] = 0.f;
   __syncthreads();
 
+  // software pipeline: operands of the cell phase of step t-1 are loaded during step t
+  float pg[SLOTS][4], pc2[SLOTS], pdh[SLOTS], pct[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int cell = tid + s * NT;
+    pg[s][0] = pg[s][1] = pg[s][2] = pg[s][3] = pc2[s] = pdh[s] = pct[s] = 0.f;
+    if (cell < nrows * H) {
+      const int r = cell / H, j = cell - r * H;
+      const size_t base = (size_t)(b0 + r) * L + (L - 1);
+      const float* gp = gates + base * G + j;
+      pg[s][0] = gp[0]; pg[s][1] = gp[H]; pg[s][2] = gp[2 * H]; pg[s][3] = gp[3 * H];
+      pct[s] = __ldg(c + base * H + j);
+      pc2[s] = (L > 1) ? __ldg(c + (base - 1) * H + j) : 0.f;
+      pdh[s] = __ldg(dh_out + base * H + j);
+    }
+  }
+
   for (int t = L - 1; t >= 0; --t) {
     // ---- cell phase: dLoss/d(pre-activations) for step t
 #pragma unroll
@@ -175,10 +207,16 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
         const int r = cell / H, j = cell - r * H;
         const size_t base = (size_t)(b0 + r) * L + t;
         float* gp = gates + base * G + j;
-        const float ig = gp[0], fg = gp[H], gg = gp[2 * H], og = gp[3 * H];
-        const float ct = __ldg(c + base * H + j);
-        const float cprev = (t > 0) ? __ldg(c + (base - 1) * H + j) : 0.f;
-        const float dh = __ldg(dh_out + base * H + j) + dhrec_s[r][j];
+        const float ig = pg[s][0], fg = pg[s][1], gg = pg[s][2], og = pg[s][3];
+        const float ct = pct[s], cprev = pc2[s];
+        const float dh = pdh[s] + dhrec_s[r][j];
+        if (t > 0) {   // issue next step's loads now; they land during the mat-vec below
+          const float* gq = gp - G;
+          pg[s][0] = gq[0]; pg[s][1] = gq[H]; pg[s][2] = gq[2 * H]; pg[s][3] = gq[3 * H];
+          pct[s] = cprev;
+          pc2[s] = (t > 1) ? __ldg(c + (base - 2) * H + j) : 0.f;
+          pdh[s] = __ldg(dh_out + (base - 1) * H + j);
+        }
         const float tc = tanhf(ct);
         const float d_o = dh * tc;
         const float dc = fmaf(dh * og, 1.0f - tc * tc, dc_s[r][j]);

@@ -1,0 +1,51 @@
+"""Micro-benchmark of individual libclv_b200 kernels (CUDA events, warm L2 = the in-step condition,
+and cold = L2 flushed before every launch).  Usage: python profiles/kbench.py [B] [L]"""
+import ctypes as C
+import os
+import sys
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import clvae_b200  # noqa: F401
+from clvae_b200._lib import lib, check, ptr
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+L = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+H, G, D, Cc, Z = 88, 352, 88, 10, 2
+dev = torch.device("cuda")
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+gates = torch.randn(B, L, G, device=dev) * 0.5
+U = torch.randn(H, G, device=dev) * 0.1
+h = torch.zeros(B, L, H, device=dev); c = torch.zeros(B, L, H, device=dev)
+dh = torch.randn(B, L, H, device=dev); dAsum = torch.zeros(B, G, device=dev)
+bias = torch.zeros(G, device=dev); Wv = torch.rand(B, Cc, device=dev); Ww = torch.randn(Cc, G, device=dev) * 0.1
+Zs = torch.randn(B, L, Z, device=dev); Kz = torch.randn(Z, G, device=dev) * 0.1
+dZ = torch.zeros(B, L, Z, device=dev); dW = torch.zeros(B, Cc, device=dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(name, fn, reps=50):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record(); torch.cuda.synchronize()
+    warm = a.elapsed_time(b) / reps * 1e3
+    tot = 0.0
+    for _ in range(10):
+        flush.zero_()
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    print("%-28s B=%d L=%d  warm %8.1f us   cold %8.1f us" % (name, B, L, warm, tot / 10 * 1e3), flush=True)
+
+
+L_ = lib()
+timeit("lstm_fwd", lambda: check(L_.clv_lstm_fwd(ptr(gates), ptr(U), ptr(h), ptr(c), None, None, B, L, H, st)))
+timeit("lstm_fwd_fused(W,Z)", lambda: check(L_.clv_lstm_fwd_fused(ptr(gates), 1, ptr(U), ptr(bias), ptr(Wv), ptr(Ww), Cc,
+                                                              ptr(Zs), ptr(Kz), Z, ptr(h), ptr(c), B, L, H, st)))
+timeit("lstm_bwd", lambda: check(L_.clv_lstm_bwd(ptr(gates), ptr(U), ptr(h), ptr(c), ptr(dh), ptr(dAsum), B, L, H, st)))
+timeit("lstm_bwd_fused(dW,dZ)", lambda: check(L_.clv_lstm_bwd_fused(ptr(gates), ptr(U), ptr(c), ptr(dh), ptr(dAsum), ptr(Ww), Cc,
+                                                                ptr(dW), 0, ptr(Kz), Z, ptr(dZ), B, L, H, st)))

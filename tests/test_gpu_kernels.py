@@ -292,7 +292,7 @@ def test_xhead_fused_matches_gemm_plus_bernoulli(R, grp):
     rng = np.random.default_rng(R)
     D = H = 88
     h = rng.normal(0, 1.0, size=(R, H)); Kx = rng.normal(0, 0.3, size=(H, D)); bx = rng.normal(0, 0.3, D)
-    roll = (rng.random((R + 40, D)) < 0.1).astype(np.uint8)
+    roll = (rng.random((R + R // grp + 40, D)) < 0.1).astype(np.uint8)
     nseq = R // grp
     off = (np.arange(nseq) * (grp + 1)).astype(np.int32)
     rows = (off[:, None] + 1 + np.arange(grp)[None, :]).reshape(-1)
