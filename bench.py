@@ -371,8 +371,19 @@ def main():
         if B != CFG["B"] or L != CFG["L"]:
             line["config"]["workload"] = "cl_vrnn train step, synthetic sweep point B=%d/GPU L=%d" % (B, L)
         print(json.dumps(line), flush=True)
+    # teardown: NCCL kernels captured in CUDA graphs must be released before the communicator goes
+    # away; a watchdog guarantees the process exits even if the communicator teardown stalls
+    sys.stdout.flush()
     if world > 1:
+        import threading
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e._graphs.clear()
+        del model
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+    os._exit(0)
 
 
 if __name__ == "__main__":
