@@ -51,6 +51,8 @@ PROTOTYPES = {
     "clv_error_string": (C.c_char_p, [C.c_int]),
     "clv_param_layout": (_I64, [_CFG, C.POINTER(_I64), C.POINTER(_I32), C.POINTER(_I32)]),
     "clv_gemm": (C.c_int, [C.POINTER(clv_gemm_args), _P]),
+    "clv_inproj_tc_scratch_bytes": (_I64, []),
+    "clv_inproj_tc": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _I64, _I32, _P, _P, _I64, _I64, _P, _I64, _I32, _P]),
     "clv_bias_act": (C.c_int, [_P, _I64, _I32, _I32, _P, _I32, _P]),
     "clv_colsum": (C.c_int, [_P, _I64, _I32, _I32, _P, _I32, _P]),
     "clv_logitnormal_fwd": (C.c_int, [_P, _I64, _P, _P, _P, _P, _I32, _I32, _F, _F, _I32, _U64, _P, _P]),

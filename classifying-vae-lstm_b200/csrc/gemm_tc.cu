@@ -1,0 +1,274 @@
+// K1 (tensor-core form): the hoisted LSTM input projection  C[M,352] = roll_u8[M,D] @ W[D,352]
+// on 5th-gen tensor cores (tcgen05.mma, accumulator in TMEM), fp32-exact:
+//   * A = piano-roll rows (uint8 {0,1}, gathered by window offset) -> bf16 in shared memory, exact;
+//   * B = fp32 weights split into bf16 hi + mid + lo (3 x 8 = 24 mantissa bits).  Since A is 0/1 every
+//     product is exact and D = A*hi + A*mid + A*lo accumulates in fp32 in TMEM;
+//   * the split/transposed weight image is built once per step by a tiny prep kernel directly in the
+//     UMMA canonical K-major (no-swizzle) shared-memory layout, so each CTA pulls it with three
+//     cp.async.bulk (TMA) copies completing on an mbarrier;
+//   * one elected thread issues the 18 MMAs (3 splits x 6 k-steps of 16) per 128x176 tile and commits
+//     to an mbarrier; four epilogue warps read TMEM with tcgen05.ld, add the optional per-sequence
+//     addend and store coalesced rows.
+// CTAs are persistent over row tiles (grid = 2 N-halves x ~SM/2), so the weight image is fetched once
+// per CTA.  Replaces the MatMul of `x @ kernel` inside Keras' LSTM preprocess_input
+// (cl_vrnn/model.py:196-199,225-228 [K2-recall]).
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int TM = 128;              // rows per tile (UMMA M)
+constexpr int TN = 176;              // columns per CTA (UMMA N); 2 halves cover 4H = 352
+constexpr int KP = 96;               // K padded to a multiple of 16 (D <= 96)
+constexpr int NSPLIT = 3;            // bf16 hi / mid / lo
+constexpr int LBO = 128;             // bytes between the two K core matrices of one MMA
+constexpr int SBO_A = (KP / 8) * 128;  // bytes between 8-row groups (A and B images share the form)
+constexpr int A_BYTES = TM * KP * 2;           // 24 576
+constexpr int B_SPLIT_BYTES = TN * KP * 2;     // 33 792
+constexpr int B_BYTES = NSPLIT * B_SPLIT_BYTES;  // 101 376 per N-half
+constexpr int TMEM_COLS = 256;
+constexpr int NTHREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// UMMA shared-memory descriptor: K-major, no swizzle, version 1 (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ULL << 46);
+}
+// instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major (cute::UMMA::InstrDescriptor)
+__device__ __forceinline__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- weight prep: fp32 [K, ldw] -> 2 halves x 3 splits of bf16 in the canonical K-major image
+__global__ void wsplit_kernel(const float* __restrict__ W, int64_t ldw, int K,
+                              __nv_bfloat16* __restrict__ img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over 352 x KP
+  if (idx >= 2 * TN * KP) return;
+  const int n = idx / KP, k = idx - n * KP;                // n in [0,352)
+  const float w = (k < K) ? __ldg(W + (int64_t)k * ldw + n) : 0.f;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+  const float r1 = w - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(mid);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
+  const int half = n / TN, nn = n - half * TN;
+  const size_t off = (size_t)(nn >> 3) * (SBO_A / 2) + (size_t)(k >> 3) * (LBO / 2) + (nn & 7) * 8 + (k & 7);
+  __nv_bfloat16* base = img + (size_t)half * (B_BYTES / 2);
+  base[off] = hi;
+  base[off + B_SPLIT_BYTES / 2] = mid;
+  base[off + 2 * (B_SPLIT_BYTES / 2)] = lo;
+}
+
+struct TcArgs {
+  const uint8_t* roll; const int32_t* off; int grp, shift, D;
+  const __nv_bfloat16* img;
+  float* C; int64_t ldc; int64_t M;
+  const float* rowadd; int64_t ldra; int ra_grp;
+  int tiles;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) inproj_tc_kernel(const TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* a_s = smem;                       // A tile, canonical K-major bf16; reused as staging
+  uint8_t* b_s = smem + A_BYTES;             // 3 split images of this N-half
+  __shared__ __align__(8) uint64_t bars[2];  // [0] weights landed, [1] MMA done
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = blockIdx.y;
+  const uint32_t bar_b = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+
+  if (tid == 0) {
+    mbar_init(bar_b, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+
+  if (tid == 0) {   // weights: three bulk (TMA) copies completing on one mbarrier
+    mbar_expect_tx(bar_b, B_BYTES);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(a.img) + (size_t)half * B_BYTES;
+#pragma unroll
+    for (int s = 0; s < NSPLIT; ++s)
+      bulk_g2s(smem_u32(b_s) + s * B_SPLIT_BYTES, src + (size_t)s * B_SPLIT_BYTES, B_SPLIT_BYTES, bar_b);
+  }
+
+  uint32_t mma_phase = 0;
+  for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
+    const int64_t m0 = (int64_t)tile * TM;
+    // ---- A tile: 2 threads per row, 6 core-matrix columns (48 keys) each; u8 {0,1} -> bf16
+    {
+      const int row = tid >> 1, part = tid & 1;
+      const int64_t m = m0 + row;
+      const uint8_t* src = nullptr;
+      if (m < a.M) {
+        const uint32_t mu = (uint32_t)m, g = mu / (uint32_t)a.grp;
+        src = a.roll + ((int64_t)__ldg(a.off + g) + a.shift + (mu - g * a.grp)) * a.D;
+      }
+      uint8_t* dst = a_s + (row >> 3) * SBO_A + (row & 7) * 16;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int k0 = (part * 6 + j) * 8;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (src && k0 < a.D) {
+          const uint2 v = __ldg(reinterpret_cast<const uint2*>(src + k0));   // 8 keys (D % 8 == 0)
+          const uint32_t b[2] = {v.x, v.y};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const uint32_t bit = (b[e >> 2] >> (8 * (e & 3))) & 0xffu;
+            if (bit) w[e >> 1] |= 0x3F80u << (16 * (e & 1));                 // bf16(1.0)
+          }
+        }
+        *reinterpret_cast<uint4*>(dst + (part * 6 + j) * LBO) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+    __syncthreads();
+    // ---- MMA: one thread issues 3 splits x 6 k-steps, accumulating in TMEM
+    if (warp == 0) {
+      if (tile == (int)blockIdx.x) mbar_wait(bar_b, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc(TM, TN);
+        const uint32_t a_addr = smem_u32(a_s), b_addr = smem_u32(b_s);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int s = 0; s < NSPLIT; ++s) {
+#pragma unroll
+          for (int kk = 0; kk < KP / 16; ++kk) {
+            const uint64_t ad = umma_desc(a_addr + kk * 2 * LBO, LBO, SBO_A);
+            const uint64_t bd = umma_desc(b_addr + s * B_SPLIT_BYTES + kk * 2 * LBO, LBO, SBO_A);
+            umma_bf16(tmem, ad, bd, idesc, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(bar_mma);
+      }
+      __syncwarp();
+    }
+    // ---- epilogue: warps 4..7 own TMEM lanes 32*(warp%4)..+31 = rows of the tile
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp >= 4) {
+      const int q = warp - 4;
+      float* stage = reinterpret_cast<float*>(a_s) + q * (32 * 17);   // A tile is free after the MMA
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) stage[lane * 17 + i] = __uint_as_float(r[i]);
+        __syncwarp();
+        const int cc = lane & 15, rsub = lane >> 4;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; rr += 2) {
+          const int64_t m = m0 + q * 32 + rr + rsub;
+          if (m < a.M) {
+            const int n = half * TN + c0 + cc;
+            float v = stage[(rr + rsub) * 17 + cc];
+            if (a.rowadd) v += __ldg(a.rowadd + (m / a.ra_grp) * a.ldra + n);
+            a.C[m * a.ldc + n] = v;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();   // TMEM drained and staging free before the next tile overwrites A / re-issues MMAs
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  if (tid == 0 && (int)blockIdx.x >= a.tiles) mbar_wait(bar_b, 0);   // never exit with a copy in flight
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+}  // namespace
+
+extern "C" int64_t clv_inproj_tc_scratch_bytes(void) { return 2 * (int64_t)B_BYTES; }
+
+extern "C" int clv_inproj_tc(const uint8_t* roll, const int32_t* win_off, int32_t grp, int32_t shift,
+                             int32_t D, const float* W, int64_t ldw, int32_t N, void* scratch,
+                             float* C, int64_t ldc, int64_t M, const float* rowadd, int64_t ldra,
+                             int32_t ra_grp, void* stream) {
+  if (!roll || !win_off || !W || !scratch || !C || grp <= 0) return CLV_E_INVALID;
+  if (rowadd && ra_grp <= 0) return CLV_E_INVALID;
+  if (N != 2 * TN || D > KP || (D & 7) || ((uintptr_t)roll & 7) || ((uintptr_t)scratch & 15))
+    return CLV_E_UNSUPPORTED;
+  if (M <= 0) return CLV_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(scratch);
+  wsplit_kernel<<<(2 * TN * KP + 255) / 256, 256, 0, st>>>(W, ldw, D, img);
+  CLV_CHECK_LAUNCH();
+  static bool attr_set = false;
+  const int smem = A_BYTES + B_BYTES + 1024;
+  if (!attr_set) {
+    CLV_CUDA(cudaFuncSetAttribute(inproj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  TcArgs a;
+  a.roll = roll; a.off = win_off; a.grp = grp; a.shift = shift; a.D = D; a.img = img; a.C = C;
+  a.ldc = ldc; a.M = M; a.rowadd = rowadd; a.ldra = ldra; a.ra_grp = ra_grp;
+  a.tiles = (int)((M + TM - 1) / TM);
+  int gx = clv_num_sms() / 2;
+  if (gx > a.tiles) gx = a.tiles;
+  if (gx < 1) gx = 1;
+  inproj_tc_kernel<<<dim3(gx, 2), NTHREADS, smem, st>>>(a);
+  CLV_CHECK_LAUNCH();
+  return CLV_OK;
+}

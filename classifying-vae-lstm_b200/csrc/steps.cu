@@ -11,6 +11,9 @@ extern "C" int clv_lstm_fwd_fused(float*, int32_t, const float*, const float*, c
 extern "C" int clv_lstm_bwd_fused(float*, const float*, const float*, const float*, float*, const float*,
                                   int32_t, float*, int32_t, const float*, int32_t, float*, int32_t,
                                   int32_t, int32_t, void*);
+extern "C" int clv_inproj_tc(const uint8_t*, const int32_t*, int32_t, int32_t, int32_t, const float*, int64_t,
+                             int32_t, void*, float*, int64_t, int64_t, const float*, int64_t, int32_t, void*);
+extern "C" int64_t clv_inproj_tc_scratch_bytes(void);
 extern "C" int clv_xhead_fwd_bwd(const float*, const float*, const float*, const uint8_t*, const int32_t*,
                                  int32_t, int32_t, float*, float*, float*, int64_t, int32_t, int32_t,
                                  float, int32_t, void*);
@@ -70,6 +73,7 @@ Ws carve(const clv_cfg* c) {
     w.add("logits", BL * D); w.add("dh", BL * H);
     w.add("dAsum_d", B * G); w.add("dAsum_e", B * G); w.add("dZ", BL * Z);
     w.add("dW_ext", B * C); w.add("dWargs", B * 2 * C1); w.add("dhW", B * D);
+    w.add("wimg_e", clv_inproj_tc_scratch_bytes() / 4); w.add("wimg_d", clv_inproj_tc_scratch_bytes() / 4);
   } else {
     const int64_t Hc = c->Hc;
     w.add("h_w", B * Hc); w.add("Wargs", B * 2 * C1); w.add("W", B * C);
@@ -194,8 +198,10 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
         *Zs = WSP("Zs"), *rb_d = WSP("rb_d"), *gates_d = WSP("gates_d"), *h_d = WSP("h_d"),
         *c_d = WSP("c_d"), *logits = WSP("logits"), *dh = WSP("dh"), *dAsum_d = WSP("dAsum_d"),
         *dAsum_e = WSP("dAsum_e"), *dZ = WSP("dZ"), *dW_ext = WSP("dW_ext"),
-        *dWargs = WSP("dWargs"), *dhW = WSP("dhW");
+        *dWargs = WSP("dWargs"), *dhW = WSP("dhW"), *wimg_e = WSP("wimg_e"), *wimg_d = WSP("wimg_d");
 #undef WSP
+  // hoisted input projections on tensor cores (tcgen05) when asked for and the shape is the built one
+  const bool tc = c->gemm_algo == 1 && G == 352 && D <= 96 && (D % 8) == 0;
   const float *Khw = P + po[R_HW_K], *bhw = P + po[R_HW_B], *Kwa = P + po[R_WA_K],
               *bwa = P + po[R_WA_B], *Ke = P + po[R_ENC_K], *Ue = P + po[R_ENC_U],
               *be = P + po[R_ENC_B], *Kzm = P + po[R_ZM_K], *bzm = P + po[R_ZM_B],
@@ -216,7 +222,8 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   // ---- decoder input projection of the history roll: depends on nothing but the batch -> side
   if (c->use_x_prev) {
     TRY(fk.fork());
-    TRY(nn_u8(roll, off, L, 0, D, Kd, G, gates_d, G, BL, G, D, nullptr, nullptr, 0, 0, 0, 0, sw));
+    if (tc) TRY(clv_inproj_tc(roll, off, L, 0, D, Kd, G, G, wimg_d, gates_d, G, BL, nullptr, 0, 0, sw));
+    else TRY(nn_u8(roll, off, L, 0, D, Kd, G, gates_d, G, BL, G, D, nullptr, nullptr, 0, 0, 0, 0, sw));
   }
   // ---- key encoder: hW, Wargs, logistic-normal W + its losses (model.py:174-191,244-255,264)
   if (fused_ke) {
@@ -241,7 +248,8 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   }
   // ---- encoder LSTM (model.py:193-199): roll part hoisted as one GEMM; bias and the
   //      RepeatVector(W) columns are folded into the recurrent kernel's per-sequence constant
-  TRY(nn_u8(roll, off, L, sx, D, Ke, G, gates_e, G, BL, G, D, nullptr, nullptr, 0, 0, 0, 0, st));
+  if (tc) TRY(clv_inproj_tc(roll, off, L, sx, D, Ke, G, G, wimg_e, gates_e, G, BL, nullptr, 0, 0, st));
+  else TRY(nn_u8(roll, off, L, sx, D, Ke, G, gates_e, G, BL, G, D, nullptr, nullptr, 0, 0, 0, 0, st));
   TRY(clv_lstm_fwd_fused(gates_e, 1, Ue, be, W, Ke_w, C, nullptr, nullptr, 0, h_e, c_e, B, L, H, st));
   // ---- Z heads + sample + kl (model.py:200-216,236-239)
   TRY(clv_gauss_heads_fwd(h_e, Kzm, bzm, Kzv, bzv, eps_z, Zargs, Zs, loss, BL, H, Z, sbl,

@@ -99,6 +99,15 @@ typedef struct clv_gemm_args {
                                    already hold the value to add to; no bias/act allowed)       */
 } clv_gemm_args;
 int clv_gemm(const clv_gemm_args* args, void* stream);
+/* Tensor-core form of the hoisted LSTM input projection (tcgen05.mma + TMEM + bulk-TMA weight loads):
+ * C[M,N] = roll_u8 rows @ W[D,N] (+ rowadd[m/ra_grp,:]), N = 4H = 352, D <= 96, D % 8 == 0.
+ * fp32-exact: the roll is {0,1} (exact in bf16) and W is split into bf16 hi+mid+lo, accumulated in
+ * fp32 in TMEM.  `scratch` (clv_inproj_tc_scratch_bytes(), 16-byte aligned) receives the split weight
+ * image, rebuilt on every call because the weights change every step. */
+int64_t clv_inproj_tc_scratch_bytes(void);
+int clv_inproj_tc(const uint8_t* roll, const int32_t* win_off, int32_t grp, int32_t shift, int32_t D,
+                  const float* W, int64_t ldw, int32_t N, void* scratch, float* C, int64_t ldc,
+                  int64_t M, const float* rowadd, int64_t ldra, int32_t ra_grp, void* stream);
 /* C[M,N] = act(C + bias[N])  -- epilogue of a split-K forward GEMM */
 int clv_bias_act(float* C, int64_t ldc, int32_t M, int32_t N, const float* bias, int32_t relu,
                  void* stream);

@@ -377,3 +377,29 @@ def test_lstm_fused_input_terms_and_extra_gradients(B_, L, Z, Cc, has_x):
     assert util.rel_err(gates.cpu().numpy(), dA) < TOL
     assert util.rel_err(dZ.cpu().numpy(), dA @ Kz.T) < TOL
     assert util.rel_err(dWe.cpu().numpy(), base + dA.sum(1) @ Ww.T) < TOL
+
+
+# ---------------------------------------------------------------------------- tcgen05 path
+@pytest.mark.parametrize("B_,Lq,shift", [(200, 16, 1), (3, 5, 0), (1000, 33, 1)])
+def test_inproj_tcgen05_is_fp32_exact(B_, Lq, shift):
+    """tcgen05/TMEM input projection vs float64 numpy: the roll is {0,1} and the weights are split into
+    bf16 hi+mid+lo, so the result must agree with fp32 to rounding (not to a bf16 tolerance)."""
+    _lib, L, check, ptr, st = _env()
+    rng = np.random.default_rng(B_ + Lq)
+    D, N = 88, 352
+    roll = (rng.random((B_ * (Lq + 1) + 8, D)) < 0.15).astype(np.uint8)
+    off = (np.arange(B_) * (Lq + 1)).astype(np.int32)
+    Wt = rng.normal(0, 0.3, (D, N)) * np.exp(rng.normal(0, 2, (D, N)))      # wide dynamic range
+    ra = rng.normal(size=(B_, N))
+    X = np.stack([roll[o + shift:o + shift + Lq] for o in off]).reshape(-1, D).astype(np.float64)
+    ref = X @ Wt.astype(np.float32).astype(np.float64) + np.repeat(ra.astype(np.float32).astype(np.float64), Lq, axis=0)
+    M_ = B_ * Lq
+    Cd = torch.full((M_, N), float("nan"), device="cuda")
+    scratch = torch.zeros(L.clv_inproj_tc_scratch_bytes() // 4, device="cuda")
+    check(L.clv_inproj_tc(ptr(dev(roll, torch.uint8)), ptr(dev(off, torch.int32)), Lq, shift, D, ptr(dev(Wt)), N, N,
+                          ptr(scratch), ptr(Cd), N, M_, ptr(dev(ra)), N, Lq, st))
+    torch.cuda.synchronize()
+    got = Cd.cpu().numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < 2e-6, err

@@ -108,3 +108,12 @@ def test_microbatch_accumulation_equals_full_batch():
     torch.cuda.synchronize()
     assert util.rel_err(e0.grads.cpu().numpy(), full.grads.cpu().numpy()) < 1e-5
     assert util.rel_err(e0.loss_acc.cpu().numpy()[:5], full.loss_acc.cpu().numpy()[:5]) < 1e-5
+
+
+def test_vrnn_step_with_tcgen05_input_projections():
+    """gemm_algo=1: the two hoisted input projections run on tcgen05 (bf16x3 split, fp32-exact); the
+    step must hold the same 1e-4 bound as the SIMT path."""
+    case = util.make_vrnn_case(77, 200, 16, C=10, Z=2, use_x_prev=True)
+    out, g = util.oracle_vrnn(case, **KW)
+    e = util.engine_for(case, "vrnn", use_graph=False, gemm_algo=1, **KW)
+    check_step(e, out, g)
