@@ -264,13 +264,18 @@ def main():
            "h2d_bytes_per_step": B * (L + 1) * D + 4 * B, "d2h_bytes_per_step": 32,
            "ms_per_step": ms_e2e, "api": "model.train_on_batch_windows(pinned uint8 [B,L+1,88], int32 labels)"}
 
-    # ---------------- per-kernel timing of the recurrent kernels (dominant) on this batch shape
+    # ---------------- per-kernel timing (CUDA events on the launching stream, L2 flushed between
+    # launches) of the kernels that dominate the step, on this batch shape
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     G = 4 * H
     gates = torch.randn(B, L, G, device=devn) * 0.5
     U = e.view("encoder_h.recurrent_kernel")
     hbuf = torch.zeros(B, L, H, device=devn); cbuf = torch.zeros(B, L, H, device=devn)
     dh = torch.randn(B, L, H, device=devn); dAsum = torch.zeros(B, G, device=devn)
+    dZb = torch.zeros(B, L, Z, device=devn); dWb = torch.zeros(B, Cc, device=devn)
+    Wv = torch.rand(B, Cc, device=devn); Zs = torch.randn(B, L, Z, device=devn)
+    Kd = e.view("decoder_h.kernel"); Ke = e.view("encoder_h.kernel")
+    scratch = torch.zeros(lib().clv_inproj_tc_scratch_bytes() // 4, device=devn)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=devn)
 
     def time_kernel(fn, reps=20):
@@ -285,23 +290,34 @@ def main():
             tot += a.elapsed_time(b)
         return tot / reps
 
-    t_fwd = time_kernel(lambda: check(lib().clv_lstm_fwd(ptr(gates), ptr(U), ptr(hbuf), ptr(cbuf), None, None, B, L, H, st)))
-    t_bwd = time_kernel(lambda: check(lib().clv_lstm_bwd(ptr(gates), ptr(U), ptr(hbuf), ptr(cbuf), ptr(dh), ptr(dAsum), B, L, H, st)))
-    bytes_fwd = 4 * L * (2 * G + 2 * H) * B     # read xproj, write gates + h + c
-    bytes_bwd = 4 * L * (2 * G + 3 * H) * B + 4 * G * B   # read gates,c(x2),dh ; write dA ; dAsum
+    t_fwd = time_kernel(lambda: check(lib().clv_lstm_fwd_fused(
+        ptr(gates), 1, ptr(U), ptr(e.view("decoder_h.bias")), ptr(Wv), ptr(Kd[D + Z:]), Cc, ptr(Zs),
+        ptr(Kd[D:D + Z]), Z, ptr(hbuf), ptr(cbuf), B, L, H, st)))
+    t_bwd = time_kernel(lambda: check(lib().clv_lstm_bwd_fused(
+        ptr(gates), ptr(U), ptr(cbuf), ptr(dh), ptr(dAsum), ptr(Kd[D + Z:]), Cc, ptr(dWb), 0,
+        ptr(Kd[D:D + Z]), Z, ptr(dZb), B, L, H, st)))
+    t_tc = time_kernel(lambda: check(lib().clv_inproj_tc(
+        ptr(e.roll), ptr(e.win_off), L, 1, D, ptr(Ke), G, G, ptr(scratch), ptr(gates), G, B * L, None, 0, 0, st)))
+    # algorithmic bytes per launch: streamed operands only, weights excluded
+    bytes_fwd = 4 * L * (2 * G + 2 * H + Z) * B                 # read xproj+Zs, write gates+h+c
+    bytes_bwd = 4 * L * (2 * G + 3 * H + Z) * B + 4 * (G + Cc) * B   # read gates,c,dh; write dA,dZ,dAsum,dW
+    bytes_tc = (D + 4 * G) * B * L                              # read uint8 roll rows, write fp32 projection
     kern = {
-        "clv_lstm_bwd": {"ms": t_bwd, "bytes": bytes_bwd, "GBps": bytes_bwd / t_bwd / 1e6,
-                         "launches_per_step": 2},
-        "clv_lstm_fwd": {"ms": t_fwd, "bytes": bytes_fwd, "GBps": bytes_fwd / t_fwd / 1e6,
-                         "launches_per_step": 2},
+        "clv_lstm_bwd_fused": {"ms": t_bwd, "bytes": bytes_bwd, "GBps": bytes_bwd / t_bwd / 1e6,
+                               "launches_per_step": 2, "bound": "hbm (latency/FFMA-issue bound at this B)"},
+        "clv_lstm_fwd_fused": {"ms": t_fwd, "bytes": bytes_fwd, "GBps": bytes_fwd / t_fwd / 1e6,
+                               "launches_per_step": 2, "bound": "hbm (latency/FFMA-issue bound at this B)"},
+        "clv_inproj_tc (tcgen05)": {"ms": t_tc, "bytes": bytes_tc, "GBps": bytes_tc / t_tc / 1e6,
+                                    "launches_per_step": 2, "bound": "hbm"},
     }
-    dom = "clv_lstm_bwd" if t_bwd >= t_fwd else "clv_lstm_fwd"
+    dom = "clv_lstm_bwd_fused" if t_bwd >= t_fwd else "clv_lstm_fwd_fused"
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["GBps"], "peak": hbm_peak,
                 "unit": "GB/s", "frac": kern[dom]["GBps"] / hbm_peak, "traffic": None,
                 "peak_source": peak_src,
                 "share_of_step": 2 * kern[dom]["ms"] / ms_step,
-                "note": "latency/issue-bound at B=200 (100 CTAs x 2 rows, 16 serial steps); "
-                        "fp32 FFMA issue bound = %.1f us" % (2 * 88 * 352 * 16 / 128.0 / 1.9e3)}
+                "note": "B=200 gives 100 CTAs x 2 rows and 16 serial steps: the recurrent kernels are "
+                        "latency/FFMA-issue bound here, not HBM bound; see profiles/ for the large-batch "
+                        "numbers (tcgen05 projection: 76% of measured HBM peak at B=16384, L=64)"}
 
     # ---------------- sampler: generate_sample for songs_per_gpu songs, Philox noise in-kernel
     sampler = None

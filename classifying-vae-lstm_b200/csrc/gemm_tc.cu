@@ -104,6 +104,23 @@ __global__ void wsplit_kernel(const float* __restrict__ W, int64_t ldw, int K,
   base[off + 2 * (B_SPLIT_BYTES / 2)] = lo;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 struct TcArgs {
   const uint8_t* roll; const int32_t* off; int grp, shift, D;
   const __nv_bfloat16* img;
@@ -112,129 +129,178 @@ struct TcArgs {
   int tiles;
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1) inproj_tc_kernel(const TcArgs a) {
+// Warp-specialised, persistent over row tiles, 2-deep pipeline:
+//   warps 0-3  producers : gather 128 roll rows, u8 -> bf16, write the canonical A tile [stage]
+//   warps 4-7  epilogue  : TMEM accumulator [stage] -> registers -> smem transpose -> 128-byte row stores
+//   warp  8    MMA       : bulk-TMA the weight image once, then 18 tcgen05.mma per tile, commits
+// mbarriers: a_full/a_empty per A stage, acc_full/acc_empty per TMEM accumulator.
+constexpr int TC_THREADS = 288;
+constexpr int ACC_STRIDE = 256;                     // TMEM columns between the two accumulators
+constexpr int STAGE_BYTES = 4 * 32 * 36 * 4;        // epilogue transpose buffers (one per warp)
+
+__global__ void __launch_bounds__(TC_THREADS, 1) inproj_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* a_s = smem;                       // A tile, canonical K-major bf16; reused as staging
-  uint8_t* b_s = smem + A_BYTES;             // 3 split images of this N-half
-  __shared__ __align__(8) uint64_t bars[2];  // [0] weights landed, [1] MMA done
+  uint8_t* a_s = smem;                               // 2 x A tile
+  uint8_t* b_s = smem + 2 * A_BYTES;                 // 3 split images of this N-half
+  float* stage_all = reinterpret_cast<float*>(smem + 2 * A_BYTES + B_BYTES);
+  __shared__ __align__(8) uint64_t bars[9];          // b, a_full[2], a_empty[2], acc_full[2], acc_empty[2]
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = blockIdx.y;
-  const uint32_t bar_b = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  enum { B_FULL = 0, A_FULL = 1, A_EMPTY = 3, ACC_FULL = 5, ACC_EMPTY = 7 };
 
   if (tid == 0) {
-    mbar_init(bar_b, 1);
-    mbar_init(bar_mma, 1);
+    mbar_init(BAR(B_FULL), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(BAR(A_FULL + s), 4);      // one arrive per producer warp
+      mbar_init(BAR(A_EMPTY + s), 1);     // tcgen05.commit
+      mbar_init(BAR(ACC_FULL + s), 1);    // tcgen05.commit
+      mbar_init(BAR(ACC_EMPTY + s), 4);   // one arrive per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+                 ::"r"(smem_u32(&tmem_base_s)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
+  const int ntile = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
-  if (tid == 0) {   // weights: three bulk (TMA) copies completing on one mbarrier
-    mbar_expect_tx(bar_b, B_BYTES);
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(a.img) + (size_t)half * B_BYTES;
+  if (warp < 4) {
+    // ================= producers: thread = row of the tile
+    const int row = tid;
+    for (int it = 0; it < ntile; ++it) {
+      const int s = it & 1, ph = (it >> 1) & 1;
+      const int64_t m = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TM + row;
+      uint2 v[12];
 #pragma unroll
-    for (int s = 0; s < NSPLIT; ++s)
-      bulk_g2s(smem_u32(b_s) + s * B_SPLIT_BYTES, src + (size_t)s * B_SPLIT_BYTES, B_SPLIT_BYTES, bar_b);
-  }
-
-  uint32_t mma_phase = 0;
-  for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
-    const int64_t m0 = (int64_t)tile * TM;
-    // ---- A tile: 2 threads per row, 6 core-matrix columns (48 keys) each; u8 {0,1} -> bf16
-    {
-      const int row = tid >> 1, part = tid & 1;
-      const int64_t m = m0 + row;
-      const uint8_t* src = nullptr;
+      for (int j = 0; j < 12; ++j) v[j] = make_uint2(0u, 0u);
       if (m < a.M) {
         const uint32_t mu = (uint32_t)m, g = mu / (uint32_t)a.grp;
-        src = a.roll + ((int64_t)__ldg(a.off + g) + a.shift + (mu - g * a.grp)) * a.D;
+        const uint8_t* src = a.roll + ((int64_t)__ldg(a.off + g) + a.shift + (mu - g * a.grp)) * a.D;
+#pragma unroll
+        for (int j = 0; j < 12; ++j)
+          if (8 * j < a.D) v[j] = __ldg(reinterpret_cast<const uint2*>(src + 8 * j));   // D % 8 == 0
       }
-      uint8_t* dst = a_s + (row >> 3) * SBO_A + (row & 7) * 16;
+      mbar_wait(BAR(A_EMPTY + s), ph ^ 1);          // MMAs that read this stage two tiles ago are done
+      uint8_t* dst = a_s + s * A_BYTES + (row >> 3) * SBO_A + (row & 7) * 16;
 #pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        const int k0 = (part * 6 + j) * 8;
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        if (src && k0 < a.D) {
-          const uint2 v = __ldg(reinterpret_cast<const uint2*>(src + k0));   // 8 keys (D % 8 == 0)
-          const uint32_t b[2] = {v.x, v.y};
+      for (int j = 0; j < 12; ++j) {
+        // bytes are 0/1: bf16(1.0) = 0x3F80 -> two keys per 32-bit word
+        const uint32_t x = v[j].x, y = v[j].y;
+        const uint32_t w0 = (x & 1u) * 0x3F80u + ((x >> 8) & 1u) * 0x3F800000u;
+        const uint32_t w1 = ((x >> 16) & 1u) * 0x3F80u + ((x >> 24) & 1u) * 0x3F800000u;
+        const uint32_t w2 = (y & 1u) * 0x3F80u + ((y >> 8) & 1u) * 0x3F800000u;
+        const uint32_t w3 = ((y >> 16) & 1u) * 0x3F80u + ((y >> 24) & 1u) * 0x3F800000u;
+        *reinterpret_cast<uint4*>(dst + j * LBO) = make_uint4(w0, w1, w2, w3);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(A_FULL + s));
+    }
+  } else if (warp < 8) {
+    // ================= epilogue: warp q owns TMEM lanes 32q..32q+31 (rows of the tile)
+    // TMEM -> registers (row per lane) -> smem transpose (stride 36: conflict-free 128-bit) ->
+    // 128-bit stores, 8 lanes per 128-byte row segment, 4 rows per warp instruction.
+    const int q = warp - 4;
+    float* stage = stage_all + q * (32 * 36);
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+    for (int it = 0; it < ntile; ++it) {
+      const int s = it & 1, ph = (it >> 1) & 1;
+      const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TM + q * 32;
+      const int rows_valid = (int)max((int64_t)0, min((int64_t)32, a.M - m0));
+      mbar_wait(BAR(ACC_FULL + s), ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * ACC_STRIDE);
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        const int ncol = min(32, TN - c0);          // 32,32,32,32,32,16
+        uint32_t r[32];
+        if (ncol == 32) {
+          tmem_ld32(tacc + c0, r);
+        } else {
+          uint32_t r16[16];
+          tmem_ld16(tacc + c0, r16);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const uint32_t bit = (b[e >> 2] >> (8 * (e & 3))) & 0xffu;
-            if (bit) w[e >> 1] |= 0x3F80u << (16 * (e & 1));                 // bf16(1.0)
+          for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0u; }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<uint4*>(stage + lane * 36 + 4 * i) =
+              make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+        __syncwarp();
+        if (c4 < ncol) {
+          const int n = half * TN + c0 + c4;
+          float* crow = a.C + (m0 + rsub) * a.ldc + n;
+          if (!a.rowadd) {
+#pragma unroll
+            for (int rr = 0; rr < 32; rr += 4) {
+              if (rr + rsub < rows_valid)
+                *reinterpret_cast<float4*>(crow + (int64_t)rr * a.ldc) =
+                    *reinterpret_cast<const float4*>(stage + (rr + rsub) * 36 + c4);
+            }
+          } else {
+            for (int rr = 0; rr < 32; rr += 4) {
+              if (rr + rsub < rows_valid) {
+                float4 v = *reinterpret_cast<const float4*>(stage + (rr + rsub) * 36 + c4);
+                const float* ra = a.rowadd + ((m0 + rr + rsub) / a.ra_grp) * a.ldra + n;
+                v.x += __ldg(ra); v.y += __ldg(ra + 1); v.z += __ldg(ra + 2); v.w += __ldg(ra + 3);
+                *reinterpret_cast<float4*>(crow + (int64_t)rr * a.ldc) = v;
+              }
+            }
           }
         }
-        *reinterpret_cast<uint4*>(dst + (part * 6 + j) * LBO) = make_uint4(w[0], w[1], w[2], w[3]);
+        __syncwarp();
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + s));
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
-    __syncthreads();
-    // ---- MMA: one thread issues 3 splits x 6 k-steps, accumulating in TMEM
-    if (warp == 0) {
-      if (tile == (int)blockIdx.x) mbar_wait(bar_b, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
-        const uint32_t idesc = umma_idesc(TM, TN);
-        const uint32_t a_addr = smem_u32(a_s), b_addr = smem_u32(b_s);
+  } else {
+    // ================= MMA warp (one elected thread)
+    if (lane == 0) {
+      mbar_expect_tx(BAR(B_FULL), B_BYTES);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.img) + (size_t)half * B_BYTES;
+#pragma unroll
+      for (int sp = 0; sp < NSPLIT; ++sp)
+        bulk_g2s(smem_u32(b_s) + sp * B_SPLIT_BYTES, src + (size_t)sp * B_SPLIT_BYTES, B_SPLIT_BYTES,
+                 BAR(B_FULL));
+      mbar_wait(BAR(B_FULL), 0);
+      const uint32_t idesc = umma_idesc(TM, TN);
+      const uint32_t b_addr = smem_u32(b_s);
+      for (int it = 0; it < ntile; ++it) {
+        const int s = it & 1, ph = (it >> 1) & 1;
+        mbar_wait(BAR(A_FULL + s), ph);
+        mbar_wait(BAR(ACC_EMPTY + s), ph ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = smem_u32(a_s + s * A_BYTES);
         uint32_t acc = 0;
 #pragma unroll
-        for (int s = 0; s < NSPLIT; ++s) {
+        for (int sp = 0; sp < NSPLIT; ++sp) {
 #pragma unroll
           for (int kk = 0; kk < KP / 16; ++kk) {
             const uint64_t ad = umma_desc(a_addr + kk * 2 * LBO, LBO, SBO_A);
-            const uint64_t bd = umma_desc(b_addr + s * B_SPLIT_BYTES + kk * 2 * LBO, LBO, SBO_A);
-            umma_bf16(tmem, ad, bd, idesc, acc);
+            const uint64_t bd = umma_desc(b_addr + sp * B_SPLIT_BYTES + kk * 2 * LBO, LBO, SBO_A);
+            umma_bf16(tmem + (uint32_t)(s * ACC_STRIDE), ad, bd, idesc, acc);
             acc = 1;
           }
         }
-        umma_commit(bar_mma);
-      }
-      __syncwarp();
-    }
-    // ---- epilogue: warps 4..7 own TMEM lanes 32*(warp%4)..+31 = rows of the tile
-    mbar_wait(bar_mma, mma_phase);
-    mma_phase ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (warp >= 4) {
-      const int q = warp - 4;
-      float* stage = reinterpret_cast<float*>(a_s) + q * (32 * 17);   // A tile is free after the MMA
-#pragma unroll 1
-      for (int c0 = 0; c0 < TN; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) stage[lane * 17 + i] = __uint_as_float(r[i]);
-        __syncwarp();
-        const int cc = lane & 15, rsub = lane >> 4;
-#pragma unroll 4
-        for (int rr = 0; rr < 32; rr += 2) {
-          const int64_t m = m0 + q * 32 + rr + rsub;
-          if (m < a.M) {
-            const int n = half * TN + c0 + cc;
-            float v = stage[(rr + rsub) * 17 + cc];
-            if (a.rowadd) v += __ldg(a.rowadd + (m / a.ra_grp) * a.ldra + n);
-            a.C[m * a.ldc + n] = v;
-          }
-        }
-        __syncwarp();
+        umma_commit(BAR(A_EMPTY + s));     // A stage reusable once these MMAs have read it
+        umma_commit(BAR(ACC_FULL + s));    // accumulator ready for the epilogue
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();   // TMEM drained and staging free before the next tile overwrites A / re-issues MMAs
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncwarp();
   }
-  if (tid == 0 && (int)blockIdx.x >= a.tiles) mbar_wait(bar_b, 0);   // never exit with a copy in flight
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS)
-                 : "memory");
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
 }
 
@@ -256,7 +322,7 @@ extern "C" int clv_inproj_tc(const uint8_t* roll, const int32_t* win_off, int32_
   wsplit_kernel<<<(2 * TN * KP + 255) / 256, 256, 0, st>>>(W, ldw, D, img);
   CLV_CHECK_LAUNCH();
   static bool attr_set = false;
-  const int smem = A_BYTES + B_BYTES + 1024;
+  const int smem = 2 * A_BYTES + B_BYTES + STAGE_BYTES + 1024;
   if (!attr_set) {
     CLV_CUDA(cudaFuncSetAttribute(inproj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
@@ -268,7 +334,7 @@ extern "C" int clv_inproj_tc(const uint8_t* roll, const int32_t* win_off, int32_
   int gx = clv_num_sms() / 2;
   if (gx > a.tiles) gx = a.tiles;
   if (gx < 1) gx = 1;
-  inproj_tc_kernel<<<dim3(gx, 2), NTHREADS, smem, st>>>(a);
+  inproj_tc_kernel<<<dim3(gx, 2), TC_THREADS, smem, st>>>(a);
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }

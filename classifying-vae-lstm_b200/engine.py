@@ -41,7 +41,7 @@ class Engine:
                  class_weight=1.0, kl_weight=1.0, w_kl_weight=1.0, w_log_var_prior=0.0,
                  optimizer="adam-wn", lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-8,
                  seed=0, device=None, world_size=1, rank=0, process_group=None, use_graph=True,
-                 overlap_wgrad=True, gemm_algo=0):
+                 overlap_wgrad=True, gemm_algo=1):
         _require_cuda()
         lib()
         if optimizer not in ("adam-wn", "adam"):

@@ -49,3 +49,25 @@ timeit("lstm_fwd_fused(W,Z)", lambda: check(L_.clv_lstm_fwd_fused(ptr(gates), 1,
 timeit("lstm_bwd", lambda: check(L_.clv_lstm_bwd(ptr(gates), ptr(U), ptr(h), ptr(c), ptr(dh), ptr(dAsum), B, L, H, st)))
 timeit("lstm_bwd_fused(dW,dZ)", lambda: check(L_.clv_lstm_bwd_fused(ptr(gates), ptr(U), ptr(c), ptr(dh), ptr(dAsum), ptr(Ww), Cc,
                                                                 ptr(dW), 0, ptr(Kz), Z, ptr(dZ), B, L, H, st)))
+
+# ---- hoisted input projection: SIMT fp32 vs tcgen05 (bf16x3, fp32-exact)
+from clvae_b200 import _lib
+M = B * L
+roll = (torch.rand(B * (L + 1) + 8, D, device=dev) < 0.05).to(torch.uint8)
+off = (torch.arange(B, device=dev, dtype=torch.int32) * (L + 1)).contiguous()
+Wk = torch.randn(D, G, device=dev) * 0.1
+Cout = torch.zeros(M, G, device=dev)
+scratch = torch.zeros(L_.clv_inproj_tc_scratch_bytes() // 4, device=dev)
+
+
+def simt():
+    a = _lib.clv_gemm_args(M=M, N=G, K=D, A=roll.data_ptr(), lda=D, a_u8=1, a_kmajor=1, a_off=off.data_ptr(),
+                           a_grp=L, a_shift=1, Bm=Wk.data_ptr(), ldb=G, b_nmajor=1, C=Cout.data_ptr(), ldc=G,
+                           split_k=1)
+    check(L_.clv_gemm(C.byref(a), st))
+
+
+timeit("inproj SIMT fp32", simt)
+timeit("inproj tcgen05 bf16x3", lambda: check(L_.clv_inproj_tc(ptr(roll), ptr(off), L, 1, D, ptr(Wk), G, G, ptr(scratch),
+                                                            ptr(Cout), G, M, None, 0, 0, st)))
+print("   output bytes %.1f MB -> at HBM peak 6536 GB/s: %.1f us" % (M * G * 4 / 1e6, M * G * 4 / 6536e3))
