@@ -97,21 +97,37 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
     }
     __syncthreads();
     const float gg_over_norm = col[0][cx];
-    // pass 2: Adam on V; new V parked in W
+    // pass 2: Adam on V; new V parked in W.  Rows are processed in explicit batches of 4 (all loads,
+    // then all stores) because W/m/v may alias as far as the compiler knows: without batching every
+    // iteration would wait a full memory round trip behind the previous iteration's stores.
     float snn = 0.f;
     if (cv)
-#pragma unroll 4
-      for (int r = ry; r < rows; r += RL) {
-        const int64_t e = off + (int64_t)r * cols + c;
-        const float V = W[e] / vs, g = G[e] * gscale;
-        const float gV = vs * (g - gg_over_norm * V);
-        const float mt = b1 * m[e] + (1.0f - b1) * gV;
-        const float vt = b2 * v[e] + (1.0f - b2) * gV * gV;
-        m[e] = mt;
-        v[e] = vt;
-        const float nV = V - lr_t * mt / (sqrtf(vt) + eps);
-        W[e] = nV;
-        snn = fmaf(nV, nV, snn);
+      for (int r0 = ry; r0 < rows; r0 += 4 * RL) {
+        float Wv[4], Gv[4], Mv[4], Vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u * RL;
+          if (r < rows) {
+            const int64_t e = off + (int64_t)r * cols + c;
+            Wv[u] = W[e]; Gv[u] = G[e]; Mv[u] = m[e]; Vv[u] = v[e];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u * RL;
+          if (r < rows) {
+            const int64_t e = off + (int64_t)r * cols + c;
+            const float V = Wv[u] / vs, g = Gv[u] * gscale;
+            const float gV = vs * (g - gg_over_norm * V);
+            const float mt = b1 * Mv[u] + (1.0f - b1) * gV;
+            const float vt = b2 * Vv[u] + (1.0f - b2) * gV * gV;
+            m[e] = mt;
+            v[e] = vt;
+            const float nV = V - lr_t * mt / (sqrtf(vt) + eps);
+            W[e] = nV;
+            snn = fmaf(nV, nV, snn);
+          }
+        }
       }
     red[0][ry][cx] = snn;
     __syncthreads();
@@ -123,13 +139,21 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
       col[2][cx] = ns;
     }
     __syncthreads();
-    // pass 3: W = V_scaler' * V'
+    // pass 3: W = V_scaler' * V'  (same batching)
     const float ns = col[2][cx];
     if (cv)
-#pragma unroll 4
-      for (int r = ry; r < rows; r += RL) {
-        const int64_t e = off + (int64_t)r * cols + c;
-        W[e] *= ns;
+      for (int r0 = ry; r0 < rows; r0 += 4 * RL) {
+        float Wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u * RL;
+          if (r < rows) Wv[u] = W[off + (int64_t)r * cols + c];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u * RL;
+          if (r < rows) W[off + (int64_t)r * cols + c] = Wv[u] * ns;
+        }
       }
   }
   // last block to finish advances `iterations`

@@ -220,6 +220,12 @@ __global__ void __launch_bounds__(256) gauss_heads_bwd_kernel(
       if (k < H) dh[row * H + k] = (relu_input && !(hk[i] > 0.f)) ? 0.f : dhk[i];
     }
   }
+  // block-level reduction in shared memory (reusing the transposed-kernel buffer), then one global
+  // atomic per element per BLOCK instead of per warp
+  __syncthreads();
+  float* red_s = Ks;                       // [2Z][H] + bias sums appended by the host-sized buffer
+  for (int i = threadIdx.x; i < 2 * Z * H + 2 * Z; i += blockDim.x) red_s[i] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int j = 0; j < ZM; ++j) {
     if (j < Z) {
@@ -227,15 +233,25 @@ __global__ void __launch_bounds__(256) gauss_heads_bwd_kernel(
       for (int i = 0; i < KMAX; ++i) {
         const int k = lane + 32 * i;
         if (k < H) {
-          atomicAdd(dKm + k * Z + j, accm[i][j]);
-          atomicAdd(dKv + k * Z + j, accv[i][j]);
+          atomicAdd(red_s + j * H + k, accm[i][j]);
+          atomicAdd(red_s + (Z + j) * H + k, accv[i][j]);
         }
       }
       if (lane == 0) {
-        atomicAdd(dbm + j, accb[j]);
-        atomicAdd(dbv + j, accb[ZM + j]);
+        atomicAdd(red_s + 2 * Z * H + j, accb[j]);
+        atomicAdd(red_s + 2 * Z * H + Z + j, accb[ZM + j]);
       }
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Z * H; i += blockDim.x) {
+    const int j = i / H, k = i - j * H;
+    atomicAdd(dKm + k * Z + j, red_s[j * H + k]);
+    atomicAdd(dKv + k * Z + j, red_s[(Z + j) * H + k]);
+  }
+  if (threadIdx.x < Z) {
+    atomicAdd(dbm + threadIdx.x, red_s[2 * Z * H + threadIdx.x]);
+    atomicAdd(dbv + threadIdx.x, red_s[2 * Z * H + Z + threadIdx.x]);
   }
 }
 
@@ -348,7 +364,7 @@ extern "C" int clv_gauss_heads_bwd(const float* h, const float* Km, const float*
     return CLV_E_INVALID;
   if (H < 1 || H > 32 * KMAX || Z < 1 || Z > 16) return CLV_E_UNSUPPORTED;
   if (R <= 0) return CLV_OK;
-  const size_t smem = sizeof(float) * 2 * Z * H;
+  const size_t smem = sizeof(float) * (2 * Z * H + 2 * Z);
   // few, fat blocks: every warp ends with H*2Z atomics, so give each warp >= 16 rows
   int64_t blocks = (R + 8 * 16 - 1) / (8 * 16);
   const int64_t cap = 2LL * clv_num_sms();

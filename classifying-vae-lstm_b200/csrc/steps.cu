@@ -148,36 +148,48 @@ int tn_u8(const uint8_t* roll, const int32_t* off, int grp, int shift, int64_t l
 // Auxiliary stream for the weight-gradient branch (off the critical path of the step).  Created by
 // clv_runtime_init() OUTSIDE any stream capture; forked from / joined back into the caller's stream
 // with events, so all work stays ordered on the caller's stream (and is captured with it).
+constexpr int NAUX = 3;
 struct SideStream {
-  cudaStream_t aux = nullptr;
-  cudaEvent_t ev[8] = {};
+  cudaStream_t aux[NAUX] = {};
+  cudaEvent_t fork_ev[8] = {};
+  cudaEvent_t join_ev[4][NAUX] = {};
   bool ready = false;
 };
 SideStream g_side[16];
 
+// Independent side work (weight gradients, the decoder's roll projection) is spread round-robin
+// over NAUX auxiliary streams so those launch-latency-bound kernels overlap each other as well as
+// the critical path.
 struct Fork {
-  cudaStream_t main, side;
+  cudaStream_t main;
   SideStream* s;
-  int n = 0, nj = 0;
+  int n = 0, nj = 0, rr = 0;
   bool on;
-  Fork(cudaStream_t st, bool want) : main(st), side(st), s(nullptr), on(false) {
+  Fork(cudaStream_t st, bool want) : main(st), s(nullptr), on(false) {
     int dev = 0;
     if (want && cudaGetDevice(&dev) == cudaSuccess && dev < 16 && g_side[dev].ready) {
-      s = &g_side[dev]; side = s->aux; on = true;
+      s = &g_side[dev]; on = true;
     }
   }
-  int fork() {   // side branch may now consume everything enqueued on main so far
+  cudaStream_t next() {   // stream for the next independent side kernel
+    if (!on) return main;
+    rr = (rr + 1) % NAUX;
+    return s->aux[rr];
+  }
+  int fork() {   // side branches may now consume everything enqueued on main so far
     if (!on) return CLV_OK;
-    CLV_CUDA(cudaEventRecord(s->ev[n], main));
-    CLV_CUDA(cudaStreamWaitEvent(side, s->ev[n], 0));
-    n = (n + 1) % 5;
+    CLV_CUDA(cudaEventRecord(s->fork_ev[n], main));
+    for (int i = 0; i < NAUX; ++i) CLV_CUDA(cudaStreamWaitEvent(s->aux[i], s->fork_ev[n], 0));
+    n = (n + 1) % 8;
     return CLV_OK;
   }
-  int join() {   // main waits for everything enqueued on the side branch so far
+  int join() {   // main waits for everything enqueued on the side branches so far
     if (!on) return CLV_OK;
-    CLV_CUDA(cudaEventRecord(s->ev[5 + nj], side));
-    CLV_CUDA(cudaStreamWaitEvent(main, s->ev[5 + nj], 0));
-    nj = (nj + 1) % 3;
+    for (int i = 0; i < NAUX; ++i) {
+      CLV_CUDA(cudaEventRecord(s->join_ev[nj][i], s->aux[i]));
+      CLV_CUDA(cudaStreamWaitEvent(main, s->join_ev[nj][i], 0));
+    }
+    nj = (nj + 1) % 4;
     return CLV_OK;
   }
 };
@@ -213,7 +225,6 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
     CLV_CUDA(cudaMemsetAsync(Gr, 0, sizeof(float) * (po[R_X_B] + pc[R_X_B]), st));
 
   Fork fk(st, c->overlap_wgrad != 0);
-  cudaStream_t sw = fk.side;   // side branch: work that is off the critical path of the step
   const bool fused_ke = (int64_t)L * D <= 65535 && (D % 4) == 0;
   const float* Ke_w = Ke + (int64_t)D * G;            // rows of the kernels that multiply W
   const float* Kd_z = Kd + (int64_t)xo * G;           //                               ... Z
@@ -222,8 +233,8 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   // ---- decoder input projection of the history roll: depends on nothing but the batch -> side
   if (c->use_x_prev) {
     TRY(fk.fork());
-    if (tc) TRY(clv_inproj_tc(roll, off, L, 0, D, Kd, G, G, wimg_d, gates_d, G, BL, nullptr, 0, 0, sw));
-    else TRY(nn_u8(roll, off, L, 0, D, Kd, G, gates_d, G, BL, G, D, nullptr, nullptr, 0, 0, 0, 0, sw));
+    if (tc) TRY(clv_inproj_tc(roll, off, L, 0, D, Kd, G, G, wimg_d, gates_d, G, BL, nullptr, 0, 0, fk.next()));
+    else TRY(nn_u8(roll, off, L, 0, D, Kd, G, gates_d, G, BL, G, D, nullptr, nullptr, 0, 0, 0, 0, fk.next()));
   }
   // ---- key encoder: hW, Wargs, logistic-normal W + its losses (model.py:174-191,244-255,264)
   if (fused_ke) {
@@ -276,31 +287,31 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
         *gUd = Gr + po[R_DEC_U], *gbd = Gr + po[R_DEC_B], *gKx = Gr + po[R_X_K],
         *gbx = Gr + po[R_X_B];
   TRY(fk.fork());
-  TRY(tn_f32(h_d, H, logits, D, gKx, D, H, D, BL, 0, 0, sw));
-  TRY(clv_colsum(logits, D, BL, D, gbx, 1, sw));
+  TRY(tn_f32(h_d, H, logits, D, gKx, D, H, D, BL, 0, 0, fk.next()));
+  TRY(clv_colsum(logits, D, BL, D, gbx, 1, fk.next()));
   TRY(clv_lstm_bwd_fused(gates_d, Ud, c_d, dh, dAsum_d, Kd_w, C, dW_ext, 0, Kd_z, Z, dZ, B, L, H, st));
   TRY(fk.fork());
-  if (c->use_x_prev) TRY(tn_u8(roll, off, L, 0, D, gates_d, G, gKd, G, D, G, BL, sw));
-  TRY(tn_f32(Zs, Z, gates_d, G, gKd + (int64_t)xo * G, G, Z, G, BL, 0, 0, sw));
-  TRY(tn_f32(W, C, dAsum_d, G, gKd + (int64_t)(xo + Z) * G, G, C, G, B, 0, 0, sw));
-  TRY(tn_f32(h_d, H, gates_d, G, gUd, G, H, G, BL, -1, L, sw));
-  TRY(clv_colsum(dAsum_d, G, B, G, gbd, 1, sw));
+  if (c->use_x_prev) TRY(tn_u8(roll, off, L, 0, D, gates_d, G, gKd, G, D, G, BL, fk.next()));
+  TRY(tn_f32(Zs, Z, gates_d, G, gKd + (int64_t)xo * G, G, Z, G, BL, 0, 0, fk.next()));
+  TRY(tn_f32(W, C, dAsum_d, G, gKd + (int64_t)(xo + Z) * G, G, C, G, B, 0, 0, fk.next()));
+  TRY(tn_f32(h_d, H, gates_d, G, gUd, G, H, G, BL, -1, L, fk.next()));
+  TRY(clv_colsum(dAsum_d, G, B, G, gbd, 1, fk.next()));
   // K2b bwd overwrites dh: its only reader (decoder BPTT) is ordered before it on st
   TRY(clv_gauss_heads_bwd(h_e, Kzm, Kzv, eps_z, Zargs, dZ, dh, gKzm, gbzm, gKzv, gbzv, BL, H, Z,
                           c->kl_weight * sbl, 0, st));
   TRY(clv_lstm_bwd_fused(gates_e, Ue, c_e, dh, dAsum_e, Ke_w, C, dW_ext, 1, nullptr, 0, nullptr, B, L, H, st));
   TRY(fk.fork());
-  TRY(tn_u8(roll, off, L, sx, D, gates_e, G, gKe, G, D, G, BL, sw));
-  TRY(tn_f32(W, C, dAsum_e, G, gKe + (int64_t)D * G, G, C, G, B, 0, 0, sw));
-  TRY(tn_f32(h_e, H, gates_e, G, gUe, G, H, G, BL, -1, L, sw));
-  TRY(clv_colsum(dAsum_e, G, B, G, gbe, 1, sw));
+  TRY(tn_u8(roll, off, L, sx, D, gates_e, G, gKe, G, D, G, BL, fk.next()));
+  TRY(tn_f32(W, C, dAsum_e, G, gKe + (int64_t)D * G, G, C, G, B, 0, 0, fk.next()));
+  TRY(tn_f32(h_e, H, gates_e, G, gUe, G, H, G, BL, -1, L, fk.next()));
+  TRY(clv_colsum(dAsum_e, G, B, G, gbe, 1, fk.next()));
   TRY(clv_keyenc_bwd(Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, B, C, D,
                      c->w_log_var_prior, c->class_weight * sb, c->w_kl_weight * sb, st));
   TRY(fk.fork());
-  TRY(tn_f32(hW, D, dWargs, 2 * C1, gKwa, 2 * C1, D, 2 * C1, B, 0, 0, sw));
-  TRY(clv_colsum(dWargs, 2 * C1, B, 2 * C1, gbwa, 1, sw));
-  TRY(tn_u8(roll, off, 1, sx, D, dhW, D, gKhw, D, L * D, D, B, sw));
-  TRY(clv_colsum(dhW, D, B, D, gbhw, 1, sw));
+  TRY(tn_f32(hW, D, dWargs, 2 * C1, gKwa, 2 * C1, D, 2 * C1, B, 0, 0, fk.next()));
+  TRY(clv_colsum(dWargs, 2 * C1, B, 2 * C1, gbwa, 1, fk.next()));
+  TRY(tn_u8(roll, off, 1, sx, D, dhW, D, gKhw, D, L * D, D, B, fk.next()));
+  TRY(clv_colsum(dhW, D, B, D, gbhw, 1, fk.next()));
   TRY(fk.join());
   return CLV_OK;
 }
@@ -397,8 +408,11 @@ extern "C" int clv_runtime_init(void) {
   if (dev >= 16) return CLV_E_UNSUPPORTED;
   SideStream& s = g_side[dev];
   if (s.ready) return CLV_OK;
-  CLV_CUDA(cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking));
-  for (int i = 0; i < 8; ++i) CLV_CUDA(cudaEventCreateWithFlags(&s.ev[i], cudaEventDisableTiming));
+  for (int i = 0; i < NAUX; ++i) CLV_CUDA(cudaStreamCreateWithFlags(&s.aux[i], cudaStreamNonBlocking));
+  for (int i = 0; i < 8; ++i) CLV_CUDA(cudaEventCreateWithFlags(&s.fork_ev[i], cudaEventDisableTiming));
+  for (int i = 0; i < 4; ++i)
+    for (int k = 0; k < NAUX; ++k)
+      CLV_CUDA(cudaEventCreateWithFlags(&s.join_ev[i][k], cudaEventDisableTiming));
   s.ready = true;
   return CLV_OK;
 }
