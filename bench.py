@@ -140,9 +140,10 @@ def run_reference(args):
         "unit": "sequences/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(1),
+        "config": workload_config(args.gpus),
         "cpu_baseline": {"value": r["value"], "unit": "sequences/s", "cores": r["cores"], "kind": "port",
-                         "sample": "%d full train steps of B=200 L=16 (oracle port, PyTorch-CPU f32)" % args.steps},
+                         "sample": "%d full train steps of B=200 L=16 = one rank's share of the global batch "
+                                   "(oracle port, PyTorch-CPU f32, all host threads)" % args.steps},
         "e2e": {"value": r["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sampler": {"metric": "cl_vrnn_sample_timesteps_per_sec", "value": samp, "unit": "timesteps/s",
                     "sample": "2 songs x (16 seed + 128) steps, batch 1 Python loop"},
