@@ -53,6 +53,7 @@ PROTOTYPES = {
     "clv_gemm": (C.c_int, [C.POINTER(clv_gemm_args), _P]),
     "clv_inproj_tc_scratch_bytes": (_I64, []),
     "clv_inproj_tc": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _I64, _I32, _P, _P, _I64, _I64, _P, _I64, _I32, _P]),
+    "clv_lstm_wgrad_tc": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _I32, _P, _P, _P, _I64, _I32, _P]),
     "clv_bias_act": (C.c_int, [_P, _I64, _I32, _I32, _P, _I32, _P]),
     "clv_colsum": (C.c_int, [_P, _I64, _I32, _I32, _P, _I32, _P]),
     "clv_logitnormal_fwd": (C.c_int, [_P, _I64, _P, _P, _P, _P, _I32, _I32, _F, _F, _I32, _U64, _P, _P]),

@@ -14,6 +14,9 @@ extern "C" int clv_lstm_bwd_fused(float*, const float*, const float*, const floa
 extern "C" int clv_inproj_tc(const uint8_t*, const int32_t*, int32_t, int32_t, int32_t, const float*, int64_t,
                              int32_t, void*, float*, int64_t, int64_t, const float*, int64_t, int32_t, void*);
 extern "C" int64_t clv_inproj_tc_scratch_bytes(void);
+extern "C" int clv_lstm_wgrad_tc(const float*, const uint8_t*, const int32_t*, int32_t, int32_t, int32_t,
+                                 const float*, const float*, int32_t, float*, float*, float*, int64_t,
+                                 int32_t, void*);
 extern "C" int clv_xhead_fwd_bwd(const float*, const float*, const float*, const uint8_t*, const int32_t*,
                                  int32_t, int32_t, float*, float*, float*, int64_t, int32_t, int32_t,
                                  float, int32_t, void*);
@@ -291,19 +294,29 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   TRY(clv_colsum(logits, D, BL, D, gbx, 1, fk.next()));
   TRY(clv_lstm_bwd_fused(gates_d, Ud, c_d, dh, dAsum_d, Kd_w, C, dW_ext, 0, Kd_z, Z, dZ, B, L, H, st));
   TRY(fk.fork());
-  if (c->use_x_prev) TRY(tn_u8(roll, off, L, 0, D, gates_d, G, gKd, G, D, G, BL, fk.next()));
-  TRY(tn_f32(Zs, Z, gates_d, G, gKd + (int64_t)xo * G, G, Z, G, BL, 0, 0, fk.next()));
+  const bool tcw = tc && H == 88 && Z <= 8;   // tcgen05 weight gradients
+  if (tcw) {
+    TRY(clv_lstm_wgrad_tc(gates_d, roll, off, L, 0, D, h_d, Zs, Z, c->use_x_prev ? gKd : nullptr, gUd,
+                          gKd + (int64_t)xo * G, BL, H, fk.next()));
+  } else {
+    if (c->use_x_prev) TRY(tn_u8(roll, off, L, 0, D, gates_d, G, gKd, G, D, G, BL, fk.next()));
+    TRY(tn_f32(Zs, Z, gates_d, G, gKd + (int64_t)xo * G, G, Z, G, BL, 0, 0, fk.next()));
+    TRY(tn_f32(h_d, H, gates_d, G, gUd, G, H, G, BL, -1, L, fk.next()));
+  }
   TRY(tn_f32(W, C, dAsum_d, G, gKd + (int64_t)(xo + Z) * G, G, C, G, B, 0, 0, fk.next()));
-  TRY(tn_f32(h_d, H, gates_d, G, gUd, G, H, G, BL, -1, L, fk.next()));
   TRY(clv_colsum(dAsum_d, G, B, G, gbd, 1, fk.next()));
   // K2b bwd overwrites dh: its only reader (decoder BPTT) is ordered before it on st
   TRY(clv_gauss_heads_bwd(h_e, Kzm, Kzv, eps_z, Zargs, dZ, dh, gKzm, gbzm, gKzv, gbzv, BL, H, Z,
                           c->kl_weight * sbl, 0, st));
   TRY(clv_lstm_bwd_fused(gates_e, Ue, c_e, dh, dAsum_e, Ke_w, C, dW_ext, 1, nullptr, 0, nullptr, B, L, H, st));
   TRY(fk.fork());
-  TRY(tn_u8(roll, off, L, sx, D, gates_e, G, gKe, G, D, G, BL, fk.next()));
+  if (tcw) {
+    TRY(clv_lstm_wgrad_tc(gates_e, roll, off, L, sx, D, h_e, nullptr, 0, gKe, gUe, nullptr, BL, H, fk.next()));
+  } else {
+    TRY(tn_u8(roll, off, L, sx, D, gates_e, G, gKe, G, D, G, BL, fk.next()));
+    TRY(tn_f32(h_e, H, gates_e, G, gUe, G, H, G, BL, -1, L, fk.next()));
+  }
   TRY(tn_f32(W, C, dAsum_e, G, gKe + (int64_t)D * G, G, C, G, B, 0, 0, fk.next()));
-  TRY(tn_f32(h_e, H, gates_e, G, gUe, G, H, G, BL, -1, L, fk.next()));
   TRY(clv_colsum(dAsum_e, G, B, G, gbe, 1, fk.next()));
   TRY(clv_keyenc_bwd(Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, B, C, D,
                      c->w_log_var_prior, c->class_weight * sb, c->w_kl_weight * sb, st));

@@ -108,6 +108,14 @@ int64_t clv_inproj_tc_scratch_bytes(void);
 int clv_inproj_tc(const uint8_t* roll, const int32_t* win_off, int32_t grp, int32_t shift, int32_t D,
                   const float* W, int64_t ldw, int32_t N, void* scratch, float* C, int64_t ldc,
                   int64_t M, const float* rowadd, int64_t ldra, int32_t ra_grp, void* stream);
+/* Tensor-core form of the LSTM weight gradients that reduce over all R = B*L rows (one launch):
+ *   gKx[D,4H] += X^T @ dA,  gU[H,4H] += Hprev^T @ dA (Hprev[b,t] = h[b,t-1], 0 at t = 0),
+ *   gKz[Z,4H] += Zs^T @ dA  (gKx / Zs+gKz optional).  tcgen05.mma with MN-major bf16 operands built
+ * in shared memory (roll exact; dA, h, Zs split hi+mid), accumulators in TMEM, rows split over CTAs,
+ * partials added with red.add (the gradient buffer must hold the value to add to).  H = 88, Z <= 8. */
+int clv_lstm_wgrad_tc(const float* dA, const uint8_t* roll, const int32_t* win_off, int32_t L,
+                      int32_t shift, int32_t D, const float* h, const float* Zs, int32_t Z, float* gKx,
+                      float* gU, float* gKz, int64_t R, int32_t H, void* stream);
 /* C[M,N] = act(C + bias[N])  -- epilogue of a split-K forward GEMM */
 int clv_bias_act(float* C, int64_t ldc, int32_t M, int32_t N, const float* bias, int32_t relu,
                  void* stream);

@@ -403,3 +403,33 @@ def test_inproj_tcgen05_is_fp32_exact(B_, Lq, shift):
     assert np.isfinite(got).all()
     err = np.abs(got - ref).max() / np.abs(ref).max()
     assert err < 2e-6, err
+
+
+@pytest.mark.parametrize("B_,Lq,Z,with_x", [(200, 16, 2, True), (7, 5, 8, True), (64, 33, 0, True), (300, 8, 2, False)])
+def test_lstm_wgrad_tcgen05(B_, Lq, Z, with_x):
+    """tcgen05 weight gradients (MN-major operands, hi+mid splits) vs float64: 1e-4 of the tensor's max."""
+    _lib, L, check, ptr, st = _env()
+    rng = np.random.default_rng(B_ * 3 + Lq)
+    D, H, G = 88, 88, 352
+    R = B_ * Lq
+    roll = (rng.random((B_ * (Lq + 1) + 4, D)) < 0.1).astype(np.uint8)
+    off = (np.arange(B_) * (Lq + 1)).astype(np.int32)
+    X = np.stack([roll[o + 1:o + 1 + Lq] for o in off]).reshape(R, D).astype(np.float64)
+    dA = rng.normal(0, 1, (R, G)) * np.exp(rng.normal(0, 1.5, (R, 1)))
+    h = np.tanh(rng.normal(0, 1, (B_, Lq, H)))
+    hprev = np.concatenate([np.zeros((B_, 1, H)), h[:, :-1]], axis=1).reshape(R, H)
+    Zs = rng.normal(size=(R, max(Z, 1)))
+    base = rng.normal(size=(D + H + max(Z, 1), G))
+    gKx, gU, gKz = dev(base[:D]), dev(base[D:D + H]), dev(base[D + H:])
+    check(L.clv_lstm_wgrad_tc(ptr(dev(dA)), ptr(dev(roll, torch.uint8)), ptr(dev(off, torch.int32)), Lq, 1, D,
+                              ptr(dev(h)), ptr(dev(Zs)) if Z else None, Z, ptr(gKx) if with_x else None, ptr(gU),
+                              ptr(gKz) if Z else None, R, H, st))
+    torch.cuda.synchronize()
+    dA32 = dA.astype(np.float32).astype(np.float64)
+    ref_x = base[:D] + (X.T @ dA32 if with_x else 0)
+    ref_u = base[D:D + H] + hprev.astype(np.float32).astype(np.float64).T @ dA32
+    assert util.rel_err(gKx.cpu().numpy(), ref_x) < TOL
+    assert util.rel_err(gU.cpu().numpy(), ref_u) < TOL
+    if Z:
+        ref_z = base[D + H:] + Zs.astype(np.float32).astype(np.float64).T @ dA32
+        assert util.rel_err(gKz.cpu().numpy(), ref_z) < TOL
