@@ -54,7 +54,8 @@ def test_microbatch_linearity_and_eval_idempotence_at_scale():
     _stage(full, win, labels, eps_w, eps_z)
     full.run(train=False, gen_noise=False); a = full.read_losses()
     full.run(train=False, gen_noise=False); b = full.read_losses()
-    assert all(abs(a[k] - b[k]) <= 1e-6 * max(1.0, abs(a[k])) for k in a)          # forward is idempotent
+    # forward is idempotent up to the order of the fp32 atomics that accumulate the loss scalars
+    assert all(abs(a[k] - b[k]) <= 2e-5 * max(1.0, abs(a[k])) for k in a)
     full.run(train=True, gen_noise=False)
     part = _engine(B // parts, L, Cc, Z)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
