@@ -128,9 +128,17 @@ __global__ void __launch_bounds__(WTHREADS, 1) lstm_wgrad_tc_kernel(const WgArgs
                  ::"r"(smem_u32(&tmem_base_s)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // zero all stages once: padding rows/columns of the operand tiles are never written afterwards
-  for (int i = tid; i < NSTAGE * STAGE / 16; i += WTHREADS)
-    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // zero the padding column groups of the three A tiles once (M rows beyond D / H+Z): they are never
+  // written by the producers
+  {
+    const int gx0 = a.D / 8, gh0 = a.H / 8 + (a.Zs ? 1 : 0);
+    for (int i = tid; i < NSTAGE * 3 * (WM / 8) * (SBO / 16); i += WTHREADS) {
+      const int c16 = i % (SBO / 16), g = (i / (SBO / 16)) % (WM / 8);
+      const int tile = (i / (SBO / 16) / (WM / 8)) % 3, s = i / (SBO / 16) / (WM / 8) / 3;
+      if (g >= (tile == 0 ? gx0 : gh0))
+        *reinterpret_cast<uint4*>(smem + s * STAGE + tile * A_TILE + g * SBO + c16 * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -155,49 +163,62 @@ __global__ void __launch_bounds__(WTHREADS, 1) lstm_wgrad_tc_kernel(const WgArgs
       }
       mbar_wait(EMPTY(s), ph ^ 1);
       uint8_t* sb = smem + s * STAGE + (lane >> 3) * LBO + (lane & 7) * 16;   // this row's slot
-      for (int task = warp; task < ntask; task += NPROD) {
-        float v[8];
-        if (task < ngb) {                                   // dA columns n0 + 8*task ..
-          if (rv) {
+      // tasks of this warp in batches of 3: issue every global load of the batch, then convert and
+      // store (one memory round trip per batch instead of per task)
+      for (int task0 = warp; task0 < ntask; task0 += 3 * NPROD) {
+        float v[3][8];
+        uint2 q[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int task = task0 + u * NPROD;
+          q[u] = make_uint2(0u, 0u);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+          if (task >= ntask || !rv) continue;
+          if (task < ngb) {                                   // dA columns n0 + 8*task ..
             const float4* p = reinterpret_cast<const float4*>(a.dA + r * a.G + n0 + 8 * task);
             const float4 x = __ldg(p), y = __ldg(p + 1);
-            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = 0.f;
-          }
-          uint4 hi, mid;
-          split8(v, hi, mid);
-          *reinterpret_cast<uint4*>(sb + 3 * A_TILE + task * SBO) = hi;
-          *reinterpret_cast<uint4*>(sb + 3 * A_TILE + B_TILE + task * SBO) = mid;
-        } else if (task < ngb + ngx) {                      // piano-roll keys 8*g .. (exact in bf16)
-          const int g = task - ngb;
-          uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-          if (rv) {
-            const uint2 q = __ldg(reinterpret_cast<const uint2*>(a.roll + xrow * a.D + 8 * g));
-            w0 = (q.x & 1u) * 0x3F80u + ((q.x >> 8) & 1u) * 0x3F800000u;
-            w1 = ((q.x >> 16) & 1u) * 0x3F80u + ((q.x >> 24) & 1u) * 0x3F800000u;
-            w2 = (q.y & 1u) * 0x3F80u + ((q.y >> 8) & 1u) * 0x3F800000u;
-            w3 = ((q.y >> 16) & 1u) * 0x3F80u + ((q.y >> 24) & 1u) * 0x3F800000u;
-          }
-          *reinterpret_cast<uint4*>(sb + g * SBO) = make_uint4(w0, w1, w2, w3);
-        } else {                                            // h_{t-1} units 8*g .., or the Z columns
-          const int g = task - ngb - ngx;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = 0.f;
-          if (g < ngh) {
-            if (rv && tpos) {
-              const float4* p = reinterpret_cast<const float4*>(a.h + (r - 1) * a.H + 8 * g);
-              const float4 x = __ldg(p), y = __ldg(p + 1);
-              v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+            v[u][0] = x.x; v[u][1] = x.y; v[u][2] = x.z; v[u][3] = x.w;
+            v[u][4] = y.x; v[u][5] = y.y; v[u][6] = y.z; v[u][7] = y.w;
+          } else if (task < ngb + ngx) {                      // piano-roll keys (exact in bf16)
+            q[u] = __ldg(reinterpret_cast<const uint2*>(a.roll + xrow * a.D + 8 * (task - ngb)));
+          } else {                                            // h_{t-1} units, or the Z columns
+            const int g = task - ngb - ngx;
+            if (g < ngh) {
+              if (tpos) {
+                const float4* p = reinterpret_cast<const float4*>(a.h + (r - 1) * a.H + 8 * g);
+                const float4 x = __ldg(p), y = __ldg(p + 1);
+                v[u][0] = x.x; v[u][1] = x.y; v[u][2] = x.z; v[u][3] = x.w;
+                v[u][4] = y.x; v[u][5] = y.y; v[u][6] = y.z; v[u][7] = y.w;
+              }
+            } else {
+              for (int j = 0; j < a.Z; ++j) v[u][j] = __ldg(a.Zs + r * a.Z + j);
             }
-          } else if (rv) {
-            for (int j = 0; j < a.Z; ++j) v[j] = __ldg(a.Zs + r * a.Z + j);
           }
-          uint4 hi, mid;
-          split8(v, hi, mid);
-          *reinterpret_cast<uint4*>(sb + A_TILE + g * SBO) = hi;
-          *reinterpret_cast<uint4*>(sb + 2 * A_TILE + g * SBO) = mid;
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int task = task0 + u * NPROD;
+          if (task >= ntask) continue;
+          if (task < ngb) {
+            uint4 hi, mid;
+            split8(v[u], hi, mid);
+            *reinterpret_cast<uint4*>(sb + 3 * A_TILE + task * SBO) = hi;
+            *reinterpret_cast<uint4*>(sb + 3 * A_TILE + B_TILE + task * SBO) = mid;
+          } else if (task < ngb + ngx) {
+            const uint32_t x = q[u].x, y = q[u].y;
+            const uint32_t w0 = (x & 1u) * 0x3F80u + ((x >> 8) & 1u) * 0x3F800000u;
+            const uint32_t w1 = ((x >> 16) & 1u) * 0x3F80u + ((x >> 24) & 1u) * 0x3F800000u;
+            const uint32_t w2 = (y & 1u) * 0x3F80u + ((y >> 8) & 1u) * 0x3F800000u;
+            const uint32_t w3 = ((y >> 16) & 1u) * 0x3F80u + ((y >> 24) & 1u) * 0x3F800000u;
+            *reinterpret_cast<uint4*>(sb + (task - ngb) * SBO) = make_uint4(w0, w1, w2, w3);
+          } else {
+            const int g = task - ngb - ngx;
+            uint4 hi, mid;
+            split8(v[u], hi, mid);
+            *reinterpret_cast<uint4*>(sb + A_TILE + g * SBO) = hi;
+            *reinterpret_cast<uint4*>(sb + 2 * A_TILE + g * SBO) = mid;
+          }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -240,6 +261,8 @@ __global__ void __launch_bounds__(WTHREADS, 1) lstm_wgrad_tc_kernel(const WgArgs
     float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 33);   // operand stages are free now
     for (int tile = (a.gKx ? 0 : 1); tile < 2; ++tile) {
       const uint32_t tacc = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tile * 256);
+      const int mvalid = (tile == 0) ? a.D : a.H + a.Z;      // rows of this accumulator that exist
+      if (warp * 32 >= mvalid) continue;
 #pragma unroll 1
       for (int c0 = 0; c0 < WN; c0 += 32) {
         const int ncol = min(32, WN - c0);
@@ -256,13 +279,14 @@ __global__ void __launch_bounds__(WTHREADS, 1) lstm_wgrad_tc_kernel(const WgArgs
         for (int i = 0; i < 32; ++i) stage[lane * 33 + i] = __uint_as_float(r[i]);
         __syncwarp();
         if (lane < ncol) {
-          for (int rr = 0; rr < 32; ++rr) {
+          const int nvalid = min(32, mvalid - warp * 32);
+          for (int rr = 0; rr < nvalid; ++rr) {
             const int m = warp * 32 + rr;
-            float* dst = nullptr;
-            if (tile == 0) { if (m < a.D) dst = a.gKx + (int64_t)m * a.G; }
+            float* dst;
+            if (tile == 0) dst = a.gKx + (int64_t)m * a.G;
             else if (m < a.H) dst = a.gU + (int64_t)m * a.G;
-            else if (a.Zs && m - a.H < a.Z) dst = a.gKz + (int64_t)(m - a.H) * a.G;
-            if (dst) atomicAdd(dst + n0 + c0 + lane, stage[rr * 33 + lane]);
+            else dst = a.gKz + (int64_t)(m - a.H) * a.G;
+            atomicAdd(dst + n0 + c0 + lane, stage[rr * 33 + lane]);
           }
         }
         __syncwarp();

@@ -71,3 +71,11 @@ timeit("inproj SIMT fp32", simt)
 timeit("inproj tcgen05 bf16x3", lambda: check(L_.clv_inproj_tc(ptr(roll), ptr(off), L, 1, D, ptr(Wk), G, G, ptr(scratch),
                                                             ptr(Cout), G, M, None, 0, 0, st)))
 print("   output bytes %.1f MB -> at HBM peak 6536 GB/s: %.1f us" % (M * G * 4 / 1e6, M * G * 4 / 6536e3))
+
+# ---- LSTM weight gradients: tcgen05 (one launch) vs the three SIMT TN GEMMs
+hh = torch.tanh(torch.randn(B, L, H, device=dev)); dAb = torch.randn(M, G, device=dev)
+gKx = torch.zeros(D, G, device=dev); gU = torch.zeros(H, G, device=dev); gKz = torch.zeros(Z, G, device=dev)
+Zsb = torch.randn(M, Z, device=dev)
+timeit("lstm_wgrad tcgen05", lambda: check(L_.clv_lstm_wgrad_tc(ptr(dAb), ptr(roll), ptr(off), L, 1, D, ptr(hh), ptr(Zsb), Z,
+                                                             ptr(gKx), ptr(gU), ptr(gKz), M, H, st)))
+print("   operand bytes %.1f MB -> at HBM peak: %.1f us" % (M * (G * 4 + H * 4 + D) / 1e6, M * (G * 4 + H * 4 + D) / 6536e3))
