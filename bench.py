@@ -44,7 +44,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -235,7 +235,7 @@ def main():
     step_resident(0)
     launches_eager = None
     barrier()
-    clk = ClockSampler(local)
+    clk = ClockSampler(local) if rank == 0 else None   # one poller per job: nvidia-smi takes driver locks
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -244,7 +244,7 @@ def main():
     ev1.record()
     barrier()
     ms_step = max_over_ranks(ev0.elapsed_time(ev1) / K)
-    clocks = clk.stop()
+    clocks = clk.stop() if clk is not None else None
     losses = e.read_losses()
     value = B * world / (ms_step / 1e3)
 
