@@ -17,6 +17,9 @@ extern "C" int64_t clv_inproj_tc_scratch_bytes(void);
 extern "C" int clv_lstm_wgrad_tc(const float*, const uint8_t*, const int32_t*, int32_t, int32_t, int32_t,
                                  const float*, const float*, int32_t, float*, float*, float*, int64_t,
                                  int32_t, void*);
+extern "C" int64_t clv_lstm_fwd_tc_scratch_bytes(void);
+extern "C" int clv_lstm_fwd_tc(float*, const float*, const float*, const float*, int32_t, float*, float*,
+                               void*, int32_t, int32_t, int32_t, void*);
 extern "C" int clv_xhead_fwd_bwd(const float*, const float*, const float*, const uint8_t*, const int32_t*,
                                  int32_t, int32_t, float*, float*, float*, int64_t, int32_t, int32_t,
                                  float, int32_t, void*);
@@ -77,6 +80,7 @@ Ws carve(const clv_cfg* c) {
     w.add("dAsum_d", B * G); w.add("dAsum_e", B * G); w.add("dZ", BL * Z);
     w.add("dW_ext", B * C); w.add("dWargs", B * 2 * C1); w.add("dhW", B * D);
     w.add("wimg_e", clv_inproj_tc_scratch_bytes() / 4); w.add("wimg_d", clv_inproj_tc_scratch_bytes() / 4);
+    w.add("uimg_e", clv_lstm_fwd_tc_scratch_bytes() / 4); w.add("uimg_d", clv_lstm_fwd_tc_scratch_bytes() / 4);
   } else {
     const int64_t Hc = c->Hc;
     w.add("h_w", B * Hc); w.add("Wargs", B * 2 * C1); w.add("W", B * C);
@@ -213,10 +217,14 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
         *Zs = WSP("Zs"), *rb_d = WSP("rb_d"), *gates_d = WSP("gates_d"), *h_d = WSP("h_d"),
         *c_d = WSP("c_d"), *logits = WSP("logits"), *dh = WSP("dh"), *dAsum_d = WSP("dAsum_d"),
         *dAsum_e = WSP("dAsum_e"), *dZ = WSP("dZ"), *dW_ext = WSP("dW_ext"),
-        *dWargs = WSP("dWargs"), *dhW = WSP("dhW"), *wimg_e = WSP("wimg_e"), *wimg_d = WSP("wimg_d");
+        *dWargs = WSP("dWargs"), *dhW = WSP("dhW"), *wimg_e = WSP("wimg_e"), *wimg_d = WSP("wimg_d"),
+        *uimg_e = WSP("uimg_e"), *uimg_d = WSP("uimg_d");
 #undef WSP
   // hoisted input projections on tensor cores (tcgen05) when asked for and the shape is the built one
   const bool tc = c->gemm_algo == 1 && G == 352 && D <= 96 && (D % 8) == 0;
+  // tensor-core recurrence: wins once a CTA can be given 128 rows (large batches); below that the
+  // register-resident FFMA kernel is latency-optimal
+  const bool tcl = tc && c->use_x_prev && B >= 1024 && Z <= 16;
   const float *Khw = P + po[R_HW_K], *bhw = P + po[R_HW_B], *Kwa = P + po[R_WA_K],
               *bwa = P + po[R_WA_B], *Ke = P + po[R_ENC_K], *Ue = P + po[R_ENC_U],
               *be = P + po[R_ENC_B], *Kzm = P + po[R_ZM_K], *bzm = P + po[R_ZM_B],
@@ -234,7 +242,7 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   const float* Kd_w = Kd + (int64_t)(xo + Z) * G;
 
   // ---- decoder input projection of the history roll: depends on nothing but the batch -> side
-  if (c->use_x_prev) {
+  if (c->use_x_prev && !tcl) {
     TRY(fk.fork());
     if (tc) TRY(clv_inproj_tc(roll, off, L, 0, D, Kd, G, G, wimg_d, gates_d, G, BL, nullptr, 0, 0, fk.next()));
     else TRY(nn_u8(roll, off, L, 0, D, Kd, G, gates_d, G, BL, G, D, nullptr, nullptr, 0, 0, 0, 0, fk.next()));
@@ -262,15 +270,26 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   }
   // ---- encoder LSTM (model.py:193-199): roll part hoisted as one GEMM; bias and the
   //      RepeatVector(W) columns are folded into the recurrent kernel's per-sequence constant
-  if (tc) TRY(clv_inproj_tc(roll, off, L, sx, D, Ke, G, G, wimg_e, gates_e, G, BL, nullptr, 0, 0, st));
-  else TRY(nn_u8(roll, off, L, sx, D, Ke, G, gates_e, G, BL, G, D, nullptr, nullptr, 0, 0, 0, 0, st));
-  TRY(clv_lstm_fwd_fused(gates_e, 1, Ue, be, W, Ke_w, C, nullptr, nullptr, 0, h_e, c_e, B, L, H, st));
+  if (tcl) {
+    // bias + W term as a per-sequence addend of the tcgen05 projection, then the tcgen05 recurrence
+    TRY(nn_f32(W, C, Ke_w, G, rb_e, G, B, G, C, be, 0, 0, st));
+    TRY(nn_f32(W, C, Kd_w, G, rb_d, G, B, G, C, bd, 0, 0, st));
+    TRY(clv_inproj_tc(roll, off, L, sx, D, Ke, G, G, wimg_e, gates_e, G, BL, rb_e, G, L, st));
+    TRY(fk.fork());
+    TRY(clv_inproj_tc(roll, off, L, 0, D, Kd, G, G, wimg_d, gates_d, G, BL, rb_d, G, L, fk.next()));
+    TRY(clv_lstm_fwd_tc(gates_e, Ue, nullptr, nullptr, 0, h_e, c_e, uimg_e, B, L, H, st));
+  } else {
+    if (tc) TRY(clv_inproj_tc(roll, off, L, sx, D, Ke, G, G, wimg_e, gates_e, G, BL, nullptr, 0, 0, st));
+    else TRY(nn_u8(roll, off, L, sx, D, Ke, G, gates_e, G, BL, G, D, nullptr, nullptr, 0, 0, 0, 0, st));
+    TRY(clv_lstm_fwd_fused(gates_e, 1, Ue, be, W, Ke_w, C, nullptr, nullptr, 0, h_e, c_e, B, L, H, st));
+  }
   // ---- Z heads + sample + kl (model.py:200-216,236-239)
   TRY(clv_gauss_heads_fwd(h_e, Kzm, bzm, Kzv, bzv, eps_z, Zargs, Zs, loss, BL, H, Z, sbl,
                           c->gen_noise, c->seed, ctr, st));
   // ---- decoder LSTM (model.py:218-228) on [Xp | Z | W]: Z enters as a rank-Z term per step
   if (c->use_x_prev) TRY(fk.join());
-  TRY(clv_lstm_fwd_fused(gates_d, c->use_x_prev, Ud, bd, W, Kd_w, C, Zs, Kd_z, Z, h_d, c_d, B, L, H, st));
+  if (tcl) TRY(clv_lstm_fwd_tc(gates_d, Ud, Zs, Kd_z, Z, h_d, c_d, uimg_d, B, L, H, st));
+  else TRY(clv_lstm_fwd_fused(gates_d, c->use_x_prev, Ud, bd, W, Kd_w, C, Zs, Kd_z, Z, h_d, c_d, B, L, H, st));
   // ---- X head + Bernoulli loss + dlogits + dgrad to h_d in one pass (model.py:229-234,241-242)
   if (H == 88 && D == 88) {
     TRY(clv_xhead_fwd_bwd(h_d, Kx, bx, roll, off, L, sx, loss, logits, dh, BL, H, D, sbl,

@@ -179,6 +179,15 @@ int clv_lstm_bwd_fused(float* gates, const float* U, const float* c, const float
                        const float* Kz, int32_t Z, float* dZ, int32_t B, int32_t L, int32_t H,
                        void* stream);
 
+/* Tensor-core form of the forward recurrence for large batches: 128 rows per CTA, h_{t-1} @ U on
+ * tcgen05 (fp16 hi+lo splits of both operands, 3 products, fp32 accumulate in TMEM), cell state in
+ * TMEM, U resident in shared memory.  `gates` must already hold x@kernel + bias + W term (use
+ * clv_inproj_tc with rowadd); the optional Z term is added in the epilogue.  scratch:
+ * clv_lstm_fwd_tc_scratch_bytes(), 16-byte aligned. */
+int64_t clv_lstm_fwd_tc_scratch_bytes(void);
+int clv_lstm_fwd_tc(float* gates, const float* U, const float* Zs, const float* Kz, int32_t Z, float* h,
+                    float* c, void* scratch, int32_t B, int32_t L, int32_t H, void* stream);
+
 /* ---------------------------------------------------------------- K4: Bernoulli loss ------ */
 /* vae_loss = 88*mean_k Keras-BCE with clip->logit semantics, fused with its backward
  * (cl_vrnn/model.py:241-242; cl_vae/model.py:190-191).  logits[R,D] are overwritten with

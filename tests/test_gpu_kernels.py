@@ -433,3 +433,28 @@ def test_lstm_wgrad_tcgen05(B_, Lq, Z, with_x):
     if Z:
         ref_z = base[D + H:] + Zs.astype(np.float32).astype(np.float64).T @ dA32
         assert util.rel_err(gKz.cpu().numpy(), ref_z) < TOL
+
+
+@pytest.mark.parametrize("B_,L,Z", [(128, 6, 0), (300, 16, 2), (1500, 5, 4)])
+def test_lstm_fwd_tcgen05_matches_oracle(B_, L, Z):
+    """tcgen05 recurrence (fp16 hi/lo splits, 3 products) vs the float64 cell: same 1e-4 bound as the
+    FFMA kernel -- and in practice ~1e-6."""
+    _lib, Lb, check, ptr, st = _env()
+    rng = np.random.default_rng(B_ + L)
+    H, G = 88, 352
+    xproj = rng.normal(0, 1.2, size=(B_, L, G)); U = rng.normal(0, 0.15, size=(H, G))
+    Zs = rng.normal(size=(B_, L, max(Z, 1))); Kz = rng.normal(0, 0.4, (max(Z, 1), G))
+    full = xproj + (Zs @ Kz if Z else 0)
+    hs, cs, a_all = M.lstm_fwd(full, U)
+    gates = dev(xproj)
+    hd = torch.zeros(B_, L, H, device="cuda"); cd = torch.zeros(B_, L, H, device="cuda")
+    scratch = torch.zeros(Lb.clv_lstm_fwd_tc_scratch_bytes() // 4, device="cuda")
+    check(Lb.clv_lstm_fwd_tc(ptr(gates), ptr(dev(U)), ptr(dev(Zs)) if Z else None, ptr(dev(Kz)) if Z else None, Z,
+                             ptr(hd), ptr(cd), ptr(scratch), B_, L, H, st))
+    torch.cuda.synchronize()
+    err_h = util.rel_err(hd.cpu().numpy(), hs)
+    assert err_h < 2e-5, err_h
+    assert util.rel_err(cd.cpu().numpy(), cs) < 2e-5
+    g_ref = np.concatenate([M._hard_sigmoid(a_all[..., :2 * H]), np.tanh(a_all[..., 2 * H:3 * H]),
+                            M._hard_sigmoid(a_all[..., 3 * H:])], -1)
+    assert util.rel_err(gates.cpu().numpy(), g_ref) < 2e-5

@@ -117,3 +117,12 @@ def test_vrnn_step_with_tcgen05_input_projections():
     out, g = util.oracle_vrnn(case, **KW)
     e = util.engine_for(case, "vrnn", use_graph=False, gemm_algo=1, **KW)
     check_step(e, out, g)
+
+
+def test_vrnn_step_large_batch_tensor_core_recurrence():
+    """B >= 1024 switches the forward recurrence to tcgen05 (plus tcgen05 projections and weight
+    gradients): the whole step still meets the 1e-4 bound against the float64 oracle."""
+    case = util.make_vrnn_case(1234, 1024, 6, C=10, Z=2, use_x_prev=True)
+    out, g = util.oracle_vrnn(case, **KW)
+    e = util.engine_for(case, "vrnn", use_graph=False, **KW)
+    check_step(e, out, g)
