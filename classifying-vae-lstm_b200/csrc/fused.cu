@@ -34,64 +34,68 @@ xhead_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const fl
   float* h_s = KT_s + XD * XD;        // [XR][XD] h tile, later the dlogits tile
   __shared__ float red[32];
   const int tid = threadIdx.x, j = tid % XD, rq = tid / XD;   // rq in 0..3 -> rows 8rq..8rq+7
-  const int64_t row0 = (int64_t)blockIdx.x * XR;
   for (int i = tid; i < XD * XD; i += XT) {
     const float v = __ldg(Kx + i);
     K_s[i] = v;
     KT_s[(i % XD) * XD + (i / XD)] = v;
   }
-  for (int i = tid; i < XR * XD; i += XT) {
-    const int64_t r = row0 + i / XD;
-    h_s[i] = (r < R) ? __ldg(h + r * XD + (i % XD)) : 0.f;
-  }
-  __syncthreads();
-  float acc[8];
   const float b = __ldg(bx + j);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = b;
-#pragma unroll 4
-  for (int k = 0; k < XD; ++k) {
-    const float w = K_s[k * XD + j];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(h_s[(rq * 8 + i) * XD + k], w, acc[i]);
-  }
-  __syncthreads();   // all reads of the h tile done; it becomes the dlogits tile
   float lsum = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int64_t r = row0 + rq * 8 + i;
-    float dl = 0.f;
-    if (r < R) {
-      const int64_t g = r / x_grp;
-      const int64_t xrow = (int64_t)__ldg(x_off + g) + x_shift + (r - g * x_grp);
-      const float x = (float)__ldg(roll + xrow * XD + j);
-      const float p = sigmoid_f(acc[i]);
-      const float pc = fminf(fmaxf(p, CLV_EPS), 1.0f - CLV_EPS);
-      const float l = logf(pc / (1.0f - pc));
-      lsum += fmaxf(l, 0.f) - l * x + log1pf(expf(-fabsf(l)));
-      const bool pass = (p >= CLV_EPS) && (p <= 1.0f - CLV_EPS);
-      dl = pass ? scale * (pc - x) : 0.f;
-      if (do_backward) dlogits[r * XD + j] = dl;
+  // persistent over 32-row tiles: the head kernel (and its transpose) is staged once per CTA
+  for (int64_t row0 = (int64_t)blockIdx.x * XR; row0 < R; row0 += (int64_t)gridDim.x * XR) {
+    __syncthreads();   // previous tile fully consumed (and K_s visible on the first pass)
+    for (int i = tid; i < XR * XD; i += XT) {
+      const int64_t r = row0 + i / XD;
+      h_s[i] = (r < R) ? __ldg(h + r * XD + (i % XD)) : 0.f;
     }
-    h_s[(rq * 8 + i) * XD + j] = dl;
-  }
-  const float t = block_sum(lsum, red);   // contains __syncthreads: the dlogits tile is complete
-  if (tid == 0) atomicAdd(loss_acc + 0, t * scale);
-  if (!do_backward) return;
-  // dh[r][k] = sum_d dlogits[r][d] * Kx[k][d]
+    __syncthreads();
+    float acc[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 8; ++i) acc[i] = b;
 #pragma unroll 4
-  for (int d = 0; d < XD; ++d) {
-    const float w = KT_s[d * XD + j];
+    for (int k = 0; k < XD; ++k) {
+      const float w = K_s[k * XD + j];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(h_s[(rq * 8 + i) * XD + d], w, acc[i]);
-  }
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(h_s[(rq * 8 + i) * XD + k], w, acc[i]);
+    }
+    __syncthreads();   // all reads of the h tile done; it becomes the dlogits tile
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int64_t r = row0 + rq * 8 + i;
-    if (r < R) dh[r * XD + j] = acc[i];
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = row0 + rq * 8 + i;
+      float dl = 0.f;
+      if (r < R) {
+        const int64_t g = r / x_grp;
+        const int64_t xrow = (int64_t)__ldg(x_off + g) + x_shift + (r - g * x_grp);
+        const float x = (float)__ldg(roll + xrow * XD + j);
+        const float p = sigmoid_f(acc[i]);
+        const float pc = fminf(fmaxf(p, CLV_EPS), 1.0f - CLV_EPS);
+        const float l = logf(pc / (1.0f - pc));
+        lsum += fmaxf(l, 0.f) - l * x + log1pf(expf(-fabsf(l)));
+        const bool pass = (p >= CLV_EPS) && (p <= 1.0f - CLV_EPS);
+        dl = pass ? scale * (pc - x) : 0.f;
+        if (do_backward) dlogits[r * XD + j] = dl;
+      }
+      h_s[(rq * 8 + i) * XD + j] = dl;
+    }
+    if (!do_backward) continue;
+    __syncthreads();   // the dlogits tile is complete
+    // dh[r][k] = sum_d dlogits[r][d] * Kx[k][d]
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < XD; ++d) {
+      const float w = KT_s[d * XD + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(h_s[(rq * 8 + i) * XD + d], w, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = row0 + rq * 8 + i;
+      if (r < R) dh[r * XD + j] = acc[i];
+    }
   }
+  const float t = block_sum(lsum, red);
+  if (tid == 0) atomicAdd(loss_acc + 0, t * scale);
 }
 
 // ------------------------------------------------------------------------------ key encoder fwd
@@ -272,7 +276,9 @@ extern "C" int clv_xhead_fwd_bwd(const float* h, const float* Kx, const float* b
     CLV_CUDA(cudaFuncSetAttribute(xhead_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  xhead_kernel<<<(unsigned)((R + XR - 1) / XR), XT, smem, (cudaStream_t)stream>>>(
+  int64_t xgrid = (R + XR - 1) / XR;
+  if (xgrid > 3LL * clv_num_sms()) xgrid = 3LL * clv_num_sms();   // 3 CTAs (73 KB smem each) per SM
+  xhead_kernel<<<(unsigned)xgrid, XT, smem, (cudaStream_t)stream>>>(
       h, Kx, bx, roll, x_off, x_grp, x_shift, loss_acc, dlogits, dh, R, scale, do_backward);
   CLV_CHECK_LAUNCH();
   return CLV_OK;

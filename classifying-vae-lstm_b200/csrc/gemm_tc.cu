@@ -215,6 +215,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) inproj_tc_kernel(const TcArgs a
       const int s = it & 1, ph = (it >> 1) & 1;
       const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TM + q * 32;
       const int rows_valid = (int)max((int64_t)0, min((int64_t)32, a.M - m0));
+      uint32_t ragrp[8];                         // per-sequence addend row of the 8 rows this lane stores
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        ragrp[i] = a.rowadd ? (uint32_t)(m0 + 4 * i + rsub) / (uint32_t)a.ra_grp : 0u;
       mbar_wait(BAR(ACC_FULL + s), ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * ACC_STRIDE);
@@ -246,11 +250,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) inproj_tc_kernel(const TcArgs a
                     *reinterpret_cast<const float4*>(stage + (rr + rsub) * 36 + c4);
             }
           } else {
-            for (int rr = 0; rr < 32; rr += 4) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i;
               if (rr + rsub < rows_valid) {
                 float4 v = *reinterpret_cast<const float4*>(stage + (rr + rsub) * 36 + c4);
-                const float* ra = a.rowadd + ((m0 + rr + rsub) / a.ra_grp) * a.ldra + n;
-                v.x += __ldg(ra); v.y += __ldg(ra + 1); v.z += __ldg(ra + 2); v.w += __ldg(ra + 3);
+                const float4 ra = __ldg(reinterpret_cast<const float4*>(a.rowadd + (int64_t)ragrp[i] * a.ldra + n));
+                v.x += ra.x; v.y += ra.y; v.z += ra.z; v.w += ra.w;
                 *reinterpret_cast<float4*>(crow + (int64_t)rr * a.ldc) = v;
               }
             }

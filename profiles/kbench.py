@@ -79,3 +79,9 @@ Zsb = torch.randn(M, Z, device=dev)
 timeit("lstm_wgrad tcgen05", lambda: check(L_.clv_lstm_wgrad_tc(ptr(dAb), ptr(roll), ptr(off), L, 1, D, ptr(hh), ptr(Zsb), Z,
                                                              ptr(gKx), ptr(gU), ptr(gKz), M, H, st)))
 print("   operand bytes %.1f MB -> at HBM peak: %.1f us" % (M * (G * 4 + H * 4 + D) / 1e6, M * (G * 4 + H * 4 + D) / 6536e3))
+
+# ---- tensor-core recurrence (forward)
+gt = torch.randn(B, L, G, device=dev) * 0.5
+uscr = torch.zeros(L_.clv_lstm_fwd_tc_scratch_bytes() // 4, device=dev)
+timeit("lstm_fwd tcgen05", lambda: check(L_.clv_lstm_fwd_tc(ptr(gt), ptr(U), ptr(Zs), ptr(Kz), Z, ptr(h), ptr(c), ptr(uscr), B, L, H, st)))
+print("   streamed bytes %.1f MB -> at HBM peak: %.1f us" % (B * L * (2 * G + 2 * H) * 4 / 1e6, B * L * (2 * G + 2 * H) * 4 / 6536e3))
