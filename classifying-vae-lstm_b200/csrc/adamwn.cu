@@ -19,12 +19,38 @@ struct AdamPlan {
 
 constexpr int CT = 8, RL = 64, NTH = CT * RL;
 
+// P2P = true: the gradient all-reduce is FUSED into the optimizer.  Every rank's [grads | losses]
+// buffer lives in symmetric (peer-mapped) memory; after a cross-GPU barrier each rank's kernel reads
+// the N peer buffers over NVLink (plain ld.global on peer addresses), sums them in the fixed order
+// p = 0..N-1 (bitwise identical on every rank, so the replicas stay in lock-step) and applies the
+// update -- no separate collective launch, no extra pass over the gradient.
+struct PeerSet {
+  const float* const* peers;   // device array of n pointers (this rank's own buffer included)
+  int n;
+  float* gsum;                 // local scratch [P]: reduced gradient for the second pass
+  float* loss_out;             // local [8]: reduced loss scalars
+};
+
+template <bool P2P>
+__device__ __forceinline__ float load_grad(const float* __restrict__ G, const PeerSet& ps, int64_t e) {
+  if (!P2P) return G[e];
+  float g = 0.f;
+  for (int p = 0; p < ps.n; ++p) g += ps.peers[p][e];
+  return g;
+}
+
+template <bool P2P>
 __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* __restrict__ W,
                                                      const float* __restrict__ G,
                                                      float* __restrict__ state, const double lr,
                                                      const double b1d, const double b2d,
                                                      const float eps, const float gscale,
-                                                     const int weightnorm) {
+                                                     const int weightnorm, const PeerSet ps) {
+  if (P2P && blockIdx.x == 0 && threadIdx.x < 8) {
+    float v = 0.f;
+    for (int p = 0; p < ps.n; ++p) v += ps.peers[p][pl.P + threadIdx.x];
+    ps.loss_out[threadIdx.x] = v;
+  }
   __shared__ float red[2][RL][CT];
   __shared__ float col[4][CT];
   float* m = state;
@@ -52,7 +78,7 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
     const int64_t n = (rows == 0) ? cols : (int64_t)rows * cols;
     const int64_t i = (int64_t)lb * NTH + tid;
     if (i < n) {
-      const float g = G[off + i] * gscale;
+      const float g = load_grad<P2P>(G, ps, off + i) * gscale;
       const float mt = b1 * m[off + i] + (1.0f - b1) * g;
       const float vt = b2 * v[off + i] + (1.0f - b2) * g * g;
       m[off + i] = mt;
@@ -71,7 +97,9 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
 #pragma unroll 4
       for (int r = ry; r < rows; r += RL) {
         const int64_t e = off + (int64_t)r * cols + c;
-        const float V = W[e] / vs, g = G[e] * gscale;
+        const float graw = load_grad<P2P>(G, ps, e);
+        if (P2P) ps.gsum[e] = graw;
+        const float V = W[e] / vs, g = graw * gscale;
         svv = fmaf(V, V, svv);
         sgv = fmaf(g, V, sgv);
       }
@@ -109,7 +137,7 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
           const int r = r0 + u * RL;
           if (r < rows) {
             const int64_t e = off + (int64_t)r * cols + c;
-            Wv[u] = W[e]; Gv[u] = G[e]; Mv[u] = m[e]; Vv[u] = v[e];
+            Wv[u] = W[e]; Gv[u] = P2P ? ps.gsum[e] : G[e]; Mv[u] = m[e]; Vv[u] = v[e];
           }
         }
 #pragma unroll
@@ -221,8 +249,25 @@ extern "C" int clv_adamwn_step(const clv_cfg* cfg, float* params, const float* g
   AdamPlan pl;
   int rc = make_plan(cfg, &pl, weightnorm);
   if (rc != CLV_OK) return rc;
-  adamwn_kernel<<<pl.first_block[CLV_N_TENSORS], NTH, 0, (cudaStream_t)stream>>>(
-      pl, params, grads, state, lr, beta_1, beta_2, (float)epsilon, (float)grad_scale, weightnorm);
+  PeerSet ps = {nullptr, 0, nullptr, nullptr};
+  adamwn_kernel<false><<<pl.first_block[CLV_N_TENSORS], NTH, 0, (cudaStream_t)stream>>>(
+      pl, params, grads, state, lr, beta_1, beta_2, (float)epsilon, (float)grad_scale, weightnorm, ps);
+  CLV_CHECK_LAUNCH();
+  return CLV_OK;
+}
+
+extern "C" int clv_adamwn_step_p2p(const clv_cfg* cfg, float* params, const float* const* peer_grads,
+                                   int32_t n_peers, float* gsum, float* loss_out, float* state,
+                                   double lr, double beta_1, double beta_2, double epsilon,
+                                   int32_t weightnorm, void* stream) {
+  if (!cfg || !params || !peer_grads || !gsum || !loss_out || !state) return CLV_E_INVALID;
+  if (n_peers < 1 || n_peers > 16) return CLV_E_UNSUPPORTED;
+  AdamPlan pl;
+  int rc = make_plan(cfg, &pl, weightnorm);
+  if (rc != CLV_OK) return rc;
+  PeerSet ps = {peer_grads, n_peers, gsum, loss_out};
+  adamwn_kernel<true><<<pl.first_block[CLV_N_TENSORS], NTH, 0, (cudaStream_t)stream>>>(
+      pl, params, nullptr, state, lr, beta_1, beta_2, (float)epsilon, 1.0f, weightnorm, ps);
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }

@@ -41,7 +41,7 @@ class Engine:
                  class_weight=1.0, kl_weight=1.0, w_kl_weight=1.0, w_log_var_prior=0.0,
                  optimizer="adam-wn", lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-8,
                  seed=0, device=None, world_size=1, rank=0, process_group=None, use_graph=True,
-                 overlap_wgrad=True, gemm_algo=1):
+                 overlap_wgrad=True, gemm_algo=1, p2p_allreduce=True):
         _require_cuda()
         lib()
         if optimizer not in ("adam-wn", "adam"):
@@ -70,8 +70,28 @@ class Engine:
         self.P, self.offs, self.rows, self.cols = _lib.param_layout(cfg)
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.params = torch.zeros(self.P, **f32)
-        self.gradbuf = torch.zeros(self.P + 8, **f32)                  # [grads | 8 loss scalars]
+        # [grads | 8 loss scalars].  Data parallel: the buffer lives in symmetric (peer-mapped) memory so
+        # the all-reduce can be fused into the Adam-WN kernel (clv_adamwn_step_p2p); falls back to an
+        # NCCL all-reduce if symmetric memory cannot be set up.
+        self.symm = None
+        if world_size > 1 and p2p_allreduce:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                group = process_group if process_group is not None else torch.distributed.group.WORLD
+                self.gradbuf = symm_mem.empty(self.P + 8, dtype=torch.float32, device=self.dev)
+                self.gradbuf.zero_()
+                self.symm = symm_mem.rendezvous(self.gradbuf, group)
+                self.peer_ptrs = torch.tensor([int(x) for x in self.symm.buffer_ptrs], dtype=torch.int64,
+                                              device=self.dev)
+                self.gsum = torch.zeros(self.P, **f32)
+                self.loss_red = torch.zeros(8, **f32)
+            except Exception as ex:  # noqa: BLE001
+                print("[clvae_b200] symmetric memory unavailable (%s): using NCCL all-reduce" % (ex,))
+                self.symm = None
+        if self.symm is None:
+            self.gradbuf = torch.zeros(self.P + 8, **f32)
         self.grads, self.loss_acc = self.gradbuf[:self.P], self.gradbuf[self.P:]
+        self._loss_src = self.loss_acc
         n_state = check(lib().clv_adamwn_state_floats(C.byref(cfg)), "clv_adamwn_state_floats")
         self.opt_state = torch.zeros(n_state, **f32)
         check(lib().clv_adamwn_init(C.byref(cfg), ptr(self.opt_state), _stream()), "clv_adamwn_init")
@@ -187,6 +207,16 @@ class Engine:
                                    ptr(self.eps_w), ptr(self.eps_z), ptr(self.rng_ctr),
                                    ptr(self.workspace), self.workspace.numel() * 4, _stream()),
               "clv_train_step")
+        if train and self.symm is not None:
+            # fused path: barrier (all ranks' gradients written) -> Adam-WN reads the peers' buffers over
+            # NVLink and reduces in-kernel -> barrier (all peers done reading before anyone overwrites)
+            self.symm.barrier(channel=0)
+            check(lib().clv_adamwn_step_p2p(C.byref(cfg), ptr(self.params), ptr(self.peer_ptrs),
+                                            self.world_size, ptr(self.gsum), ptr(self.loss_red),
+                                            ptr(self.opt_state), self.lr, self.b1, self.b2, self.eps,
+                                            int(self.optimizer == "adam-wn"), _stream()), "clv_adamwn_step_p2p")
+            self.symm.barrier(channel=1)
+            return
         if self.world_size > 1:
             buf = self.gradbuf if train else self.loss_acc
             torch.distributed.all_reduce(buf, group=self.pg)
@@ -199,6 +229,8 @@ class Engine:
         """Launch one step on the current stream using the staged batch.  With use_graph the launch
         sequence (fwd+bwd kernels, NCCL all-reduce, Adam-WN) is captured once per
         (train, gen_noise, roll buffer) and replayed."""
+        # where the (globally reduced) loss scalars of this step end up
+        self._loss_src = self.loss_red if (train and self.symm is not None) else self.loss_acc
         if not self.use_graph:
             n0 = lib().clv_launch_count()
             self._launch_step(train, gen_noise)
@@ -224,7 +256,7 @@ class Engine:
 
     def read_losses(self):
         """D2H of the 5 scalars (already global means) -> dict incl. Keras' weighted total."""
-        self.loss_host.copy_(self.loss_acc, non_blocking=True)
+        self.loss_host.copy_(self._loss_src, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         v = self.loss_host.tolist()
         d = dict(zip(LOSS_NAMES, v[:5]))

@@ -204,7 +204,7 @@ class BaseModel:
         for i in range(n // B):
             e.stage_offsets(off_all[i * B:(i + 1) * B], lab_all[i * B:(i + 1) * B])
             e.run(train=train, gen_noise=True)
-            acc += e.loss_acc
+            acc += e._loss_src
         v = (acc / (n // B)).tolist()
         d = dict(zip(LOSS_NAMES, v[:5]))
         h = e.hyper

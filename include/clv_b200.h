@@ -232,6 +232,16 @@ int clv_adamwn_step(const clv_cfg* cfg, float* params, const float* grads, float
                     double beta_1, double beta_2, double epsilon, double grad_scale, int32_t weightnorm,
                     void* stream);
 
+/* Data-parallel form: gradient all-reduce FUSED into the optimizer over NVLink peer memory.
+ * peer_grads = device array of n_peers pointers to every rank's [grads(P) | losses(8)] buffer in
+ * symmetric (peer-mapped) memory, in rank order, own buffer included.  The caller places a
+ * cross-GPU barrier before the call (all gradients written) and after it (all peers done reading).
+ * Each rank sums the peers in rank order (bitwise identical everywhere), keeps the reduced gradient
+ * in gsum[P] for the second pass and writes the reduced loss scalars to loss_out[8]. */
+int clv_adamwn_step_p2p(const clv_cfg* cfg, float* params, const float* const* peer_grads,
+                        int32_t n_peers, float* gsum, float* loss_out, float* state, double lr,
+                        double beta_1, double beta_2, double epsilon, int32_t weightnorm, void* stream);
+
 /* ---------------------------------------------------------------- fused training step ----- */
 /* zero loss_acc[8] (zero_losses) and advance the device RNG call counter (bump). */
 int clv_step_begin(float* loss_acc, uint64_t* rng_ctr, int32_t zero_losses, int32_t bump,

@@ -1,0 +1,58 @@
+"""Run under torchrun with >= 2 GPUs: the fused peer-memory all-reduce + Adam-WN path must track the
+NCCL all-reduce path (same data, same noise tapes) and keep all ranks' parameters bit-identical."""
+import os
+import sys
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import util  # noqa: E402
+from clvae_b200.engine import Engine  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = 24
+    case = util.make_vrnn_case(5, B * world, 6, C=4, Z=2)
+    sl = slice(rank * B, (rank + 1) * B)
+    results = {}
+    for mode, use_graph in (("nccl", False), ("p2p", False), ("p2p", True)):
+        e = Engine("vrnn", B, L=6, D=88, H=88, Z=2, n_classes=4, use_x_prev=True, world_size=world, rank=rank,
+                   use_graph=use_graph, p2p_allreduce=(mode == "p2p"))
+        assert (e.symm is not None) == (mode == "p2p"), "symmetric memory set-up failed"
+        e.set_params({k: v.numpy() for k, v in case["p"].items()})
+        e.stage_windows(torch.tensor(case["win"][sl]).cuda(), torch.tensor(case["labels"][sl]).cuda())
+        e.eps_w.copy_(torch.tensor(case["eps_w"][sl], dtype=torch.float32).reshape(-1))
+        e.eps_z.copy_(torch.tensor(case["eps_z"][sl], dtype=torch.float32).reshape(-1))
+        losses = []
+        for _ in range(4):
+            e.run(train=True, gen_noise=False)
+            losses.append(e.read_losses()["loss"])
+        torch.cuda.synchronize()
+        results[(mode, use_graph)] = (losses, e.params.clone())
+        # replicas in lock-step: parameters bit-identical on every rank
+        ref = e.params.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(ref, e.params), "ranks diverged in mode %s" % mode
+    base_l, base_p = results[("nccl", False)]
+    for key in (("p2p", False), ("p2p", True)):
+        l, p = results[key]
+        assert np.allclose(l, base_l, rtol=2e-5), (key, l, base_l)
+        err = float((p - base_p).abs().max() / base_p.abs().max())
+        assert err < 2e-5, (key, err)
+    # against the single-process oracle on the full batch (first step loss)
+    if rank == 0:
+        out, _ = util.oracle_vrnn(case)
+        assert abs(base_l[0] - float(out["loss"])) < 1e-4 * float(out["loss"])
+        print("P2P_CHECK_OK world=%d losses=%s" % (world, ["%.5f" % x for x in base_l]), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    os._exit(0)
+
+
+if __name__ == "__main__":
+    main()

@@ -126,3 +126,15 @@ def test_vrnn_step_large_batch_tensor_core_recurrence():
     out, g = util.oracle_vrnn(case, **KW)
     e = util.engine_for(case, "vrnn", use_graph=False, **KW)
     check_step(e, out, g)
+
+
+def test_fused_p2p_allreduce_adam_matches_nccl_on_two_gpus():
+    """Needs >= 2 GPUs (skipped on the 1-GPU box): launches tests/dist_p2p_check.py under torchrun."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dist_p2p_check.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", script],
+                       capture_output=True, text=True, timeout=300)
+    assert "P2P_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
