@@ -23,7 +23,7 @@ class clv_cfg(C.Structure):
                 ("class_weight", C.c_float), ("kl_weight", C.c_float), ("w_kl_weight", C.c_float),
                 ("w_log_var_prior", C.c_float),
                 ("gen_noise", C.c_int32), ("do_backward", C.c_int32), ("accumulate", C.c_int32),
-                ("gemm_algo", C.c_int32), ("x_shift", C.c_int32), ("overlap_wgrad", C.c_int32),
+                ("gemm_algo", C.c_int32), ("x_shift", C.c_int32), ("gemm_algo_tc_lstm_min", C.c_int32), ("overlap_wgrad", C.c_int32),
                 ("seed", C.c_uint64)]
 
 
@@ -72,6 +72,8 @@ PROTOTYPES = {
     "clv_keyenc_fwd": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32,
                                  _F, _F, _I32, _U64, _P, _P]),
     "clv_keyenc_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _F, _F, _F, _P]),
+    "clv_keyenc_bwd_full": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                      _I32, _I32, _F, _F, _F, _P]),
     "clv_bernoulli_ce_fwd_bwd": (C.c_int, [_P, _P, _P, _I32, _I32, _P, _I64, _I32, _F, _I32, _P]),
     "clv_adamwn_state_floats": (_I64, [_CFG]),
     "clv_adamwn_init": (C.c_int, [_CFG, _P, _P]),
@@ -118,12 +120,13 @@ def ptr(t):
 
 def make_cfg(model, B, L, D, H, Z, C_, use_x_prev, Hc=0, B_global=None, class_weight=1.0,
              kl_weight=1.0, w_kl_weight=1.0, w_log_var_prior=0.0, gen_noise=0, do_backward=1,
-             accumulate=0, gemm_algo=0, seed=0, x_shift=0, overlap_wgrad=0):
+             accumulate=0, gemm_algo=0, seed=0, x_shift=0, overlap_wgrad=0, tc_lstm_min=0):
     return clv_cfg(model=model, B=B, B_global=B if B_global is None else B_global, L=L, D=D, H=H,
                    Hc=Hc, Z=Z, C=C_, use_x_prev=int(bool(use_x_prev)), class_weight=class_weight,
                    kl_weight=kl_weight, w_kl_weight=w_kl_weight, w_log_var_prior=w_log_var_prior,
                    gen_noise=gen_noise, do_backward=do_backward, accumulate=accumulate,
-                   gemm_algo=gemm_algo, x_shift=x_shift, overlap_wgrad=overlap_wgrad, seed=seed)
+                   gemm_algo=gemm_algo, x_shift=x_shift, gemm_algo_tc_lstm_min=tc_lstm_min,
+                   overlap_wgrad=overlap_wgrad, seed=seed)
 
 
 def param_layout(cfg):

@@ -260,6 +260,107 @@ keyenc_bwd_kernel(const float* __restrict__ Wargs, const float* __restrict__ eps
     }
 }
 
+// ------------------------------------------------------------------------------ key encoder bwd + wgrads
+// One CTA per sequence: K2 backward -> dWargs -> dhW, and ALL four weight gradients of the key encoder
+// accumulated with red.add: dK_Wa (outer product), db_Wa, db_hW and dK_hW -- the latter as a sparse
+// scatter of dhW into the kernel rows of the SET keys of the window (the transpose of the forward
+// gather-sum), so no dense [L*D, B] x [B, D] GEMM and no launch remains behind this kernel.
+__global__ void __launch_bounds__(KT)
+keyenc_bwd_full_kernel(const uint8_t* __restrict__ roll, const int32_t* __restrict__ off, const int shift,
+                       const int L, const int D, const float* __restrict__ Wargs,
+                       const float* __restrict__ eps_w, const int32_t* __restrict__ labels,
+                       const float* __restrict__ W, const float* __restrict__ dW_ext,
+                       const float* __restrict__ Kwa, const float* __restrict__ hW,
+                       float* __restrict__ dWargs, float* __restrict__ dhW, float* __restrict__ gKhw,
+                       float* __restrict__ gbhw, float* __restrict__ gKwa, float* __restrict__ gbwa,
+                       const int C, const float prior, const float cw_over_B, const float wkl_over_B) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  const int n = L * D, nwords = n >> 2;
+  uint32_t* win_s = reinterpret_cast<uint32_t*>(dyn);
+  uint16_t* list_s = reinterpret_cast<uint16_t*>(dyn + (size_t)nwords * 4);
+  __shared__ int cnt_s[KT + 1];
+  __shared__ float dwa_s[32];
+  __shared__ float dhw_s[128];
+  __shared__ float hw_s[128];
+  const int tid = threadIdx.x, b = blockIdx.x;
+  const int C1 = C - 1, NW = 2 * C1;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(roll + ((size_t)__ldg(off + b) + shift) * D);
+  for (int i = tid; i < nwords; i += KT) win_s[i] = __ldg(src + i);
+  if (tid < D) hw_s[tid] = __ldg(hW + (size_t)b * D + tid);
+  // ---- K2 backward on lanes 0..15 of warp 0 (same maths as logitnormal_bwd_kernel)
+  if (tid < 32) {
+    const int j = tid & 15;
+    float w = 0.f, dwe = 0.f;
+    if (j < C) { w = __ldg(W + (size_t)b * C + j); dwe = __ldg(dW_ext + (size_t)b * C + j); }
+    const int lab = __ldg(labels + b);
+    const float w2 = (j < C) ? (w + 1e-10f) : 0.f;
+    const float S = seg16_sum(w2);
+    const float q = w2 / S;
+    const bool pass = (q >= CLV_EPS) && (q <= 1.0f - CLV_EPS);
+    const float qc = fminf(fmaxf(q, CLV_EPS), 1.0f - CLV_EPS);
+    const float dq = (j == lab && j < C && pass) ? (-(float)C1 / qc) * cw_over_B : 0.f;
+    const float dqw = seg16_sum(dq * w2);
+    const float dWv = (j < C) ? (dwe + dq / S - dqw / (S * S)) : 0.f;
+    const float dot = seg16_sum(dWv * w);
+    const float ds = w * (dWv - dot);
+    if (j < C1 && tid < 16) {
+      const float mu = __ldg(Wargs + (size_t)b * NW + j), lv = __ldg(Wargs + (size_t)b * NW + C1 + j);
+      const float eps = __ldg(eps_w + (size_t)b * C1 + j);
+      const float ep = expf(prior);
+      const float dm = ds + wkl_over_B * mu / ep;
+      const float dv = ds * eps * 0.5f * expf(lv * 0.5f) + wkl_over_B * (-0.5f) * (1.0f - expf(lv) / ep);
+      dWargs[(size_t)b * NW + j] = dm; dWargs[(size_t)b * NW + C1 + j] = dv;
+      dwa_s[j] = dm; dwa_s[C1 + j] = dv;
+    }
+  }
+  __syncthreads();
+  // ---- ordered compaction of the set keys (as in the forward kernel)
+  const int chunk = (nwords + KT - 1) / KT;
+  const int w0 = tid * chunk, w1 = min(nwords, w0 + chunk);
+  int cnt = 0;
+  for (int i = w0; i < w1; ++i) {
+    const uint32_t v = win_s[i];
+    cnt += (v & 0xffu ? 1 : 0) + (v & 0xff00u ? 1 : 0) + (v & 0xff0000u ? 1 : 0) + (v & 0xff000000u ? 1 : 0);
+  }
+  cnt_s[tid + 1] = cnt;
+  if (tid == 0) cnt_s[0] = 0;
+  // ---- dhW = (dWargs @ Kwa^T) * [hW > 0];  bias gradients
+  if (tid < D) {
+    float a = 0.f;
+    for (int o = 0; o < NW; ++o) a = fmaf(dwa_s[o], __ldg(Kwa + (size_t)tid * NW + o), a);
+    a = (hw_s[tid] > 0.f) ? a : 0.f;
+    dhw_s[tid] = a;
+    dhW[(size_t)b * D + tid] = a;
+    if (a != 0.f) atomicAdd(gbhw + tid, a);
+  }
+  if (tid < NW) atomicAdd(gbwa + tid, dwa_s[tid]);
+  __syncthreads();
+  if (tid == 0)
+    for (int i = 1; i <= KT; ++i) cnt_s[i] += cnt_s[i - 1];
+  // ---- dK_Wa += hW^T (x) dWargs   (outer product of this sequence)
+  for (int i = tid; i < D * NW; i += KT) {
+    const int j = i / NW, o = i - j * NW;
+    const float hv = hw_s[j];
+    if (hv != 0.f) atomicAdd(gKwa + i, hv * dwa_s[o]);
+  }
+  __syncthreads();
+  int pos = cnt_s[tid];
+  for (int i = w0; i < w1; ++i) {
+    const uint32_t v = win_s[i];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if ((v >> (8 * q)) & 0xffu) list_s[pos++] = (uint16_t)(4 * i + q);
+  }
+  const int nact = cnt_s[KT];
+  __syncthreads();
+  // ---- dK_hW[p, :] += dhW for every set key p of the window (sparse scatter, coalesced rows)
+  if (tid < D) {
+    const float g = dhw_s[tid];
+    if (g != 0.f)
+      for (int i = 0; i < nact; ++i) atomicAdd(gKhw + (size_t)list_s[i] * D + tid, g);
+  }
+}
+
 }  // namespace
 
 extern "C" int clv_xhead_fwd_bwd(const float* h, const float* Kx, const float* bx,
@@ -320,6 +421,32 @@ extern "C" int clv_keyenc_bwd(const float* Wargs, const float* eps_w, const int3
   keyenc_bwd_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
       Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, B, C, D, w_log_var_prior, cw_over_B,
       wkl_over_B);
+  CLV_CHECK_LAUNCH();
+  return CLV_OK;
+}
+
+extern "C" int clv_keyenc_bwd_full(const uint8_t* roll, const int32_t* win_off, int32_t shift, int32_t L,
+                                   int32_t D, const float* Wargs, const float* eps_w,
+                                   const int32_t* labels, const float* W, const float* dW_ext,
+                                   const float* Kwa, const float* hW, float* dWargs, float* dhW,
+                                   float* gKhw, float* gbhw, float* gKwa, float* gbwa, int32_t B,
+                                   int32_t C, float w_log_var_prior, float cw_over_B, float wkl_over_B,
+                                   void* stream) {
+  if (!roll || !win_off || !Wargs || !eps_w || !labels || !W || !dW_ext || !Kwa || !hW || !dWargs || !dhW ||
+      !gKhw || !gbhw || !gKwa || !gbwa)
+    return CLV_E_INVALID;
+  if (C < 2 || C > 16 || D > 128 || (D & 3) || (int64_t)L * D > 65535) return CLV_E_UNSUPPORTED;
+  if (B <= 0) return CLV_OK;
+  const size_t smem = (size_t)L * D + 2 * (size_t)L * D + 16;
+  static size_t attr_smem = 48 * 1024;
+  if (smem > attr_smem) {
+    if (smem > 227 * 1024) return CLV_E_UNSUPPORTED;
+    CLV_CUDA(cudaFuncSetAttribute(keyenc_bwd_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  keyenc_bwd_full_kernel<<<B, KT, smem, (cudaStream_t)stream>>>(
+      roll, win_off, shift, L, D, Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, gKhw, gbhw, gKwa,
+      gbwa, C, w_log_var_prior, cw_over_B, wkl_over_B);
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }

@@ -27,6 +27,10 @@ extern "C" int clv_keyenc_fwd(const uint8_t*, const int32_t*, int32_t, int32_t, 
                               const float*, const float*, const float*, float*, const int32_t*, float*,
                               float*, float*, float*, int32_t, int32_t, float, float, int32_t, uint64_t,
                               const uint64_t*, void*);
+extern "C" int clv_keyenc_bwd_full(const uint8_t*, const int32_t*, int32_t, int32_t, int32_t, const float*,
+                                   const float*, const int32_t*, const float*, const float*, const float*,
+                                   const float*, float*, float*, float*, float*, float*, float*, int32_t,
+                                   int32_t, float, float, float, void*);
 extern "C" int clv_keyenc_bwd(const float*, const float*, const int32_t*, const float*, const float*,
                               const float*, const float*, float*, float*, int32_t, int32_t, int32_t, float,
                               float, float, void*);
@@ -224,7 +228,9 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   const bool tc = c->gemm_algo == 1 && G == 352 && D <= 96 && (D % 8) == 0;
   // tensor-core recurrence: wins once a CTA can be given 128 rows (large batches); below that the
   // register-resident FFMA kernel is latency-optimal
-  const bool tcl = tc && c->use_x_prev && B >= 1024 && Z <= 16;
+  // measured crossover on B200: 128-row CTAs are latency-bound (~30 us/step), so the chip must be
+  // filled (>= 64 CTAs) before tensor cores beat the 2..8-row FFMA kernel
+  const bool tcl = tc && c->use_x_prev && B >= (c->gemm_algo_tc_lstm_min > 0 ? c->gemm_algo_tc_lstm_min : 8192) && Z <= 16;
   const float *Khw = P + po[R_HW_K], *bhw = P + po[R_HW_B], *Kwa = P + po[R_WA_K],
               *bwa = P + po[R_WA_B], *Ke = P + po[R_ENC_K], *Ue = P + po[R_ENC_U],
               *be = P + po[R_ENC_B], *Kzm = P + po[R_ZM_K], *bzm = P + po[R_ZM_B],
@@ -337,13 +343,20 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   }
   TRY(tn_f32(W, C, dAsum_e, G, gKe + (int64_t)D * G, G, C, G, B, 0, 0, fk.next()));
   TRY(clv_colsum(dAsum_e, G, B, G, gbe, 1, fk.next()));
-  TRY(clv_keyenc_bwd(Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, B, C, D,
-                     c->w_log_var_prior, c->class_weight * sb, c->w_kl_weight * sb, st));
-  TRY(fk.fork());
-  TRY(tn_f32(hW, D, dWargs, 2 * C1, gKwa, 2 * C1, D, 2 * C1, B, 0, 0, fk.next()));
-  TRY(clv_colsum(dWargs, 2 * C1, B, 2 * C1, gbwa, 1, fk.next()));
-  TRY(tn_u8(roll, off, 1, sx, D, dhW, D, gKhw, D, L * D, D, B, fk.next()));
-  TRY(clv_colsum(dhW, D, B, D, gbhw, 1, fk.next()));
+  if (fused_ke) {
+    // K2 backward + every key-encoder weight gradient in one kernel (sparse scatter for dK_hW)
+    TRY(clv_keyenc_bwd_full(roll, off, sx, L, D, Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, gKhw,
+                            gbhw, gKwa, gbwa, B, C, c->w_log_var_prior, c->class_weight * sb,
+                            c->w_kl_weight * sb, st));
+  } else {
+    TRY(clv_keyenc_bwd(Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, B, C, D,
+                       c->w_log_var_prior, c->class_weight * sb, c->w_kl_weight * sb, st));
+    TRY(fk.fork());
+    TRY(tn_f32(hW, D, dWargs, 2 * C1, gKwa, 2 * C1, D, 2 * C1, B, 0, 0, fk.next()));
+    TRY(clv_colsum(dWargs, 2 * C1, B, 2 * C1, gbwa, 1, fk.next()));
+    TRY(tn_u8(roll, off, 1, sx, D, dhW, D, gKhw, D, L * D, D, B, fk.next()));
+    TRY(clv_colsum(dhW, D, B, D, gbhw, 1, fk.next()));
+  }
   TRY(fk.join());
   return CLV_OK;
 }

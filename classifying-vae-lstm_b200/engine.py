@@ -41,7 +41,7 @@ class Engine:
                  class_weight=1.0, kl_weight=1.0, w_kl_weight=1.0, w_log_var_prior=0.0,
                  optimizer="adam-wn", lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-8,
                  seed=0, device=None, world_size=1, rank=0, process_group=None, use_graph=True,
-                 overlap_wgrad=True, gemm_algo=1, p2p_allreduce=False):
+                 overlap_wgrad=True, gemm_algo=1, p2p_allreduce=False, tc_lstm_min=0):
         _require_cuda()
         lib()
         if optimizer not in ("adam-wn", "adam"):
@@ -61,6 +61,7 @@ class Engine:
         self.seed = (int(seed) * 1000003 + rank * 7919 + 1) & 0xFFFFFFFFFFFFFFFF
         self.use_graph = use_graph
         self.overlap_wgrad = bool(overlap_wgrad)
+        self.tc_lstm_min = int(tc_lstm_min)        # 0 = library default (8192)
         self.gemm_algo = int(gemm_algo)            # 0: exact-fp32 SIMT GEMMs, 1: tcgen05 input projections
         if self.overlap_wgrad:
             with torch.cuda.device(self.dev):
@@ -116,6 +117,7 @@ class Engine:
         kw = dict(model=self.model, B=self.B, L=self.L, D=self.D, H=self.H, Z=self.Z, C_=self.C,
                   use_x_prev=self.use_x_prev, Hc=self.Hc, B_global=self.B * self.world_size,
                   seed=self.seed, x_shift=self.x_shift, overlap_wgrad=int(self.overlap_wgrad), gemm_algo=self.gemm_algo,
+                  tc_lstm_min=self.tc_lstm_min,
                   **self.hyper)
         kw.update(over)
         return _lib.make_cfg(**kw)

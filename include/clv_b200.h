@@ -60,6 +60,7 @@ typedef struct clv_cfg {
   int32_t x_shift;      /* frame of `current` inside a window; 0 = default (1 with use_x_prev
                            [history = frames 0..L-1, current = 1..L], else 0).  L for windows
                            stored as [history | current] when the two inputs do not overlap     */
+  int32_t gemm_algo_tc_lstm_min; /* batch from which the tcgen05 recurrence is used (0 = default 8192) */
   int32_t overlap_wgrad;/* 1: run the weight-gradient GEMMs on the library's auxiliary stream
                            (needs clv_runtime_init()); forked from / joined into `stream`       */
   uint64_t seed;        /* Philox key for gen_noise (make it rank-dependent)                  */
@@ -219,6 +220,15 @@ int clv_keyenc_bwd(const float* Wargs, const float* eps_w, const int32_t* labels
                    const float* dW_ext, const float* Kwa, const float* hW, float* dWargs, float* dhW,
                    int32_t B, int32_t C, int32_t D, float w_log_var_prior, float cw_over_B,
                    float wkl_over_B, void* stream);
+
+/* clv_keyenc_bwd plus ALL key-encoder weight gradients in the same kernel (one CTA per sequence):
+ * gKwa += hW^T (x) dWargs, gbwa, gbhw, and gKhw[p,:] += dhW for every SET key p of the window -- the
+ * sparse-scatter transpose of the forward gather-sum (red.add into pre-zeroed gradients). */
+int clv_keyenc_bwd_full(const uint8_t* roll, const int32_t* win_off, int32_t shift, int32_t L, int32_t D,
+                        const float* Wargs, const float* eps_w, const int32_t* labels, const float* W,
+                        const float* dW_ext, const float* Kwa, const float* hW, float* dWargs, float* dhW,
+                        float* gKhw, float* gbhw, float* gKwa, float* gbwa, int32_t B, int32_t C,
+                        float w_log_var_prior, float cw_over_B, float wkl_over_B, void* stream);
 
 /* ---------------------------------------------------------------- K6: Adam + weight-norm -- */
 /* AdamWithWeightnorm.get_updates (utils/weightnorm.py:75-143,146-178) on the flat buffers.

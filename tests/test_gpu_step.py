@@ -124,7 +124,7 @@ def test_vrnn_step_large_batch_tensor_core_recurrence():
     gradients): the whole step still meets the 1e-4 bound against the float64 oracle."""
     case = util.make_vrnn_case(1234, 1024, 6, C=10, Z=2, use_x_prev=True)
     out, g = util.oracle_vrnn(case, **KW)
-    e = util.engine_for(case, "vrnn", use_graph=False, **KW)
+    e = util.engine_for(case, "vrnn", use_graph=False, tc_lstm_min=512, **KW)
     check_step(e, out, g)
 
 
