@@ -17,7 +17,7 @@ struct AdamPlan {
   int32_t NC;
 };
 
-constexpr int CT = 8, RL = 64, NTH = CT * RL;
+constexpr int CT = 8, RL = 128, NTH = CT * RL;
 
 // P2P = true: the gradient all-reduce is FUSED into the optimizer.  Every rank's [grads | losses]
 // buffer lives in symmetric (peer-mapped) memory; after a cross-GPU barrier each rank's kernel reads
