@@ -22,8 +22,12 @@ __device__ __forceinline__ float seg16_sum(float v) {
 constexpr int XR = 32;         // rows per CTA
 constexpr int XT = 352;        // threads: (column/unit, row-quarter)
 constexpr int XD = 88;         // D == H == 88 specialisation
+constexpr int XRP = 36;        // padded row count of the transposed [k][row] tiles (16-byte aligned)
 
-__global__ void __launch_bounds__(XT, 1)
+// MB = resident CTAs per SM the register allocation is capped for: 3 for grids that fill the GPU
+// (55 registers), 1 for the single-wave small-batch case (no cap, more load/FMA overlap).
+template <int MB>
+__global__ void __launch_bounds__(XT, MB)
 xhead_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const float* __restrict__ bx,
              const uint8_t* __restrict__ roll, const int32_t* __restrict__ x_off, const int x_grp,
              const int x_shift, float* __restrict__ loss_acc, float* __restrict__ dlogits,
@@ -31,7 +35,7 @@ xhead_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const fl
   extern __shared__ __align__(16) float sm[];
   float* K_s = sm;                    // [k][d]   (forward: lanes over d)
   float* KT_s = K_s + XD * XD;        // [d][k]   (dgrad: lanes over k)
-  float* h_s = KT_s + XD * XD;        // [XR][XD] h tile, later the dlogits tile
+  float* h_s = KT_s + XD * XD;        // [XD][XRP] TRANSPOSED h tile ([k][row]), later the dlogits tile
   __shared__ float red[32];
   const int tid = threadIdx.x, j = tid % XD, rq = tid / XD;   // rq in 0..3 -> rows 8rq..8rq+7
   for (int i = tid; i < XD * XD; i += XT) {
@@ -45,8 +49,9 @@ xhead_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const fl
   for (int64_t row0 = (int64_t)blockIdx.x * XR; row0 < R; row0 += (int64_t)gridDim.x * XR) {
     __syncthreads();   // previous tile fully consumed (and K_s visible on the first pass)
     for (int i = tid; i < XR * XD; i += XT) {
-      const int64_t r = row0 + i / XD;
-      h_s[i] = (r < R) ? __ldg(h + r * XD + (i % XD)) : 0.f;
+      const int rr = i / XD, k = i - rr * XD;
+      const int64_t r = row0 + rr;
+      h_s[k * XRP + rr] = (r < R) ? __ldg(h + r * XD + k) : 0.f;
     }
     __syncthreads();
     float acc[8];
@@ -55,8 +60,12 @@ xhead_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const fl
 #pragma unroll 4
     for (int k = 0; k < XD; ++k) {
       const float w = K_s[k * XD + j];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(h_s[(rq * 8 + i) * XD + k], w, acc[i]);
+      const float4 h0 = *reinterpret_cast<const float4*>(h_s + k * XRP + rq * 8);
+      const float4 h1 = *reinterpret_cast<const float4*>(h_s + k * XRP + rq * 8 + 4);
+      acc[0] = fmaf(h0.x, w, acc[0]); acc[1] = fmaf(h0.y, w, acc[1]);
+      acc[2] = fmaf(h0.z, w, acc[2]); acc[3] = fmaf(h0.w, w, acc[3]);
+      acc[4] = fmaf(h1.x, w, acc[4]); acc[5] = fmaf(h1.y, w, acc[5]);
+      acc[6] = fmaf(h1.z, w, acc[6]); acc[7] = fmaf(h1.w, w, acc[7]);
     }
     __syncthreads();   // all reads of the h tile done; it becomes the dlogits tile
 #pragma unroll
@@ -75,7 +84,7 @@ xhead_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const fl
         dl = pass ? scale * (pc - x) : 0.f;
         if (do_backward) dlogits[r * XD + j] = dl;
       }
-      h_s[(rq * 8 + i) * XD + j] = dl;
+      h_s[j * XRP + rq * 8 + i] = dl;
     }
     if (!do_backward) continue;
     __syncthreads();   // the dlogits tile is complete
@@ -85,8 +94,12 @@ xhead_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const fl
 #pragma unroll 4
     for (int d = 0; d < XD; ++d) {
       const float w = KT_s[d * XD + j];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(h_s[(rq * 8 + i) * XD + d], w, acc[i]);
+      const float4 g0 = *reinterpret_cast<const float4*>(h_s + d * XRP + rq * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(h_s + d * XRP + rq * 8 + 4);
+      acc[0] = fmaf(g0.x, w, acc[0]); acc[1] = fmaf(g0.y, w, acc[1]);
+      acc[2] = fmaf(g0.z, w, acc[2]); acc[3] = fmaf(g0.w, w, acc[3]);
+      acc[4] = fmaf(g1.x, w, acc[4]); acc[5] = fmaf(g1.y, w, acc[5]);
+      acc[6] = fmaf(g1.z, w, acc[6]); acc[7] = fmaf(g1.w, w, acc[7]);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -371,16 +384,25 @@ extern "C" int clv_xhead_fwd_bwd(const float* h, const float* Kx, const float* b
   if (do_backward && (!dlogits || !dh)) return CLV_E_INVALID;
   if (H != XD || D != XD) return CLV_E_UNSUPPORTED;
   if (R <= 0) return CLV_OK;
-  const size_t smem = sizeof(float) * (2 * XD * XD + XR * XD);
+  const size_t smem = sizeof(float) * (2 * XD * XD + XD * XRP);
   static bool attr_set = false;
   if (!attr_set) {
-    CLV_CUDA(cudaFuncSetAttribute(xhead_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CLV_CUDA(cudaFuncSetAttribute(xhead_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CLV_CUDA(cudaFuncSetAttribute(xhead_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // without this the driver sizes the carve-out for ONE block and the grid's co-residency is lost
+    CLV_CUDA(cudaFuncSetAttribute(xhead_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   int64_t xgrid = (R + XR - 1) / XR;
-  if (xgrid > 3LL * clv_num_sms()) xgrid = 3LL * clv_num_sms();   // 3 CTAs (73 KB smem each) per SM
-  xhead_kernel<<<(unsigned)xgrid, XT, smem, (cudaStream_t)stream>>>(
-      h, Kx, bx, roll, x_off, x_grp, x_shift, loss_acc, dlogits, dh, R, scale, do_backward);
+  if (xgrid <= clv_num_sms()) {
+    xhead_kernel<1><<<(unsigned)xgrid, XT, smem, (cudaStream_t)stream>>>(
+        h, Kx, bx, roll, x_off, x_grp, x_shift, loss_acc, dlogits, dh, R, scale, do_backward);
+  } else {
+    if (xgrid > 3LL * clv_num_sms()) xgrid = 3LL * clv_num_sms();   // 3 CTAs (73 KB smem each) per SM
+    xhead_kernel<3><<<(unsigned)xgrid, XT, smem, (cudaStream_t)stream>>>(
+        h, Kx, bx, roll, x_off, x_grp, x_shift, loss_acc, dlogits, dh, R, scale, do_backward);
+  }
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }
@@ -402,6 +424,9 @@ extern "C" int clv_keyenc_fwd(const uint8_t* roll, const int32_t* win_off, int32
   if (smem > attr_smem) {
     if (smem > 227 * 1024) return CLV_E_UNSUPPORTED;
     CLV_CUDA(cudaFuncSetAttribute(keyenc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // without this the driver sizes the carve-out for ONE block and the grid's co-residency is lost
+    CLV_CUDA(cudaFuncSetAttribute(keyenc_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared));
     attr_smem = smem;
   }
   keyenc_fwd_kernel<<<B, KT, smem, (cudaStream_t)stream>>>(
@@ -442,6 +467,9 @@ extern "C" int clv_keyenc_bwd_full(const uint8_t* roll, const int32_t* win_off, 
   if (smem > attr_smem) {
     if (smem > 227 * 1024) return CLV_E_UNSUPPORTED;
     CLV_CUDA(cudaFuncSetAttribute(keyenc_bwd_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // without this the driver sizes the carve-out for ONE block and the grid's co-residency is lost
+    CLV_CUDA(cudaFuncSetAttribute(keyenc_bwd_full_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared));
     attr_smem = smem;
   }
   keyenc_bwd_full_kernel<<<B, KT, smem, (cudaStream_t)stream>>>(

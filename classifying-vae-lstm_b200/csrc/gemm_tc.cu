@@ -6,11 +6,11 @@
 //   * the split/transposed weight image is built once per step by a tiny prep kernel directly in the
 //     UMMA canonical K-major (no-swizzle) shared-memory layout, so each CTA pulls it with three
 //     cp.async.bulk (TMA) copies completing on an mbarrier;
-//   * one elected thread issues the 18 MMAs (3 splits x 6 k-steps of 16) per 128x176 tile and commits
-//     to an mbarrier; four epilogue warps read TMEM with tcgen05.ld, add the optional per-sequence
-//     addend and store coalesced rows.
-// CTAs are persistent over row tiles (grid = 2 N-halves x ~SM/2), so the weight image is fetched once
-// per CTA.  Replaces the MatMul of `x @ kernel` inside Keras' LSTM preprocess_input
+//   * warp-specialised persistent CTAs (grid = 2 N-halves x SMs/2): four producer warps gather and
+//     convert the A tile, one elected thread issues the 18 MMAs (3 splits x 6 k-steps of 16) per
+//     128x176 tile and commits to mbarriers, four epilogue warps read TMEM with tcgen05.ld, add the
+//     optional per-sequence addend and store 128-bit coalesced rows; A tiles and TMEM accumulators
+//     are double-buffered so the store-bound epilogue runs back to back.  Replaces the MatMul of `x @ kernel` inside Keras' LSTM preprocess_input
 // (cl_vrnn/model.py:196-199,225-228 [K2-recall]).
 #include <cuda_bf16.h>
 #include "common.cuh"
@@ -26,8 +26,6 @@ constexpr int SBO_A = (KP / 8) * 128;  // bytes between 8-row groups (A and B im
 constexpr int A_BYTES = TM * KP * 2;           // 24 576
 constexpr int B_SPLIT_BYTES = TN * KP * 2;     // 33 792
 constexpr int B_BYTES = NSPLIT * B_SPLIT_BYTES;  // 101 376 per N-half
-constexpr int TMEM_COLS = 256;
-constexpr int NTHREADS = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -250,12 +248,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) inproj_tc_kernel(const TcArgs a
                     *reinterpret_cast<const float4*>(stage + (rr + rsub) * 36 + c4);
             }
           } else {
+            // the addend is per sequence: consecutive rows share it, so it is re-read only when the
+            // sequence index changes (once or twice per 32-row slab for L >= 16)
+            uint32_t gcur = 0xffffffffu;
+            float4 ra = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = 4 * i;
               if (rr + rsub < rows_valid) {
+                if (ragrp[i] != gcur) {
+                  gcur = ragrp[i];
+                  ra = __ldg(reinterpret_cast<const float4*>(a.rowadd + (int64_t)gcur * a.ldra + n));
+                }
                 float4 v = *reinterpret_cast<const float4*>(stage + (rr + rsub) * 36 + c4);
-                const float4 ra = __ldg(reinterpret_cast<const float4*>(a.rowadd + (int64_t)ragrp[i] * a.ldra + n));
                 v.x += ra.x; v.y += ra.y; v.z += ra.z; v.w += ra.w;
                 *reinterpret_cast<float4*>(crow + (int64_t)rr * a.ldc) = v;
               }

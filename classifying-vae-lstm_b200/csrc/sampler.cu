@@ -364,6 +364,11 @@ extern "C" int clv_vrnn_sample(const clv_cfg* cfg, const float* params, const fl
   if (!attr_set) {
     CLV_CUDA(cudaFuncSetAttribute(vrnn_sample_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_for(24)));
+    // 4 CTAs per SM need 140-210 KB of shared memory: ask for the maximum carve-out explicitly
+    CLV_CUDA(cudaFuncSetAttribute(vrnn_sample_kernel<24>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared));
+    CLV_CUDA(cudaFuncSetAttribute(vrnn_sample_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   if (cost24 < cost16)

@@ -85,3 +85,13 @@ gt = torch.randn(B, L, G, device=dev) * 0.5
 uscr = torch.zeros(L_.clv_lstm_fwd_tc_scratch_bytes() // 4, device=dev)
 timeit("lstm_fwd tcgen05", lambda: check(L_.clv_lstm_fwd_tc(ptr(gt), ptr(U), ptr(Zs), ptr(Kz), Z, ptr(h), ptr(c), ptr(uscr), B, L, H, st)))
 print("   streamed bytes %.1f MB -> at HBM peak: %.1f us" % (B * L * (2 * G + 2 * H) * 4 / 1e6, B * L * (2 * G + 2 * H) * 4 / 6536e3))
+
+# ---- input projection with the per-sequence addend (decoder form) and the fused X head
+rb = torch.randn(B, G, device=dev)
+timeit("inproj tcgen05 + rowadd", lambda: check(L_.clv_inproj_tc(ptr(roll), ptr(off), L, 0, D, ptr(Wk), G, G, ptr(scratch),
+                                                              ptr(Cout), G, M, ptr(rb), G, L, st)))
+Kxh = torch.randn(H, D, device=dev) * 0.1; bxh = torch.zeros(D, device=dev)
+lacc = torch.zeros(8, device=dev); dlg = torch.zeros(M, D, device=dev); dhx = torch.zeros(M, H, device=dev)
+timeit("xhead fwd+bwd", lambda: check(L_.clv_xhead_fwd_bwd(ptr(hh), ptr(Kxh), ptr(bxh), ptr(roll), ptr(off), L, 1, ptr(lacc),
+                                                        ptr(dlg), ptr(dhx), M, H, D, 1.0 / M, 1, st)))
+print("   2 x 88x88 FMA per row: %.2f GFMA -> at 36 TFMA/s: %.1f us" % (M * 2 * H * D / 1e9, M * 2 * H * D / 36e6))
