@@ -2,17 +2,34 @@
 // 225-228 [K2-recall (1)]: gate order i,f,c,o; hard-sigmoid gates; tanh candidate/output).
 //
 // One CTA owns R batch rows for all L timesteps.  The recurrent kernel U[H,4H] lives in REGISTERS
-// for the whole kernel (4H*2 = 704 threads x 44 floats = 30 976 = H*4H), so the per-step mat-vec
-// reads only h (broadcast LDS.128 from smem) -- no per-step weight traffic at all.  The hoisted
-// input projection is read once per step from HBM and the activated gates are written back in place
-// (the BPTT stash); BPTT overwrites them in place again with dLoss/d(pre-activation).
-//   forward : thread (n, ks)  owns gate column n, k-slice ks (44 rows of U);   reduce over 2 lanes
-//   backward: thread (k, ns)  owns h index k, n-slice ns (44 columns of U^T);  reduce over 8 lanes
+// for the whole kernel (352 threads x 88 floats = 30 976 = H*4H), so the per-step mat-vec reads
+// only h (from smem) -- no per-step weight traffic at all.  The hoisted input projection is read
+// once per step from HBM and the activated gates are written back in place (the BPTT stash); BPTT
+// overwrites them in place again with dLoss/d(pre-activation).
+//   forward : thread (j, ks)   owns the 4 gate columns of unit j, k-slice ks (22 rows of U)
+//   backward: thread (kq, ns)  owns outputs 4kq..4kq+3, n-slice ns (22 columns of U^T)
 #include "common.cuh"
+
+#ifdef CLV_PROF
+__device__ long long g_prof[16];
+#define PROF_T(i) do { if (threadIdx.x == PROF_TID && blockIdx.x == 0) { long long now_ = clock64(); g_prof[i] += now_ - tprev_; tprev_ = now_; } } while (0)
+#define PROF_INIT long long tprev_ = clock64()
+extern "C" int clv_debug_prof(long long* out, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, g_prof, sizeof(long long) * 16);
+  if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); }
+  return 0;
+}
+#ifndef PROF_TID
+#define PROF_TID 0
+#endif
+#else
+#define PROF_T(i)
+#define PROF_INIT
+#endif
 
 namespace {
 
-constexpr int RMAX = 8;  // batch rows per CTA (smem tile)
+constexpr int RMAX = 4;  // batch rows per CTA (one register pass of RC rows per step)
 
 // Optional fused input terms (the parts of the Keras LSTM input projection that are not a GEMM over
 // the piano-roll): a = xproj + bias + Wv[b,:] @ Ww (RepeatVector(W) columns, constant over t)
@@ -28,267 +45,345 @@ struct LstmExtra {
   int C, Z, has_xproj, dW_accumulate;
 };
 constexpr int ZMAX = 16;
+constexpr int ZR = 2;     // latent values per step kept / prefetched in registers (forward)
+constexpr int ZQ = 8;     // latent dimensions folded into the backward mat-vec as extra output quads
 
+// Shared memory delivers 4 bytes per lane per cycle whether or not the address is a broadcast, so
+// the per-step cost of a register-resident mat-vec is (threads x floats each thread must RECEIVE).
+// Both kernels therefore give every thread a 2-D register tile of U (4 outputs x 22 reduction
+// indices = 88 registers): four times fewer operand floats per thread than a 1 x 44 tile and half
+// the threads, and the cross-lane reduction is a reduce-scatter that leaves each lane with exactly
+// the one (row, unit) cell whose state it owns in registers.
+
+// Sum v[0..N) over the lane group {lane ^ m : m < 2N} so that the lane whose low bits are e ends
+// with the total of element e (N shuffles instead of N log N).
+template <int N>
+__device__ __forceinline__ float reduce_scatter(float (&v)[N], const int lane_bits) {
+#pragma unroll
+  for (int half = N / 2; half >= 1; half >>= 1) {
+    const bool upper = (lane_bits & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
+// forward: thread (j, ks) owns the FOUR gate columns of unit j for k-slice ks (22 rows of U); after
+// the reduce-scatter over the 4 ks lanes, lane ks holds the 4 gate sums of row r0+ks and performs
+// that cell's update in registers (cell state never leaves the thread).  h_t is double-buffered in
+// smem: one block barrier per step.
 template <int H, int RC>
-__global__ void __launch_bounds__(8 * H, 1)
+__global__ void __launch_bounds__(4 * H, 1)
 lstm_fwd_kernel(float* __restrict__ gates, const float* __restrict__ U, float* __restrict__ hout,
                 float* __restrict__ cout, const float* __restrict__ h0, const float* __restrict__ c0,
                 const int B, const int L, const int R, const LstmExtra ex) {
-  constexpr int G = 4 * H, KSZ = H / 2, NT = 8 * H;
-  static_assert(KSZ % 4 == 0, "H must be a multiple of 8");
-  __shared__ __align__(16) float h_s[RMAX][H];
-  __shared__ __align__(16) float a_s[RMAX][G];
-  __shared__ float c_s[RMAX][H];
+  constexpr int G = 4 * H, KS = 4, KSZ = H / KS, NT = 4 * H, NP = RMAX / RC;
+  static_assert(KSZ % 2 == 0, "H must be a multiple of 8");
+  static_assert(RC == 2 || RC == 4, "RC");
+  __shared__ __align__(16) float h_s[2][RMAX][H];
   __shared__ float kz_s[ZMAX][G];
-  const int tid = threadIdx.x, n = tid >> 1, ks = tid & 1;
+  const int tid = threadIdx.x, j = tid >> 2, ks = tid & 3;
   const int b0 = blockIdx.x * R;
   const int nrows = min(R, B - b0);
+  // the row (within a pass of RC rows) whose cell this lane finalises
+  const int q = (RC == 2) ? (ks & 1) : ks;
+  const bool lane_on = (RC == 4) || ks < 2;
 
-  float Ureg[KSZ];
+  float Ureg[4][KSZ];
 #pragma unroll
-  for (int i = 0; i < KSZ; ++i) Ureg[i] = __ldg(U + (size_t)(ks * KSZ + i) * G + n);
-  // per-row constant: bias + W[b,:] @ Ww   (rows this lane finalises: r = 2q + ks)
-  float cb[RMAX / 2];
+  for (int g = 0; g < 4; ++g)
 #pragma unroll
-  for (int q = 0; q < RMAX / 2; ++q) {
-    const int r = 2 * q + ks;
-    float v = ex.bias ? __ldg(ex.bias + n) : 0.f;
-    if (ex.Wv && r < nrows)
-      for (int c = 0; c < ex.C; ++c)
-        v = fmaf(__ldg(ex.Wv + (size_t)(b0 + r) * ex.C + c), __ldg(ex.Ww + (size_t)c * G + n), v);
-    cb[q] = v;
-  }
+    for (int i = 0; i < KSZ; ++i) Ureg[g][i] = __ldg(U + (size_t)(ks * KSZ + i) * G + g * H + j);
   const int Z = ex.Zs ? ex.Z : 0;
+  float kzr[4][ZR];
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+#pragma unroll
+    for (int z = 0; z < ZR; ++z) kzr[g][z] = (z < Z) ? __ldg(ex.Kz + (size_t)z * G + g * H + j) : 0.f;
   for (int i = tid; i < Z * G; i += NT) kz_s[i / G][i % G] = __ldg(ex.Kz + i);
 
+  // per-cell constants: bias + W[b,:] @ Ww, initial cell state
+  float cb[NP][4], creg[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const int r = p * RC + q;
+    const bool on = lane_on && r < nrows;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float v = ex.bias ? __ldg(ex.bias + g * H + j) : 0.f;
+      if (ex.Wv && on)
+        for (int c = 0; c < ex.C; ++c)
+          v = fmaf(__ldg(ex.Wv + (size_t)(b0 + r) * ex.C + c), __ldg(ex.Ww + (size_t)c * G + g * H + j), v);
+      cb[p][g] = v;
+    }
+    creg[p] = (on && c0) ? c0[(size_t)(b0 + r) * H + j] : 0.f;
+  }
   for (int i = tid; i < RMAX * H; i += NT) {
-    const int r = i / H, j = i - r * H;
-    const bool v = r < nrows;
-    h_s[r][j] = (v && h0) ? h0[(size_t)(b0 + r) * H + j] : 0.f;
-    c_s[r][j] = (v && c0) ? c0[(size_t)(b0 + r) * H + j] : 0.f;
+    const int r = i / H, jj = i - r * H;
+    h_s[0][r][jj] = (r < nrows && h0) ? h0[(size_t)(b0 + r) * H + jj] : 0.f;
+    h_s[1][r][jj] = 0.f;
+  }
+
+  // software pipeline: the hoisted projection and the Z row of step t+1 are loaded while step t computes
+  float xpre[NP][4], zpre[NP][ZR];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const int r = p * RC + q;
+    const bool on = lane_on && r < nrows;
+    const size_t bt = (size_t)(b0 + r) * L;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) xpre[p][g] = (ex.has_xproj && on) ? gates[bt * G + g * H + j] : 0.f;
+#pragma unroll
+    for (int z = 0; z < ZR; ++z) zpre[p][z] = (z < Z && on) ? __ldg(ex.Zs + bt * Z + z) : 0.f;
   }
   __syncthreads();
 
-  // software pipeline: the hoisted projection of step t+1 is loaded while step t computes
-  float xpre[RMAX / 2];
-#pragma unroll
-  for (int q = 0; q < RMAX / 2; ++q) {
-    const int r = 2 * q + ks;
-    xpre[q] = (ex.has_xproj && r < nrows) ? gates[((size_t)(b0 + r) * L) * G + n] : 0.f;
-  }
-
+  PROF_INIT;
+  int cur = 0;
   for (int t = 0; t < L; ++t) {
-    // ---- a = xproj_t + h_{t-1} @ U
-    float xcur[RMAX / 2];
+    PROF_T(0);
 #pragma unroll
-    for (int q = 0; q < RMAX / 2; ++q) {
-      xcur[q] = xpre[q];
-      const int r = 2 * q + ks;
-      if (ex.has_xproj && r < nrows && t + 1 < L)
-        xpre[q] = gates[((size_t)(b0 + r) * L + t + 1) * G + n];
-    }
-#pragma unroll
-    for (int rr = 0; rr < RMAX / RC; ++rr) {
-      const int r0 = rr * RC;
+    for (int p = 0; p < NP; ++p) {
+      const int r0 = p * RC;
       if (r0 >= nrows) break;
-      float xv[RC / 2];
+      const int r = r0 + q;
+      const bool on = lane_on && r < nrows;
+      const size_t bt = (size_t)(b0 + r) * L + t;
+      float xc[4], zc[ZR];
 #pragma unroll
-      for (int q = 0; q < RC / 2; ++q) {
-        const int r = r0 + 2 * q + ks;
-        float v = 0.f;
-        if (r < nrows) {
-          const size_t bt = (size_t)(b0 + r) * L + t;
-          v = cb[rr * (RC / 2) + q] + xcur[rr * (RC / 2) + q];
-          for (int j = 0; j < Z; ++j) v = fmaf(__ldg(ex.Zs + bt * Z + j), kz_s[j][n], v);
+      for (int g = 0; g < 4; ++g) xc[g] = xpre[p][g];
+#pragma unroll
+      for (int z = 0; z < ZR; ++z) zc[z] = zpre[p][z];
+      if (on && t + 1 < L) {
+        if (ex.has_xproj) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) xpre[p][g] = gates[(bt + 1) * G + g * H + j];
         }
-        xv[q] = v;
+#pragma unroll
+        for (int z = 0; z < ZR; ++z)
+          if (z < Z) zpre[p][z] = __ldg(ex.Zs + (bt + 1) * Z + z);
       }
-      float acc[RC];
+      // ---- partial h_{t-1} @ U over this lane's k-slice, 4 gates x RC rows
+      float acc[4 * RC];
 #pragma unroll
-      for (int q = 0; q < RC; ++q) acc[q] = 0.f;
+      for (int i = 0; i < 4 * RC; ++i) acc[i] = 0.f;
 #pragma unroll
-      for (int i4 = 0; i4 < KSZ / 4; ++i4) {
+      for (int i2 = 0; i2 < KSZ / 2; ++i2) {
 #pragma unroll
-        for (int q = 0; q < RC; ++q) {
-          const float4 hv = *reinterpret_cast<const float4*>(&h_s[r0 + q][ks * KSZ + 4 * i4]);
-          acc[q] = fmaf(Ureg[4 * i4 + 0], hv.x, acc[q]);
-          acc[q] = fmaf(Ureg[4 * i4 + 1], hv.y, acc[q]);
-          acc[q] = fmaf(Ureg[4 * i4 + 2], hv.z, acc[q]);
-          acc[q] = fmaf(Ureg[4 * i4 + 3], hv.w, acc[q]);
+        for (int qq = 0; qq < RC; ++qq) {
+          const float2 hv = *reinterpret_cast<const float2*>(&h_s[cur][r0 + qq][ks * KSZ + 2 * i2]);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            acc[g * RC + qq] = fmaf(Ureg[g][2 * i2], hv.x, acc[g * RC + qq]);
+            acc[g * RC + qq] = fmaf(Ureg[g][2 * i2 + 1], hv.y, acc[g * RC + qq]);
+          }
         }
       }
+      // ---- reduce over the 4 k-slices; lane ks keeps row q of every gate
+      float a[4];
 #pragma unroll
-      for (int q = 0; q < RC; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 1);
+      for (int g = 0; g < 4; ++g) {
+        float v[RC == 2 ? 2 : 4];
+        if (RC == 2) {
+          v[0] = acc[g * RC + 0] + __shfl_xor_sync(0xffffffffu, acc[g * RC + 0], 2);
+          v[1] = acc[g * RC + 1] + __shfl_xor_sync(0xffffffffu, acc[g * RC + 1], 2);
+        } else {
 #pragma unroll
-      for (int q = 0; q < RC / 2; ++q) {
-        const int r = r0 + 2 * q + ks;
-        const float mine = ks ? acc[2 * q + 1] : acc[2 * q];
-        if (r < nrows) a_s[r][n] = xv[q] + mine;
+          for (int qq = 0; qq < RC; ++qq) v[qq] = acc[g * RC + qq];
+        }
+        a[g] = reduce_scatter(v, ks);
       }
+      PROF_T(1);
+      // ---- cell update in registers
+      if (on) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float v = a[g] + cb[p][g] + xc[g];
+#pragma unroll
+          for (int z = 0; z < ZR; ++z) v = fmaf(zc[z], kzr[g][z], v);
+          for (int z = ZR; z < Z; ++z) v = fmaf(__ldg(ex.Zs + bt * Z + z), kz_s[z][g * H + j], v);
+          a[g] = v;
+        }
+        const float ig = hard_sigmoid_f(a[0]);
+        const float fg = hard_sigmoid_f(a[1]);
+        const float gg = tanhf(a[2]);
+        const float og = hard_sigmoid_f(a[3]);
+        const float c = fmaf(fg, creg[p], ig * gg);
+        const float h = og * tanhf(c);
+        creg[p] = c;
+        h_s[cur ^ 1][r][j] = h;
+        float* gp = gates + bt * G + j;
+        gp[0] = ig; gp[H] = fg; gp[2 * H] = gg; gp[3 * H] = og;
+        hout[bt * H + j] = h;
+        cout[bt * H + j] = c;
+      }
+      PROF_T(2);
     }
     __syncthreads();
-    // ---- cell update, one (row, unit) cell per thread-slot
-    for (int cell = tid; cell < nrows * H; cell += NT) {
-      const int r = cell / H, j = cell - r * H;
-      const float ig = hard_sigmoid_f(a_s[r][j]);
-      const float fg = hard_sigmoid_f(a_s[r][H + j]);
-      const float gg = tanhf(a_s[r][2 * H + j]);
-      const float og = hard_sigmoid_f(a_s[r][3 * H + j]);
-      const float c = fmaf(fg, c_s[r][j], ig * gg);
-      const float h = og * tanhf(c);
-      c_s[r][j] = c;
-      h_s[r][j] = h;
-      const size_t base = (size_t)(b0 + r) * L + t;
-      float* gp = gates + base * G + j;
-      gp[0] = ig; gp[H] = fg; gp[2 * H] = gg; gp[3 * H] = og;
-      hout[base * H + j] = h;
-      cout[base * H + j] = c;
-    }
-    __syncthreads();
+    PROF_T(3);
+    cur ^= 1;
   }
 }
 
+// backward: thread (kq, ns) owns a 4 x 22 tile of U^T: outputs k = 4kq..4kq+3 (kq < H/4) -- or rows
+// z = 4(kq-H/4).. of Kz, which turns dZ = dA @ Kz^T into four more outputs of the same mat-vec --
+// and the n-slice ns (22 of the 4H gate columns).  The reduce-scatter over the 16 ns lanes leaves
+// lane ns with dh_rec of ONE (unit, row) cell, whose dc / running sums / prefetched operands live in
+// that lane's registers.  dA_t is double-buffered in smem: one block barrier per step.
 template <int H, int RC>
-__global__ void __launch_bounds__(8 * H, 1)
+__global__ void __launch_bounds__(16 * (H / 4 + ZQ / 4), 1)
 lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const float* __restrict__ c,
                 const float* __restrict__ dh_out, float* __restrict__ dAsum, const int B,
                 const int L, const int R, const LstmExtra ex) {
-  constexpr int G = 4 * H, NS = 8, NSZ = G / NS, NT = 8 * H;
-  static_assert(NSZ % 4 == 0, "H must be a multiple of 8");
-  constexpr int SLOTS = (RMAX * H + NT - 1) / NT;
-  __shared__ __align__(16) float da_s[RMAX][G];
-  __shared__ float dhrec_s[RMAX][H];
-  __shared__ float dc_s[RMAX][H];
-  __shared__ float kz_s[ZMAX][G];
-  const int tid = threadIdx.x, k = tid >> 3, ns = tid & 7;
-  const int lane = tid & 31, wid = tid >> 5;
+  constexpr int G = 4 * H, NS = 16, NSZ = G / NS, NKU = H / 4, NP = RMAX / RC;
+  static_assert(NSZ % 2 == 0 && H % 4 == 0, "H must be a multiple of 8");
+  static_assert(RC == 2 || RC == 4, "RC");
+  __shared__ __align__(16) float da_s[2][RMAX][G];
+  const int tid = threadIdx.x, kq = tid >> 4, ns = tid & 15;
+  const int lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
   const int Z = ex.dZ ? ex.Z : 0;
-  for (int i = tid; i < Z * G; i += NT) kz_s[i / G][i % G] = __ldg(ex.Kz + i);
   const int b0 = blockIdx.x * R;
   const int nrows = min(R, B - b0);
+  const bool is_u = kq < NKU;
+  // the (output-in-quad, row-in-pass) cell this lane finalises
+  const int kk_c = (RC == 4) ? (ns >> 2) : ((ns & 7) >> 1);
+  const int q_c = (RC == 4) ? (ns & 3) : (ns & 1);
+  const bool lane_on = (RC == 4) || ns < 8;
+  const int j = 4 * kq + kk_c;                 // unit (is_u)
+  const int zo = 4 * (kq - NKU) + kk_c;        // latent index (!is_u)
 
-  float Ureg[NSZ];
-  // scalar loads: U sits at an arbitrary float offset of the flat parameter buffer (not 16B-aligned)
+  float Ureg[4][NSZ];
 #pragma unroll
-  for (int i = 0; i < NSZ; ++i) Ureg[i] = __ldg(U + (size_t)k * G + ns * NSZ + i);
-  for (int i = tid; i < RMAX * H; i += NT) {
-    dhrec_s[i / H][i % H] = 0.f;
-    dc_s[i / H][i % H] = 0.f;
+  for (int kk = 0; kk < 4; ++kk) {
+    const int zz = 4 * (kq - NKU) + kk;
+    // scalar loads: U sits at an arbitrary float offset of the flat parameter buffer
+#pragma unroll
+    for (int i = 0; i < NSZ; ++i)
+      Ureg[kk][i] = is_u ? __ldg(U + (size_t)(4 * kq + kk) * G + ns * NSZ + i)
+                         : ((zz < Z && zz < ZQ) ? __ldg(ex.Kz + (size_t)zz * G + ns * NSZ + i) : 0.f);
   }
-  for (int i = tid; i < RMAX * G; i += NT) da_s[i / G][i % G] = 0.f;
-  float asum[SLOTS][4];
-#pragma unroll
-  for (int s = 0; s < SLOTS; ++s) asum[s][0] = asum[s][1] = asum[s][2] = asum[s][3] = 0.f;
-  __syncthreads();
+  for (int i = tid; i < 2 * RMAX * G; i += blockDim.x) (&da_s[0][0][0])[i] = 0.f;
 
+  float dc[NP], dhrec[NP], asum[NP][4];
   // software pipeline: operands of the cell phase of step t-1 are loaded during step t
-  float pg[SLOTS][4], pc2[SLOTS], pdh[SLOTS], pct[SLOTS];
+  float pg[NP][4], pct[NP], pc2[NP], pdh[NP];
 #pragma unroll
-  for (int s = 0; s < SLOTS; ++s) {
-    const int cell = tid + s * NT;
-    pg[s][0] = pg[s][1] = pg[s][2] = pg[s][3] = pc2[s] = pdh[s] = pct[s] = 0.f;
-    if (cell < nrows * H) {
-      const int r = cell / H, j = cell - r * H;
+  for (int p = 0; p < NP; ++p) {
+    dc[p] = dhrec[p] = 0.f;
+    asum[p][0] = asum[p][1] = asum[p][2] = asum[p][3] = 0.f;
+    pg[p][0] = pg[p][1] = pg[p][2] = pg[p][3] = pct[p] = pc2[p] = pdh[p] = 0.f;
+    const int r = p * RC + q_c;
+    if (is_u && lane_on && r < nrows) {
       const size_t base = (size_t)(b0 + r) * L + (L - 1);
       const float* gp = gates + base * G + j;
-      pg[s][0] = gp[0]; pg[s][1] = gp[H]; pg[s][2] = gp[2 * H]; pg[s][3] = gp[3 * H];
-      pct[s] = __ldg(c + base * H + j);
-      pc2[s] = (L > 1) ? __ldg(c + (base - 1) * H + j) : 0.f;
-      pdh[s] = __ldg(dh_out + base * H + j);
+      pg[p][0] = gp[0]; pg[p][1] = gp[H]; pg[p][2] = gp[2 * H]; pg[p][3] = gp[3 * H];
+      pct[p] = __ldg(c + base * H + j);
+      pc2[p] = (L > 1) ? __ldg(c + (base - 1) * H + j) : 0.f;
+      pdh[p] = __ldg(dh_out + base * H + j);
     }
   }
+  __syncthreads();
 
+  int buf = 0;
   for (int t = L - 1; t >= 0; --t) {
-    // ---- cell phase: dLoss/d(pre-activations) for step t
+    // ---- cell phase: dLoss/d(pre-activations) for step t, one cell per lane and pass
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-      const int cell = tid + s * NT;
-      if (cell < nrows * H) {
-        const int r = cell / H, j = cell - r * H;
+    for (int p = 0; p < NP; ++p) {
+      const int r = p * RC + q_c;
+      if (p * RC >= nrows) break;
+      if (is_u && lane_on && r < nrows) {
         const size_t base = (size_t)(b0 + r) * L + t;
         float* gp = gates + base * G + j;
-        const float ig = pg[s][0], fg = pg[s][1], gg = pg[s][2], og = pg[s][3];
-        const float ct = pct[s], cprev = pc2[s];
-        const float dh = pdh[s] + dhrec_s[r][j];
+        const float ig = pg[p][0], fg = pg[p][1], gg = pg[p][2], og = pg[p][3];
+        const float ct = pct[p], cprev = pc2[p];
+        const float dh = pdh[p] + dhrec[p];
         if (t > 0) {   // issue next step's loads now; they land during the mat-vec below
           const float* gq = gp - G;
-          pg[s][0] = gq[0]; pg[s][1] = gq[H]; pg[s][2] = gq[2 * H]; pg[s][3] = gq[3 * H];
-          pct[s] = cprev;
-          pc2[s] = (t > 1) ? __ldg(c + (base - 2) * H + j) : 0.f;
-          pdh[s] = __ldg(dh_out + (base - 1) * H + j);
+          pg[p][0] = gq[0]; pg[p][1] = gq[H]; pg[p][2] = gq[2 * H]; pg[p][3] = gq[3 * H];
+          pct[p] = cprev;
+          pc2[p] = (t > 1) ? __ldg(c + (base - 2) * H + j) : 0.f;
+          pdh[p] = __ldg(dh_out + (base - 1) * H + j);
         }
         const float tc = tanhf(ct);
         const float d_o = dh * tc;
-        const float dc = fmaf(dh * og, 1.0f - tc * tc, dc_s[r][j]);
-        dc_s[r][j] = dc * fg;
+        const float dcc = fmaf(dh * og, 1.0f - tc * tc, dc[p]);
+        dc[p] = dcc * fg;
         // hard-sigmoid passes its gradient on the interior of [0,1] (the stored activation cannot
         // tell an exact boundary hit from a clipped value; see DESIGN.md "closed interval")
-        const float dai = (ig > 0.f && ig < 1.f) ? 0.2f * dc * gg : 0.f;
-        const float daf = (fg > 0.f && fg < 1.f) ? 0.2f * dc * cprev : 0.f;
-        const float dag = dc * ig * (1.0f - gg * gg);
+        const float dai = (ig > 0.f && ig < 1.f) ? 0.2f * dcc * gg : 0.f;
+        const float daf = (fg > 0.f && fg < 1.f) ? 0.2f * dcc * cprev : 0.f;
+        const float dag = dcc * ig * (1.0f - gg * gg);
         const float dao = (og > 0.f && og < 1.f) ? 0.2f * d_o : 0.f;
-        da_s[r][j] = dai; da_s[r][H + j] = daf; da_s[r][2 * H + j] = dag; da_s[r][3 * H + j] = dao;
+        float* ds = &da_s[buf][r][j];
+        ds[0] = dai; ds[H] = daf; ds[2 * H] = dag; ds[3 * H] = dao;
         gp[0] = dai; gp[H] = daf; gp[2 * H] = dag; gp[3 * H] = dao;
-        asum[s][0] += dai; asum[s][1] += daf; asum[s][2] += dag; asum[s][3] += dao;
+        asum[p][0] += dai; asum[p][1] += daf; asum[p][2] += dag; asum[p][3] += dao;
       }
     }
     if (t == 0 && Z == 0) break;
     __syncthreads();
-    // ---- dZ[b,t,:] = da @ Kz^T (rank-Z gradient to the latent; one warp per (row, j) pair)
-    for (int pz = wid; pz < nrows * Z; pz += NT / 32) {
-      const int r = pz / Z, j = pz - r * Z;
-      float p = 0.f;
-      for (int i = lane; i < G; i += 32) p = fmaf(da_s[r][i], kz_s[j][i], p);
-      p = warp_sum(p);
-      if (lane == 0) ex.dZ[((size_t)(b0 + r) * L + t) * Z + j] = p;
-    }
-    if (t == 0) break;
-    // ---- dh_rec = da @ U^T
-    for (int r0 = 0; r0 < nrows; r0 += RC) {
-      float acc[RC];
+    // ---- [dh_rec | dZ_t] = dA_t @ [U | Kz]^T
 #pragma unroll
-      for (int q = 0; q < RC; ++q) acc[q] = 0.f;
+    for (int p = 0; p < NP; ++p) {
+      const int r0 = p * RC;
+      if (r0 >= nrows) break;
+      float acc[4 * RC];
 #pragma unroll
-      for (int i4 = 0; i4 < NSZ / 4; ++i4) {
+      for (int i = 0; i < 4 * RC; ++i) acc[i] = 0.f;
 #pragma unroll
-        for (int q = 0; q < RC; ++q) {
-          const float4 dv = *reinterpret_cast<const float4*>(&da_s[r0 + q][ns * NSZ + 4 * i4]);
-          acc[q] = fmaf(Ureg[4 * i4 + 0], dv.x, acc[q]);
-          acc[q] = fmaf(Ureg[4 * i4 + 1], dv.y, acc[q]);
-          acc[q] = fmaf(Ureg[4 * i4 + 2], dv.z, acc[q]);
-          acc[q] = fmaf(Ureg[4 * i4 + 3], dv.w, acc[q]);
+      for (int i2 = 0; i2 < NSZ / 2; ++i2) {
+#pragma unroll
+        for (int qq = 0; qq < RC; ++qq) {
+          const float2 dv = *reinterpret_cast<const float2*>(&da_s[buf][r0 + qq][ns * NSZ + 2 * i2]);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            acc[kk * RC + qq] = fmaf(Ureg[kk][2 * i2], dv.x, acc[kk * RC + qq]);
+            acc[kk * RC + qq] = fmaf(Ureg[kk][2 * i2 + 1], dv.y, acc[kk * RC + qq]);
+          }
         }
       }
+      if (RC == 2) {
 #pragma unroll
-      for (int q = 0; q < RC; ++q) {
-        acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 1);
-        acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 2);
-        acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 4);
+        for (int i = 0; i < 4 * RC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
       }
-#pragma unroll
-      for (int q = 0; q < RC; ++q)
-        if (ns == q && r0 + q < nrows) dhrec_s[r0 + q][k] = acc[q];
+      const float val = reduce_scatter(acc, ns);   // element kk_c * RC + q_c
+      if (is_u) {
+        dhrec[p] = val;
+      } else if (lane_on && zo < Z && zo < ZQ && r0 + q_c < nrows) {
+        ex.dZ[((size_t)(b0 + r0 + q_c) * L + t) * Z + zo] = val;
+      }
     }
-    __syncthreads();
+    // latent dimensions beyond the folded ones: one warp per (row, z) dot product
+    for (int pz = wid; pz < nrows * (Z - ZQ); pz += nwarps) {
+      const int r = pz / (Z - ZQ), zz = ZQ + pz - r * (Z - ZQ);
+      float p = 0.f;
+      for (int i = lane; i < G; i += 32) p = fmaf(da_s[buf][r][i], __ldg(ex.Kz + (size_t)zz * G + i), p);
+      p = warp_sum(p);
+      if (lane == 0) ex.dZ[((size_t)(b0 + r) * L + t) * Z + zz] = p;
+    }
+    buf ^= 1;
   }
   __syncthreads();   // every warp is past its last read of da_s: reuse it for the per-row sums
 #pragma unroll
-  for (int s = 0; s < SLOTS; ++s) {
-    const int cell = tid + s * NT;
-    if (cell < nrows * H) {
-      const int r = cell / H, j = cell - r * H;
+  for (int p = 0; p < NP; ++p) {
+    const int r = p * RC + q_c;
+    if (is_u && lane_on && r < nrows) {
       float* ap = dAsum + (size_t)(b0 + r) * G + j;
-      ap[0] = asum[s][0]; ap[H] = asum[s][1]; ap[2 * H] = asum[s][2]; ap[3 * H] = asum[s][3];
-      da_s[r][j] = asum[s][0]; da_s[r][H + j] = asum[s][1];
-      da_s[r][2 * H + j] = asum[s][2]; da_s[r][3 * H + j] = asum[s][3];
+      ap[0] = asum[p][0]; ap[H] = asum[p][1]; ap[2 * H] = asum[p][2]; ap[3 * H] = asum[p][3];
+      float* ds = &da_s[0][r][j];
+      ds[0] = asum[p][0]; ds[H] = asum[p][1]; ds[2 * H] = asum[p][2]; ds[3 * H] = asum[p][3];
     }
   }
   if (ex.dW_ext) {   // dW[b,:] (+)= (sum_t da[b,t,:]) @ Ww^T : gradient to the simplex W
     __syncthreads();
-    for (int pc = wid; pc < nrows * ex.C; pc += NT / 32) {
+    for (int pc = wid; pc < nrows * ex.C; pc += nwarps) {
       const int r = pc / ex.C, cc = pc - r * ex.C;
       float p = 0.f;
-      for (int i = lane; i < G; i += 32) p = fmaf(da_s[r][i], __ldg(ex.Ww + (size_t)cc * G + i), p);
+      for (int i = lane; i < G; i += 32) p = fmaf(da_s[0][r][i], __ldg(ex.Ww + (size_t)cc * G + i), p);
       p = warp_sum(p);
       if (lane == 0) {
         float* o = ex.dW_ext + (size_t)(b0 + r) * ex.C + cc;
@@ -313,8 +408,8 @@ int lstm_fwd_launch(float* gates, const float* U, float* h, float* c, const floa
   if (B <= 0 || L <= 0) return CLV_OK;
   const int R = pick_rows(B);
   const int grid = (B + R - 1) / R;
-  if (R % 4 == 0) lstm_fwd_kernel<88, 4><<<grid, 8 * 88, 0, st>>>(gates, U, h, c, h0, c0, B, L, R, ex);
-  else lstm_fwd_kernel<88, 2><<<grid, 8 * 88, 0, st>>>(gates, U, h, c, h0, c0, B, L, R, ex);
+  if (R > 2) lstm_fwd_kernel<88, 4><<<grid, 4 * 88, 0, st>>>(gates, U, h, c, h0, c0, B, L, R, ex);
+  else lstm_fwd_kernel<88, 2><<<grid, 4 * 88, 0, st>>>(gates, U, h, c, h0, c0, B, L, R, ex);
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }
@@ -326,8 +421,11 @@ int lstm_bwd_launch(float* gates, const float* U, const float* c, const float* d
   if (B <= 0 || L <= 0) return CLV_OK;
   const int R = pick_rows(B);
   const int grid = (B + R - 1) / R;
-  if (R % 4 == 0) lstm_bwd_kernel<88, 4><<<grid, 8 * 88, 0, st>>>(gates, U, c, dh_out, dAsum, B, L, R, ex);
-  else lstm_bwd_kernel<88, 2><<<grid, 8 * 88, 0, st>>>(gates, U, c, dh_out, dAsum, B, L, R, ex);
+  // 22 unit quads + one quad of 16 lanes per 4 latent dimensions, rounded up to whole warps
+  const int zq = ex.dZ ? (ex.Z < ZQ ? ex.Z : ZQ) : 0;
+  const int nthreads = ((16 * (88 / 4 + (zq + 3) / 4)) + 31) & ~31;
+  if (R > 2) lstm_bwd_kernel<88, 4><<<grid, nthreads, 0, st>>>(gates, U, c, dh_out, dAsum, B, L, R, ex);
+  else lstm_bwd_kernel<88, 2><<<grid, nthreads, 0, st>>>(gates, U, c, dh_out, dAsum, B, L, R, ex);
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }
