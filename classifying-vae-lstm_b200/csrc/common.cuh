@@ -22,6 +22,29 @@ extern unsigned long long g_clv_launches;
     if ((call) != cudaSuccess) return CLV_E_CUDA;           \
   } while (0)
 
+// ---- programmatic dependent launch (PDL).  Kernels on the step's critical path begin with a
+// parameter-only prologue (weights -> registers / smem), then pdl_wait() for the stream predecessor
+// to complete and flush, then pdl_launch_dependents() so the successor's prologue overlaps this
+// kernel's body.  pdl_wait() is a no-op for a kernel launched without the attribute.  The step
+// scheduler sets g_clv_pdl around launches whose stream predecessor is one of our kernels.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+extern thread_local int g_clv_pdl;
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t clv_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = g_clv_pdl ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 static inline int clv_num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -120,6 +120,8 @@ __global__ void __launch_bounds__(256) gauss_heads_fwd_kernel(
     Ks[j * H + k] = __ldg(Km + i);
     Ks[(Z + j) * H + k] = __ldg(Kv + i);
   }
+  pdl_wait();                 // everything above reads parameters only
+  pdl_launch_dependents();
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float kl_local = 0.f;
@@ -176,6 +178,8 @@ __global__ void __launch_bounds__(256) gauss_heads_bwd_kernel(
     Ks[j * H + k] = __ldg(Km + i);
     Ks[(Z + j) * H + k] = __ldg(Kv + i);
   }
+  pdl_wait();                 // everything above reads parameters only
+  pdl_launch_dependents();
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float accm[KMAX][ZM], accv[KMAX][ZM], accb[2 * ZM];
@@ -349,8 +353,8 @@ extern "C" int clv_gauss_heads_fwd(const float* h, const float* Km, const float*
   if (gen_noise && !ctr) return CLV_E_INVALID;
   if (R <= 0) return CLV_OK;
   const size_t smem = sizeof(float) * 2 * Z * H;
-  gauss_heads_fwd_kernel<<<rows_grid(R, 8), 256, smem, (cudaStream_t)stream>>>(
-      h, Km, bm, Kv, bv, eps, Zargs, Zs, loss_acc, R, H, Z, scale, gen_noise, seed, ctr);
+  CLV_CUDA(clv_launch(gauss_heads_fwd_kernel, rows_grid(R, 8), 256, smem, (cudaStream_t)stream,
+                      h, Km, bm, Kv, bv, eps, Zargs, Zs, loss_acc, R, H, Z, scale, gen_noise, seed, ctr));
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }
@@ -365,15 +369,15 @@ extern "C" int clv_gauss_heads_bwd(const float* h, const float* Km, const float*
   if (H < 1 || H > 32 * KMAX || Z < 1 || Z > 16) return CLV_E_UNSUPPORTED;
   if (R <= 0) return CLV_OK;
   const size_t smem = sizeof(float) * (2 * Z * H + 2 * Z);
-  // few, fat blocks: every warp ends with H*2Z atomics, so give each warp >= 16 rows
-  int64_t blocks = (R + 8 * 16 - 1) / (8 * 16);
+  // each warp walks its rows serially (a global-load latency chain per row) and every block ends
+  // with H*2Z global atomics: 4 rows per warp balances the two at small R, the cap at large R
+  int64_t blocks = (R + 8 * 4 - 1) / (8 * 4);
   const int64_t cap = 2LL * clv_num_sms();
   if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
-#define CLV_LAUNCH_GH(ZM)                                                                       \
-  gauss_heads_bwd_kernel<ZM><<<(int)blocks, 256, smem, st>>>(h, Km, Kv, eps, Zargs, dZ, dh, dKm, \
-                                                             dbm, dKv, dbv, R, H, Z, klw_scale,  \
-                                                             relu_input)
+#define CLV_LAUNCH_GH(ZM)                                                                        \
+  CLV_CUDA(clv_launch(gauss_heads_bwd_kernel<ZM>, (int)blocks, 256, smem, st, h, Km, Kv, eps, Zargs, \
+                      dZ, dh, dKm, dbm, dKv, dbv, R, H, Z, klw_scale, relu_input))
   if (Z <= 2) CLV_LAUNCH_GH(2);
   else if (Z <= 4) CLV_LAUNCH_GH(4);
   else if (Z <= 8) CLV_LAUNCH_GH(8);

@@ -45,6 +45,8 @@ xhead_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const fl
   }
   const float b = __ldg(bx + j);
   float lsum = 0.f;
+  pdl_wait();                 // everything above reads parameters only
+  pdl_launch_dependents();
   // persistent over 32-row tiles: the head kernel (and its transpose) is staged once per CTA
   for (int64_t row0 = (int64_t)blockIdx.x * XR; row0 < R; row0 += (int64_t)gridDim.x * XR) {
     __syncthreads();   // previous tile fully consumed (and K_s visible on the first pass)
@@ -183,6 +185,10 @@ keyenc_fwd_kernel(const uint8_t* __restrict__ roll, const int32_t* __restrict__ 
     Wargs[(size_t)b * NW + tid] = a;
   }
   __syncthreads();
+  // everything above depends on the batch and the parameters only; the Philox counter and the loss
+  // accumulators below are reset by the step's first kernel
+  pdl_wait();
+  pdl_launch_dependents();
   // ---- logistic-normal sample + losses (same maths as logitnormal_fwd_kernel), lanes 0..15
   if (tid < 32) {
     const int j = tid & 15;
@@ -300,6 +306,8 @@ keyenc_bwd_full_kernel(const uint8_t* __restrict__ roll, const int32_t* __restri
   const uint32_t* src = reinterpret_cast<const uint32_t*>(roll + ((size_t)__ldg(off + b) + shift) * D);
   for (int i = tid; i < nwords; i += KT) win_s[i] = __ldg(src + i);
   if (tid < D) hw_s[tid] = __ldg(hW + (size_t)b * D + tid);
+  pdl_wait();                 // above: the batch and forward activations only (complete long ago)
+  pdl_launch_dependents();
   // ---- K2 backward on lanes 0..15 of warp 0 (same maths as logitnormal_bwd_kernel)
   if (tid < 32) {
     const int j = tid & 15;
@@ -396,12 +404,12 @@ extern "C" int clv_xhead_fwd_bwd(const float* h, const float* Kx, const float* b
   }
   int64_t xgrid = (R + XR - 1) / XR;
   if (xgrid <= clv_num_sms()) {
-    xhead_kernel<1><<<(unsigned)xgrid, XT, smem, (cudaStream_t)stream>>>(
-        h, Kx, bx, roll, x_off, x_grp, x_shift, loss_acc, dlogits, dh, R, scale, do_backward);
+    CLV_CUDA(clv_launch(xhead_kernel<1>, (unsigned)xgrid, XT, smem, (cudaStream_t)stream,
+                        h, Kx, bx, roll, x_off, x_grp, x_shift, loss_acc, dlogits, dh, R, scale, do_backward));
   } else {
     if (xgrid > 3LL * clv_num_sms()) xgrid = 3LL * clv_num_sms();   // 3 CTAs (73 KB smem each) per SM
-    xhead_kernel<3><<<(unsigned)xgrid, XT, smem, (cudaStream_t)stream>>>(
-        h, Kx, bx, roll, x_off, x_grp, x_shift, loss_acc, dlogits, dh, R, scale, do_backward);
+    CLV_CUDA(clv_launch(xhead_kernel<3>, (unsigned)xgrid, XT, smem, (cudaStream_t)stream,
+                        h, Kx, bx, roll, x_off, x_grp, x_shift, loss_acc, dlogits, dh, R, scale, do_backward));
   }
   CLV_CHECK_LAUNCH();
   return CLV_OK;
@@ -429,9 +437,9 @@ extern "C" int clv_keyenc_fwd(const uint8_t* roll, const int32_t* win_off, int32
                                   (int)cudaSharedmemCarveoutMaxShared));
     attr_smem = smem;
   }
-  keyenc_fwd_kernel<<<B, KT, smem, (cudaStream_t)stream>>>(
-      roll, win_off, shift, L, D, Khw, bhw, Kwa, bwa, eps_w, labels, hW, Wargs, W, loss_acc, C,
-      w_log_var_prior, scale_b, gen_noise, seed, ctr);
+  CLV_CUDA(clv_launch(keyenc_fwd_kernel, B, KT, smem, (cudaStream_t)stream,
+                      roll, win_off, shift, L, D, Khw, bhw, Kwa, bwa, eps_w, labels, hW, Wargs, W, loss_acc, C,
+                      w_log_var_prior, scale_b, gen_noise, seed, ctr));
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }
@@ -472,9 +480,9 @@ extern "C" int clv_keyenc_bwd_full(const uint8_t* roll, const int32_t* win_off, 
                                   (int)cudaSharedmemCarveoutMaxShared));
     attr_smem = smem;
   }
-  keyenc_bwd_full_kernel<<<B, KT, smem, (cudaStream_t)stream>>>(
-      roll, win_off, shift, L, D, Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, gKhw, gbhw, gKwa,
-      gbwa, C, w_log_var_prior, cw_over_B, wkl_over_B);
+  CLV_CUDA(clv_launch(keyenc_bwd_full_kernel, B, KT, smem, (cudaStream_t)stream,
+                      roll, win_off, shift, L, D, Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, gKhw,
+                      gbhw, gKwa, gbwa, C, w_log_var_prior, cw_over_B, wkl_over_B));
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }

@@ -105,6 +105,8 @@ lstm_fwd_kernel(float* __restrict__ gates, const float* __restrict__ U, float* _
 #pragma unroll
     for (int z = 0; z < ZR; ++z) kzr[g][z] = (z < Z) ? __ldg(ex.Kz + (size_t)z * G + g * H + j) : 0.f;
   for (int i = tid; i < Z * G; i += NT) kz_s[i / G][i % G] = __ldg(ex.Kz + i);
+  pdl_wait();                 // everything above reads parameters only
+  pdl_launch_dependents();
 
   // per-cell constants: bias + W[b,:] @ Ww, initial cell state
   float cb[NP][4], creg[NP];
@@ -266,6 +268,8 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
       Ureg[kk][i] = is_u ? __ldg(U + (size_t)(4 * kq + kk) * G + ns * NSZ + i)
                          : ((zz < Z && zz < ZQ) ? __ldg(ex.Kz + (size_t)zz * G + ns * NSZ + i) : 0.f);
   }
+  pdl_wait();                 // everything above reads parameters only
+  pdl_launch_dependents();
   for (int i = tid; i < 2 * RMAX * G; i += blockDim.x) (&da_s[0][0][0])[i] = 0.f;
 
   float dc[NP], dhrec[NP], asum[NP][4];
@@ -408,8 +412,8 @@ int lstm_fwd_launch(float* gates, const float* U, float* h, float* c, const floa
   if (B <= 0 || L <= 0) return CLV_OK;
   const int R = pick_rows(B);
   const int grid = (B + R - 1) / R;
-  if (R > 2) lstm_fwd_kernel<88, 4><<<grid, 4 * 88, 0, st>>>(gates, U, h, c, h0, c0, B, L, R, ex);
-  else lstm_fwd_kernel<88, 2><<<grid, 4 * 88, 0, st>>>(gates, U, h, c, h0, c0, B, L, R, ex);
+  if (R > 2) CLV_CUDA(clv_launch(lstm_fwd_kernel<88, 4>, grid, 4 * 88, 0, st, gates, U, h, c, h0, c0, B, L, R, ex));
+  else CLV_CUDA(clv_launch(lstm_fwd_kernel<88, 2>, grid, 4 * 88, 0, st, gates, U, h, c, h0, c0, B, L, R, ex));
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }
@@ -424,8 +428,8 @@ int lstm_bwd_launch(float* gates, const float* U, const float* c, const float* d
   // 22 unit quads + one quad of 16 lanes per 4 latent dimensions, rounded up to whole warps
   const int zq = ex.dZ ? (ex.Z < ZQ ? ex.Z : ZQ) : 0;
   const int nthreads = ((16 * (88 / 4 + (zq + 3) / 4)) + 31) & ~31;
-  if (R > 2) lstm_bwd_kernel<88, 4><<<grid, nthreads, 0, st>>>(gates, U, c, dh_out, dAsum, B, L, R, ex);
-  else lstm_bwd_kernel<88, 2><<<grid, nthreads, 0, st>>>(gates, U, c, dh_out, dAsum, B, L, R, ex);
+  if (R > 2) CLV_CUDA(clv_launch(lstm_bwd_kernel<88, 4>, grid, nthreads, 0, st, gates, U, c, dh_out, dAsum, B, L, R, ex));
+  else CLV_CUDA(clv_launch(lstm_bwd_kernel<88, 2>, grid, nthreads, 0, st, gates, U, c, dh_out, dAsum, B, L, R, ex));
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }

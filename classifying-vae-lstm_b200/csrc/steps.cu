@@ -4,6 +4,7 @@
 // Host code only: no allocation, no synchronisation, everything stream-ordered (graph-capturable).
 #include <string.h>
 #include "common.cuh"
+#include <cstdlib>
 
 extern "C" int clv_lstm_fwd_fused(float*, int32_t, const float*, const float*, const float*, const float*,
                                   int32_t, const float*, const float*, int32_t, float*, float*, int32_t,
@@ -155,6 +156,14 @@ int tn_u8(const uint8_t* roll, const int32_t* off, int grp, int shift, int64_t l
 }
 
 #define TRY(x) do { int rc__ = (x); if (rc__ != CLV_OK) return rc__; } while (0)
+// launch whose stream predecessor is one of our kernels: allow programmatic dependent launch
+// (the kernel's parameter-only prologue overlaps the predecessor; see common.cuh)
+#define TRY_PDL(x) do { g_clv_pdl = pdl_enabled(); int rc__ = (x); g_clv_pdl = 0; if (rc__ != CLV_OK) return rc__; } while (0)
+static int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CLV_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v;
+}
 
 // Auxiliary stream for the weight-gradient branch (off the critical path of the step).  Created by
 // clv_runtime_init() OUTSIDE any stream capture; forked from / joined back into the caller's stream
@@ -237,9 +246,9 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
               *Kzv = P + po[R_ZV_K], *bzv = P + po[R_ZV_B], *Kd = P + po[R_DEC_K],
               *Ud = P + po[R_DEC_U], *bd = P + po[R_DEC_B], *Kx = P + po[R_X_K], *bx = P + po[R_X_B];
 
-  TRY(clv_step_begin(loss, ctr, !c->accumulate, c->gen_noise, st));
   if (c->do_backward && !c->accumulate)
     CLV_CUDA(cudaMemsetAsync(Gr, 0, sizeof(float) * (po[R_X_B] + pc[R_X_B]), st));
+  TRY(clv_step_begin(loss, ctr, !c->accumulate, c->gen_noise, st));   // last: the key encoder chains on it
 
   Fork fk(st, c->overlap_wgrad != 0);
   const bool fused_ke = (int64_t)L * D <= 65535 && (D % 4) == 0;
@@ -247,14 +256,24 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   const float* Kd_z = Kd + (int64_t)xo * G;           //                               ... Z
   const float* Kd_w = Kd + (int64_t)(xo + Z) * G;
 
-  // ---- decoder input projection of the history roll: depends on nothing but the batch -> side
-  if (c->use_x_prev && !tcl) {
+  // ---- both roll projections depend on nothing but the batch -> side streams, concurrent with the
+  //      key encoder (the encoder LSTM joins them)
+  const bool enc_proj_side = !tcl && c->overlap_wgrad != 0;
+  if (!tcl && (c->use_x_prev || enc_proj_side)) {
     TRY(fk.fork());
-    if (tc) TRY(clv_inproj_tc(roll, off, L, 0, D, Kd, G, G, wimg_d, gates_d, G, BL, nullptr, 0, 0, fk.next()));
-    else TRY(nn_u8(roll, off, L, 0, D, Kd, G, gates_d, G, BL, G, D, nullptr, nullptr, 0, 0, 0, 0, fk.next()));
+    if (enc_proj_side) {
+      if (tc) TRY(clv_inproj_tc(roll, off, L, sx, D, Ke, G, G, wimg_e, gates_e, G, BL, nullptr, 0, 0, fk.next()));
+      else TRY(nn_u8(roll, off, L, sx, D, Ke, G, gates_e, G, BL, G, D, nullptr, nullptr, 0, 0, 0, 0, fk.next()));
+    }
+    if (c->use_x_prev) {
+      if (tc) TRY(clv_inproj_tc(roll, off, L, 0, D, Kd, G, G, wimg_d, gates_d, G, BL, nullptr, 0, 0, fk.next()));
+      else TRY(nn_u8(roll, off, L, 0, D, Kd, G, gates_d, G, BL, G, D, nullptr, nullptr, 0, 0, 0, 0, fk.next()));
+    }
   }
   // ---- key encoder: hW, Wargs, logistic-normal W + its losses (model.py:174-191,244-255,264)
   if (fused_ke) {
+    // (measured: letting the key encoder start under step_begin costs 2 us -- its CTAs crowd out the
+    //  two projection kernels on the side streams -- so this launch stays fully serialised)
     TRY(clv_keyenc_fwd(roll, off, sx, L, D, Khw, bhw, Kwa, bwa, eps_w, labels, hW, Wargs, W, loss, B, C,
                        c->w_log_var_prior, sb, c->gen_noise, c->seed, ctr, st));
   } else {
@@ -285,21 +304,26 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
     TRY(clv_inproj_tc(roll, off, L, 0, D, Kd, G, G, wimg_d, gates_d, G, BL, rb_d, G, L, fk.next()));
     TRY(clv_lstm_fwd_tc(gates_e, Ue, nullptr, nullptr, 0, h_e, c_e, uimg_e, B, L, H, st));
   } else {
-    if (tc) TRY(clv_inproj_tc(roll, off, L, sx, D, Ke, G, G, wimg_e, gates_e, G, BL, nullptr, 0, 0, st));
-    else TRY(nn_u8(roll, off, L, sx, D, Ke, G, gates_e, G, BL, G, D, nullptr, nullptr, 0, 0, 0, 0, st));
+    if (!enc_proj_side) {
+      if (tc) TRY(clv_inproj_tc(roll, off, L, sx, D, Ke, G, G, wimg_e, gates_e, G, BL, nullptr, 0, 0, st));
+      else TRY(nn_u8(roll, off, L, sx, D, Ke, G, gates_e, G, BL, G, D, nullptr, nullptr, 0, 0, 0, 0, st));
+    } else {
+      TRY(fk.join());   // both roll projections (issued before the key encoder) are done
+    }
     TRY(clv_lstm_fwd_fused(gates_e, 1, Ue, be, W, Ke_w, C, nullptr, nullptr, 0, h_e, c_e, B, L, H, st));
   }
   // ---- Z heads + sample + kl (model.py:200-216,236-239)
-  TRY(clv_gauss_heads_fwd(h_e, Kzm, bzm, Kzv, bzv, eps_z, Zargs, Zs, loss, BL, H, Z, sbl,
-                          c->gen_noise, c->seed, ctr, st));
+  TRY_PDL(clv_gauss_heads_fwd(h_e, Kzm, bzm, Kzv, bzv, eps_z, Zargs, Zs, loss, BL, H, Z, sbl,
+                              c->gen_noise, c->seed, ctr, st));
   // ---- decoder LSTM (model.py:218-228) on [Xp | Z | W]: Z enters as a rank-Z term per step
-  if (c->use_x_prev) TRY(fk.join());
+  if (c->use_x_prev && (tcl || !enc_proj_side)) TRY(fk.join());
   if (tcl) TRY(clv_lstm_fwd_tc(gates_d, Ud, Zs, Kd_z, Z, h_d, c_d, uimg_d, B, L, H, st));
-  else TRY(clv_lstm_fwd_fused(gates_d, c->use_x_prev, Ud, bd, W, Kd_w, C, Zs, Kd_z, Z, h_d, c_d, B, L, H, st));
+  else if (c->use_x_prev && !enc_proj_side) TRY(clv_lstm_fwd_fused(gates_d, c->use_x_prev, Ud, bd, W, Kd_w, C, Zs, Kd_z, Z, h_d, c_d, B, L, H, st));
+  else TRY_PDL(clv_lstm_fwd_fused(gates_d, c->use_x_prev, Ud, bd, W, Kd_w, C, Zs, Kd_z, Z, h_d, c_d, B, L, H, st));
   // ---- X head + Bernoulli loss + dlogits + dgrad to h_d in one pass (model.py:229-234,241-242)
   if (H == 88 && D == 88) {
-    TRY(clv_xhead_fwd_bwd(h_d, Kx, bx, roll, off, L, sx, loss, logits, dh, BL, H, D, sbl,
-                          c->do_backward, st));
+    TRY_PDL(clv_xhead_fwd_bwd(h_d, Kx, bx, roll, off, L, sx, loss, logits, dh, BL, H, D, sbl,
+                              c->do_backward, st));
   } else {
     TRY(nn_f32(h_d, H, Kx, D, logits, D, BL, D, H, bx, 0, 0, st));
     TRY(clv_bernoulli_ce_fwd_bwd(logits, roll, off, L, sx, loss, BL, D, sbl, c->do_backward, st));
@@ -317,7 +341,8 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   TRY(fk.fork());
   TRY(tn_f32(h_d, H, logits, D, gKx, D, H, D, BL, 0, 0, fk.next()));
   TRY(clv_colsum(logits, D, BL, D, gbx, 1, fk.next()));
-  TRY(clv_lstm_bwd_fused(gates_d, Ud, c_d, dh, dAsum_d, Kd_w, C, dW_ext, 0, Kd_z, Z, dZ, B, L, H, st));
+  if (H == 88 && D == 88) TRY_PDL(clv_lstm_bwd_fused(gates_d, Ud, c_d, dh, dAsum_d, Kd_w, C, dW_ext, 0, Kd_z, Z, dZ, B, L, H, st));
+  else TRY(clv_lstm_bwd_fused(gates_d, Ud, c_d, dh, dAsum_d, Kd_w, C, dW_ext, 0, Kd_z, Z, dZ, B, L, H, st));
   TRY(fk.fork());
   const bool tcw = tc && H == 88 && Z <= 8;   // tcgen05 weight gradients
   if (tcw) {
@@ -331,9 +356,9 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   TRY(tn_f32(W, C, dAsum_d, G, gKd + (int64_t)(xo + Z) * G, G, C, G, B, 0, 0, fk.next()));
   TRY(clv_colsum(dAsum_d, G, B, G, gbd, 1, fk.next()));
   // K2b bwd overwrites dh: its only reader (decoder BPTT) is ordered before it on st
-  TRY(clv_gauss_heads_bwd(h_e, Kzm, Kzv, eps_z, Zargs, dZ, dh, gKzm, gbzm, gKzv, gbzv, BL, H, Z,
-                          c->kl_weight * sbl, 0, st));
-  TRY(clv_lstm_bwd_fused(gates_e, Ue, c_e, dh, dAsum_e, Ke_w, C, dW_ext, 1, nullptr, 0, nullptr, B, L, H, st));
+  TRY_PDL(clv_gauss_heads_bwd(h_e, Kzm, Kzv, eps_z, Zargs, dZ, dh, gKzm, gbzm, gKzv, gbzv, BL, H, Z,
+                              c->kl_weight * sbl, 0, st));
+  TRY_PDL(clv_lstm_bwd_fused(gates_e, Ue, c_e, dh, dAsum_e, Ke_w, C, dW_ext, 1, nullptr, 0, nullptr, B, L, H, st));
   TRY(fk.fork());
   if (tcw) {
     TRY(clv_lstm_wgrad_tc(gates_e, roll, off, L, sx, D, h_e, nullptr, 0, gKe, gUe, nullptr, BL, H, fk.next()));
@@ -345,9 +370,9 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   TRY(clv_colsum(dAsum_e, G, B, G, gbe, 1, fk.next()));
   if (fused_ke) {
     // K2 backward + every key-encoder weight gradient in one kernel (sparse scatter for dK_hW)
-    TRY(clv_keyenc_bwd_full(roll, off, sx, L, D, Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, gKhw,
-                            gbhw, gKwa, gbwa, B, C, c->w_log_var_prior, c->class_weight * sb,
-                            c->w_kl_weight * sb, st));
+    TRY_PDL(clv_keyenc_bwd_full(roll, off, sx, L, D, Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, gKhw,
+                                gbhw, gKwa, gbwa, B, C, c->w_log_var_prior, c->class_weight * sb,
+                                c->w_kl_weight * sb, st));
   } else {
     TRY(clv_keyenc_bwd(Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, B, C, D,
                        c->w_log_var_prior, c->class_weight * sb, c->w_kl_weight * sb, st));
@@ -444,6 +469,7 @@ int vae_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uin
 }  // namespace
 
 unsigned long long g_clv_launches = 0;
+thread_local int g_clv_pdl = 0;
 extern "C" int clv_version(void) { return 100; }
 extern "C" int64_t clv_launch_count(void) { return (int64_t)g_clv_launches; }
 
