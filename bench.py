@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sampler", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-fused-opt", action="store_true", help="step then Adam-WN as two calls (N=1)")
     ap.add_argument("--p2p", type=int, default=-1, help="1/0: force the fused peer-memory all-reduce+Adam path on/off")
     ap.add_argument("--batch", type=int, default=CFG["B"], help="per-GPU batch (sweep points)")
     ap.add_argument("--seq-len", type=int, default=CFG["L"])
@@ -214,6 +215,8 @@ def main():
 
     # ---------------- model through the public API (mirrors cl_vrnn/train.py:45-46)
     extra = {} if args.p2p < 0 else {"p2p_allreduce": bool(args.p2p)}
+    if args.no_fused_opt:
+        extra["fused_optimizer"] = False
     model, _ = get_model(B, D, H, Z, L, Cc, True, "adam-wn", world_size=world, rank=rank,
                          use_graph=not args.no_graph, seed=1234, **extra)
     e = model.engine

@@ -45,7 +45,9 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
                                                      float* __restrict__ state, const double lr,
                                                      const double b1d, const double b2d,
                                                      const float eps, const float gscale,
-                                                     const int weightnorm, const PeerSet ps) {
+                                                     const int weightnorm, const PeerSet ps,
+                                                     const int block_base, const int advance) {
+  pdl_wait();   // no-op unless launched as a programmatic dependent
   if (P2P && blockIdx.x == 0 && threadIdx.x < 8) {
     float v = 0.f;
     for (int p = 0; p < ps.n; ++p) v += ps.peers[p][pl.P + threadIdx.x];
@@ -65,11 +67,13 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
   const float lr_t = (float)(lr * sqrt(1.0 - pow(b2d, (double)t)) / (1.0 - pow(b1d, (double)t)));
   const float b1 = (float)b1d, b2 = (float)b2d;
 
+  // block_base: first plan block of this launch (a launch may cover a sub-range of the tensors)
+  const int gb = (int)blockIdx.x + block_base;
   int ti = 0;
 #pragma unroll
   for (int i = 1; i < CLV_N_TENSORS; ++i)
-    if ((int)blockIdx.x >= pl.first_block[i]) ti = i;
-  const int lb = blockIdx.x - pl.first_block[ti];
+    if (gb >= pl.first_block[i]) ti = i;
+  const int lb = gb - pl.first_block[ti];
   const int64_t off = pl.off[ti];
   const int rows = pl.rows[ti], cols = pl.cols[ti];
   const int tid = threadIdx.x;
@@ -184,7 +188,8 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
         }
       }
   }
-  // last block to finish advances `iterations`
+  // last block to finish advances `iterations` (only the final launch of a step is told to)
+  if (!advance) return;
   __threadfence();
   __syncthreads();
   if (tid == 0) {
@@ -242,18 +247,30 @@ extern "C" int clv_adamwn_init(const clv_cfg* cfg, float* state, void* stream) {
   return CLV_OK;
 }
 
-extern "C" int clv_adamwn_step(const clv_cfg* cfg, float* params, const float* grads, float* state,
-                               double lr, double beta_1, double beta_2, double epsilon,
-                               double grad_scale, int32_t weightnorm, void* stream) {
+extern "C" int clv_adamwn_step_range(const clv_cfg* cfg, float* params, const float* grads, float* state,
+                                     double lr, double beta_1, double beta_2, double epsilon,
+                                     double grad_scale, int32_t weightnorm, int32_t t_first,
+                                     int32_t t_last, int32_t advance, void* stream) {
   if (!cfg || !params || !grads || !state) return CLV_E_INVALID;
+  if (t_first < 0 || t_last > CLV_N_TENSORS || t_first >= t_last) return CLV_E_INVALID;
   AdamPlan pl;
   int rc = make_plan(cfg, &pl, weightnorm);
   if (rc != CLV_OK) return rc;
   PeerSet ps = {nullptr, 0, nullptr, nullptr};
-  adamwn_kernel<false><<<pl.first_block[CLV_N_TENSORS], NTH, 0, (cudaStream_t)stream>>>(
-      pl, params, grads, state, lr, beta_1, beta_2, (float)epsilon, (float)grad_scale, weightnorm, ps);
+  const int nb = pl.first_block[t_last] - pl.first_block[t_first];
+  if (nb <= 0) return CLV_OK;
+  CLV_CUDA(clv_launch(adamwn_kernel<false>, nb, NTH, 0, (cudaStream_t)stream, pl, params, grads, state, lr,
+                      beta_1, beta_2, (float)epsilon, (float)grad_scale, (int)weightnorm, ps,
+                      pl.first_block[t_first], (int)advance));
   CLV_CHECK_LAUNCH();
   return CLV_OK;
+}
+
+extern "C" int clv_adamwn_step(const clv_cfg* cfg, float* params, const float* grads, float* state,
+                               double lr, double beta_1, double beta_2, double epsilon,
+                               double grad_scale, int32_t weightnorm, void* stream) {
+  return clv_adamwn_step_range(cfg, params, grads, state, lr, beta_1, beta_2, epsilon, grad_scale,
+                               weightnorm, 0, CLV_N_TENSORS, 1, stream);
 }
 
 extern "C" int clv_adamwn_step_p2p(const clv_cfg* cfg, float* params, const float* const* peer_grads,
@@ -267,7 +284,7 @@ extern "C" int clv_adamwn_step_p2p(const clv_cfg* cfg, float* params, const floa
   if (rc != CLV_OK) return rc;
   PeerSet ps = {peer_grads, n_peers, gsum, loss_out};
   adamwn_kernel<true><<<pl.first_block[CLV_N_TENSORS], NTH, 0, (cudaStream_t)stream>>>(
-      pl, params, nullptr, state, lr, beta_1, beta_2, (float)epsilon, 1.0f, weightnorm, ps);
+      pl, params, nullptr, state, lr, beta_1, beta_2, (float)epsilon, 1.0f, weightnorm, ps, 0, 1);
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }

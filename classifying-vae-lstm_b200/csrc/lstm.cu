@@ -258,15 +258,23 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
   const int j = 4 * kq + kk_c;                 // unit (is_u)
   const int zo = 4 * (kq - NKU) + kk_c;        // latent index (!is_u)
 
+  // n-slice ns = the column PAIRS {2(16 i2 + ns), +1 : i2 < 11}: for a fixed register the 16 lanes of a
+  // quad read 128 contiguous bytes of a U row (4 sectors per row instead of one sector per lane --
+  // the contiguous-slice mapping made this prologue cost ~8 steps), and the matching dA reads are
+  // conflict-free LDS.64.  U and Kz are 8-byte aligned (every tensor before them has an even size).
   float Ureg[4][NSZ];
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
     const int zz = 4 * (kq - NKU) + kk;
-    // scalar loads: U sits at an arbitrary float offset of the flat parameter buffer
+    const float* rowp = is_u ? U + (size_t)(4 * kq + kk) * G
+                             : ((zz < Z && zz < ZQ) ? ex.Kz + (size_t)zz * G : nullptr);
 #pragma unroll
-    for (int i = 0; i < NSZ; ++i)
-      Ureg[kk][i] = is_u ? __ldg(U + (size_t)(4 * kq + kk) * G + ns * NSZ + i)
-                         : ((zz < Z && zz < ZQ) ? __ldg(ex.Kz + (size_t)zz * G + ns * NSZ + i) : 0.f);
+    for (int i2 = 0; i2 < NSZ / 2; ++i2) {
+      float2 u = make_float2(0.f, 0.f);
+      if (rowp) u = __ldg(reinterpret_cast<const float2*>(rowp + (i2 * NS + ns) * 2));
+      Ureg[kk][2 * i2] = u.x;
+      Ureg[kk][2 * i2 + 1] = u.y;
+    }
   }
   pdl_wait();                 // everything above reads parameters only
   pdl_launch_dependents();
@@ -342,7 +350,7 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
       for (int i2 = 0; i2 < NSZ / 2; ++i2) {
 #pragma unroll
         for (int qq = 0; qq < RC; ++qq) {
-          const float2 dv = *reinterpret_cast<const float2*>(&da_s[buf][r0 + qq][ns * NSZ + 2 * i2]);
+          const float2 dv = *reinterpret_cast<const float2*>(&da_s[buf][r0 + qq][(i2 * NS + ns) * 2]);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             acc[kk * RC + qq] = fmaf(Ureg[kk][2 * i2], dv.x, acc[kk * RC + qq]);
@@ -422,6 +430,8 @@ int lstm_bwd_launch(float* gates, const float* U, const float* c, const float* d
                     int B, int L, int H, const LstmExtra& ex, cudaStream_t st) {
   if (!gates || !U || !c || !dh_out || !dAsum) return CLV_E_INVALID;
   if (H != 88 || ex.Z > ZMAX) return CLV_E_UNSUPPORTED;
+  // float2 parameter loads (true for clv_param_layout offsets: every tensor before U / Kz has even size)
+  if (((uintptr_t)U & 7) || (ex.dZ && ((uintptr_t)ex.Kz & 7))) return CLV_E_UNSUPPORTED;
   if (B <= 0 || L <= 0) return CLV_OK;
   const int R = pick_rows(B);
   const int grid = (B + R - 1) / R;

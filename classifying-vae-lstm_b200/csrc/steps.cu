@@ -168,7 +168,8 @@ static int pdl_enabled() {
 // Auxiliary stream for the weight-gradient branch (off the critical path of the step).  Created by
 // clv_runtime_init() OUTSIDE any stream capture; forked from / joined back into the caller's stream
 // with events, so all work stays ordered on the caller's stream (and is captured with it).
-constexpr int NAUX = 3;
+constexpr int NAUX = 4;     // aux[0..2]: round-robin side work; aux[3]: optimizer launches
+constexpr int NRR = 3;
 struct SideStream {
   cudaStream_t aux[NAUX] = {};
   cudaEvent_t fork_ev[8] = {};
@@ -193,8 +194,18 @@ struct Fork {
   }
   cudaStream_t next() {   // stream for the next independent side kernel
     if (!on) return main;
-    rr = (rr + 1) % NAUX;
+    rr = (rr + 1) % NRR;
     return s->aux[rr];
+  }
+  cudaStream_t opt_stream() { return on ? s->aux[NRR] : main; }
+  int gather() {   // the optimizer stream waits for everything enqueued on the round-robin streams
+    if (!on) return CLV_OK;
+    for (int i = 0; i < NRR; ++i) {
+      CLV_CUDA(cudaEventRecord(s->join_ev[nj][i], s->aux[i]));
+      CLV_CUDA(cudaStreamWaitEvent(s->aux[NRR], s->join_ev[nj][i], 0));
+    }
+    nj = (nj + 1) % 4;
+    return CLV_OK;
   }
   int fork() {   // side branches may now consume everything enqueued on main so far
     if (!on) return CLV_OK;
@@ -214,9 +225,17 @@ struct Fork {
   }
 };
 
+// opt != null: the optimizer is part of the schedule (single-GPU form, no exchange between backward
+// and update).  Adam-WN runs per tensor range as soon as that range's gradients are complete and
+// nothing later in the step reads those parameters: [Z heads | decoder | X head] during the encoder
+// BPTT, [key encoder] during the encoder weight gradients, [encoder LSTM] last.
 int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uint8_t* roll,
               const int32_t* off, const int32_t* labels, float* eps_w, float* eps_z,
-              uint64_t* ctr, float* ws, cudaStream_t st) {
+              uint64_t* ctr, float* ws, cudaStream_t st, const clv_adam_args* opt) {
+  auto adam = [&](int t0, int t1, int advance, cudaStream_t s_) {
+    return clv_adamwn_step_range(c, const_cast<float*>(P), Gr, opt->state, opt->lr, opt->beta_1, opt->beta_2,
+                                 opt->epsilon, opt->grad_scale, opt->weightnorm, t0, t1, advance, s_);
+  };
   int64_t po[CLV_N_TENSORS]; int32_t pr[CLV_N_TENSORS], pc[CLV_N_TENSORS];
   clv_param_layout(c, po, pr, pc);
   const int B = c->B, L = c->L, D = c->D, H = c->H, Z = c->Z, C = c->C, C1 = C - 1, G = 4 * H;
@@ -358,6 +377,11 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   // K2b bwd overwrites dh: its only reader (decoder BPTT) is ordered before it on st
   TRY_PDL(clv_gauss_heads_bwd(h_e, Kzm, Kzv, eps_z, Zargs, dZ, dh, gKzm, gbzm, gKzv, gbzv, BL, H, Z,
                               c->kl_weight * sbl, 0, st));
+  if (opt) {   // Z-head, decoder and X-head gradients are complete once the side branches drain
+    TRY(fk.fork());
+    TRY(fk.gather());
+    TRY(adam(R_ZM_K, CLV_N_TENSORS, 0, fk.opt_stream()));
+  }
   TRY_PDL(clv_lstm_bwd_fused(gates_e, Ue, c_e, dh, dAsum_e, Ke_w, C, dW_ext, 1, nullptr, 0, nullptr, B, L, H, st));
   TRY(fk.fork());
   if (tcw) {
@@ -373,6 +397,7 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
     TRY_PDL(clv_keyenc_bwd_full(roll, off, sx, L, D, Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, gKhw,
                                 gbhw, gKwa, gbwa, B, C, c->w_log_var_prior, c->class_weight * sb,
                                 c->w_kl_weight * sb, st));
+    if (opt) TRY_PDL(adam(R_HW_K, R_ENC_K, 0, st));   // key-encoder tensors: overlaps the encoder wgrads
   } else {
     TRY(clv_keyenc_bwd(Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, B, C, D,
                        c->w_log_var_prior, c->class_weight * sb, c->w_kl_weight * sb, st));
@@ -383,12 +408,13 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
     TRY(clv_colsum(dhW, D, B, D, gbhw, 1, fk.next()));
   }
   TRY(fk.join());
+  if (opt) TRY(adam(fused_ke ? R_ENC_K : R_HW_K, R_ZM_K, 1, st));
   return CLV_OK;
 }
 
 int vae_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uint8_t* roll,
              const int32_t* off, const int32_t* labels, float* eps_w, float* eps_z, uint64_t* ctr,
-             float* ws, cudaStream_t st) {
+             float* ws, cudaStream_t st, const clv_adam_args* opt) {
   int64_t po[CLV_N_TENSORS]; int32_t pr[CLV_N_TENSORS], pc[CLV_N_TENSORS];
   clv_param_layout(c, po, pr, pc);
   const int B = c->B, D = c->D, H = c->H, Hc = c->Hc, Z = c->Z, C = c->C, C1 = C - 1;
@@ -463,6 +489,9 @@ int vae_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uin
   TRY(nt_f32(dWargs + C1, 2 * C1, Kwv, C1, dh_w, Hc, B, Hc, C1, h_w, Hc, 1, st));
   TRY(tn_u8(roll, off, 1, sx, D, dh_w, Hc, gKhw, Hc, D, Hc, B, st));
   TRY(clv_colsum(dh_w, Hc, B, Hc, gbhw, 1, st));
+  if (opt)
+    TRY(clv_adamwn_step_range(c, const_cast<float*>(P), Gr, opt->state, opt->lr, opt->beta_1, opt->beta_2,
+                              opt->epsilon, opt->grad_scale, opt->weightnorm, 0, CLV_N_TENSORS, 1, st));
   return CLV_OK;
 }
 
@@ -535,22 +564,40 @@ extern "C" int64_t clv_workspace_offset(const clv_cfg* cfg, const char* name) {
   return carve(cfg).find(name);
 }
 
-extern "C" int clv_train_step(const clv_cfg* cfg, const float* params, float* grads,
-                              float* loss_acc, const uint8_t* roll, const int32_t* win_off,
-                              const int32_t* labels, float* eps_w, float* eps_z, uint64_t* rng_ctr,
-                              void* workspace, int64_t workspace_bytes, void* stream) {
+static int train_step_impl(const clv_cfg* cfg, const float* params, float* grads, float* loss_acc,
+                           const uint8_t* roll, const int32_t* win_off, const int32_t* labels,
+                           float* eps_w, float* eps_z, uint64_t* rng_ctr, void* workspace,
+                           int64_t workspace_bytes, const clv_adam_args* opt, void* stream) {
   int rc = check_cfg(cfg);
   if (rc != CLV_OK) return rc;
   if (!params || !loss_acc || !roll || !win_off || !labels || !eps_w || !eps_z || !workspace)
     return CLV_E_INVALID;
   if (cfg->do_backward && !grads) return CLV_E_INVALID;
   if (cfg->gen_noise && !rng_ctr) return CLV_E_INVALID;
+  if (opt && (!opt->state || !cfg->do_backward || cfg->accumulate)) return CLV_E_INVALID;
   if (workspace_bytes < carve(cfg).total * (int64_t)sizeof(float)) return CLV_E_WORKSPACE;
   if (cfg->B == 0) return CLV_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (cfg->model == 0)
     return vrnn_step(cfg, params, grads, loss_acc, roll, win_off, labels, eps_w, eps_z, rng_ctr,
-                     (float*)workspace, st);
+                     (float*)workspace, st, opt);
   return vae_step(cfg, params, grads, loss_acc, roll, win_off, labels, eps_w, eps_z, rng_ctr,
-                  (float*)workspace, st);
+                  (float*)workspace, st, opt);
+}
+
+extern "C" int clv_train_step(const clv_cfg* cfg, const float* params, float* grads,
+                              float* loss_acc, const uint8_t* roll, const int32_t* win_off,
+                              const int32_t* labels, float* eps_w, float* eps_z, uint64_t* rng_ctr,
+                              void* workspace, int64_t workspace_bytes, void* stream) {
+  return train_step_impl(cfg, params, grads, loss_acc, roll, win_off, labels, eps_w, eps_z, rng_ctr,
+                         workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" int clv_train_step_opt(const clv_cfg* cfg, float* params, float* grads, float* loss_acc,
+                                  const uint8_t* roll, const int32_t* win_off, const int32_t* labels,
+                                  float* eps_w, float* eps_z, uint64_t* rng_ctr, void* workspace,
+                                  int64_t workspace_bytes, const clv_adam_args* opt, void* stream) {
+  if (!opt) return CLV_E_INVALID;
+  return train_step_impl(cfg, params, grads, loss_acc, roll, win_off, labels, eps_w, eps_z, rng_ctr,
+                         workspace, workspace_bytes, opt, stream);
 }

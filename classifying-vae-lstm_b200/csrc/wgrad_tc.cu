@@ -12,6 +12,18 @@
 #include <cuda_bf16.h>
 #include "common.cuh"
 
+#ifdef CLV_PROF
+__device__ long long g_wprof[16];
+extern "C" int clv_debug_wprof(long long* out, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, g_wprof, sizeof(long long) * 16);
+  if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(g_wprof, z, sizeof(z)); }
+  return 0;
+}
+#define WPROF(i, cond) do { if ((cond) && blockIdx.x == 0 && blockIdx.y == 0) g_wprof[i] = clock64(); } while (0)
+#else
+#define WPROF(i, cond)
+#endif
+
 namespace {
 
 constexpr int WM = 128, WN = 176, KS = 32;          // UMMA M, N (one half of 4H) and rows per stage
@@ -22,6 +34,7 @@ constexpr int B_TILE = (WN / 8) * SBO;              // 11 264 B
 constexpr int STAGE = 3 * A_TILE + 2 * B_TILE;      // X | Hhi | Hmid | Dhi | Dmid = 47 104 B
 constexpr int NSTAGE = 4;
 constexpr int NPROD = 8;                            // producer warps
+constexpr int NBATCH = 6;                           // column-group tasks a producer warp keeps in flight
 constexpr int WTHREADS = (NPROD + 1) * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,6 +126,7 @@ __global__ void __launch_bounds__(WTHREADS, 1) lstm_wgrad_tc_kernel(const WgArgs
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = blockIdx.y, n0 = half * WN;
+  WPROF(0, tid == 0);
   const uint32_t bar0 = smem_u32(&bars[0]);
   auto FULL = [&](int s) { return bar0 + 8u * s; };
   auto EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
@@ -144,6 +158,7 @@ __global__ void __launch_bounds__(WTHREADS, 1) lstm_wgrad_tc_kernel(const WgArgs
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
+  WPROF(1, tid == 0);
   const int st0 = blockIdx.x * a.stages_per_cta;
   const int nst = max(0, min(a.stages_per_cta, a.stages - st0));
   const int ngx = a.D / 8, ngh = a.H / 8, ngz = a.Zs ? 1 : 0, ngb = WN / 8;   // 8-column group tasks
@@ -163,13 +178,13 @@ __global__ void __launch_bounds__(WTHREADS, 1) lstm_wgrad_tc_kernel(const WgArgs
       }
       mbar_wait(EMPTY(s), ph ^ 1);
       uint8_t* sb = smem + s * STAGE + (lane >> 3) * LBO + (lane & 7) * 16;   // this row's slot
-      // tasks of this warp in batches of 3: issue every global load of the batch, then convert and
-      // store (one memory round trip per batch instead of per task)
-      for (int task0 = warp; task0 < ntask; task0 += 3 * NPROD) {
-        float v[3][8];
-        uint2 q[3];
+      // tasks of this warp in batches of NBATCH (all of a stage's for the built shapes): issue every
+      // global load of the batch, then convert and store -- one memory round trip per stage
+      for (int task0 = warp; task0 < ntask; task0 += NBATCH * NPROD) {
+        float v[NBATCH][8];
+        uint2 q[NBATCH];
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
+        for (int u = 0; u < NBATCH; ++u) {
           const int task = task0 + u * NPROD;
           q[u] = make_uint2(0u, 0u);
 #pragma unroll
@@ -192,12 +207,14 @@ __global__ void __launch_bounds__(WTHREADS, 1) lstm_wgrad_tc_kernel(const WgArgs
                 v[u][4] = y.x; v[u][5] = y.y; v[u][6] = y.z; v[u][7] = y.w;
               }
             } else {
-              for (int j = 0; j < a.Z; ++j) v[u][j] = __ldg(a.Zs + r * a.Z + j);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (j < a.Z) v[u][j] = __ldg(a.Zs + r * a.Z + j);
             }
           }
         }
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
+        for (int u = 0; u < NBATCH; ++u) {
           const int task = task0 + u * NPROD;
           if (task >= ntask) continue;
           if (task < ngb) {
@@ -224,6 +241,7 @@ __global__ void __launch_bounds__(WTHREADS, 1) lstm_wgrad_tc_kernel(const WgArgs
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(FULL(s));
+      WPROF(2 + it, tid == 0 && it < 4);
     }
   } else if (lane == 0) {
     // ================= MMA thread
@@ -253,18 +271,26 @@ __global__ void __launch_bounds__(WTHREADS, 1) lstm_wgrad_tc_kernel(const WgArgs
     }
     umma_commit(DONE);
   }
-  // ================= epilogue: everything joins; warps 0-3 drain TMEM (warp q = lanes 32q..)
+  // ================= epilogue: everything joins; the 8 producer warps drain TMEM
   __syncwarp();
   mbar_wait(DONE, 0);
+  WPROF(6, tid == 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (warp < 4 && nst > 0) {
+  if (warp < NPROD && nst > 0) {
+    // warps w and w+4 share TMEM lane quadrant w%4 and split its column chunks; CTAs start at
+    // different chunks / rows so that concurrent CTAs do not queue on the same L2 atomics
+    // (red.add.v2 was measured slower than scalar red here: the L2 cost is per element)
+    const int quad = warp & 3;
     float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 33);   // operand stages are free now
+    constexpr int NCH = (WN + 31) / 32;
     for (int tile = (a.gKx ? 0 : 1); tile < 2; ++tile) {
-      const uint32_t tacc = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tile * 256);
+      const uint32_t tacc = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tile * 256);
       const int mvalid = (tile == 0) ? a.D : a.H + a.Z;      // rows of this accumulator that exist
-      if (warp * 32 >= mvalid) continue;
+      if (quad * 32 >= mvalid) continue;
+      const int nvalid = min(32, mvalid - quad * 32);
 #pragma unroll 1
-      for (int c0 = 0; c0 < WN; c0 += 32) {
+      for (int ci = (warp >> 2); ci < NCH; ci += 2) {
+        const int c0 = 32 * ((ci + (int)blockIdx.x) % NCH);
         const int ncol = min(32, WN - c0);
         uint32_t r[32];
         if (ncol == 32) {
@@ -278,23 +304,27 @@ __global__ void __launch_bounds__(WTHREADS, 1) lstm_wgrad_tc_kernel(const WgArgs
 #pragma unroll
         for (int i = 0; i < 32; ++i) stage[lane * 33 + i] = __uint_as_float(r[i]);
         __syncwarp();
+        const int rot = (5 * (int)blockIdx.x) % nvalid;
         if (lane < ncol) {
-          const int nvalid = min(32, mvalid - warp * 32);
-          for (int rr = 0; rr < nvalid; ++rr) {
-            const int m = warp * 32 + rr;
+          int rr = rot;
+          for (int i = 0; i < nvalid; ++i) {
+            const int m = quad * 32 + rr;
             float* dst;
             if (tile == 0) dst = a.gKx + (int64_t)m * a.G;
             else if (m < a.H) dst = a.gU + (int64_t)m * a.G;
             else dst = a.gKz + (int64_t)(m - a.H) * a.G;
             atomicAdd(dst + n0 + c0 + lane, stage[rr * 33 + lane]);
+            rr = (rr + 1 == nvalid) ? 0 : rr + 1;
           }
         }
         __syncwarp();
       }
     }
   }
+  WPROF(7, tid == 0);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  WPROF(8, tid == 0);
   if (warp == NPROD) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import lib, check, ptr
+from ._lib import lib, check, ptr, clv_adam_args
 
 VRNN_TENSORS = ["hW.kernel", "hW.bias", "Wargs.kernel", "Wargs.bias",
                 "encoder_h.kernel", "encoder_h.recurrent_kernel", "encoder_h.bias",
@@ -41,7 +41,8 @@ class Engine:
                  class_weight=1.0, kl_weight=1.0, w_kl_weight=1.0, w_log_var_prior=0.0,
                  optimizer="adam-wn", lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-8,
                  seed=0, device=None, world_size=1, rank=0, process_group=None, use_graph=True,
-                 overlap_wgrad=True, gemm_algo=1, p2p_allreduce=False, tc_lstm_min=0):
+                 overlap_wgrad=True, gemm_algo=1, p2p_allreduce=False, tc_lstm_min=0,
+                 fused_optimizer=True):
         _require_cuda()
         lib()
         if optimizer not in ("adam-wn", "adam"):
@@ -62,6 +63,7 @@ class Engine:
         self.use_graph = use_graph
         self.overlap_wgrad = bool(overlap_wgrad)
         self.tc_lstm_min = int(tc_lstm_min)        # 0 = library default (8192)
+        self.fused_optimizer = bool(fused_optimizer)   # world_size 1: clv_train_step_opt
         self.gemm_algo = int(gemm_algo)            # 0: exact-fp32 SIMT GEMMs, 1: tcgen05 input projections
         if self.overlap_wgrad:
             with torch.cuda.device(self.dev):
@@ -206,6 +208,17 @@ class Engine:
     # ------------------------------------------------------------------ one step
     def _launch_step(self, train, gen_noise):
         cfg = self.cfg(gen_noise=int(gen_noise), do_backward=int(train))
+        if train and self.world_size == 1 and self.fused_optimizer:
+            # single GPU: nothing sits between backward and update, so the optimizer is part of the
+            # step's schedule (Adam-WN per tensor range, overlapped with the encoder BPTT / wgrads)
+            opt = clv_adam_args(state=self.opt_state.data_ptr(), lr=self.lr, beta_1=self.b1, beta_2=self.b2,
+                                epsilon=self.eps, grad_scale=1.0, weightnorm=int(self.optimizer == "adam-wn"))
+            check(lib().clv_train_step_opt(C.byref(cfg), ptr(self.params), ptr(self.grads), ptr(self.loss_acc),
+                                           ptr(self.roll), ptr(self.win_off), ptr(self.labels),
+                                           ptr(self.eps_w), ptr(self.eps_z), ptr(self.rng_ctr),
+                                           ptr(self.workspace), self.workspace.numel() * 4, C.byref(opt),
+                                           _stream()), "clv_train_step_opt")
+            return
         check(lib().clv_train_step(C.byref(cfg), ptr(self.params), ptr(self.grads), ptr(self.loss_acc),
                                    ptr(self.roll), ptr(self.win_off), ptr(self.labels),
                                    ptr(self.eps_w), ptr(self.eps_z), ptr(self.rng_ctr),

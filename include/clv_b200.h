@@ -241,6 +241,14 @@ int clv_adamwn_init(const clv_cfg* cfg, float* state, void* stream);
 int clv_adamwn_step(const clv_cfg* cfg, float* params, const float* grads, float* state, double lr,
                     double beta_1, double beta_2, double epsilon, double grad_scale, int32_t weightnorm,
                     void* stream);
+/* The same update restricted to the tensors [t_first, t_last) of clv_param_layout's order (weight-norm
+ * is per tensor column, so ranges are independent).  `advance` != 0 on exactly one -- the last -- call
+ * of a step: it increments `iterations` when its last block retires; all ranges of a step must be
+ * issued before that call completes. */
+int clv_adamwn_step_range(const clv_cfg* cfg, float* params, const float* grads, float* state, double lr,
+                          double beta_1, double beta_2, double epsilon, double grad_scale,
+                          int32_t weightnorm, int32_t t_first, int32_t t_last, int32_t advance,
+                          void* stream);
 
 /* Data-parallel form: gradient all-reduce FUSED into the optimizer over NVLink peer memory.
  * peer_grads = device array of n_peers pointers to every rank's [grads(P) | losses(8)] buffer in
@@ -268,6 +276,22 @@ int clv_train_step(const clv_cfg* cfg, const float* params, float* grads, float*
                    const uint8_t* roll, const int32_t* win_off, const int32_t* labels,
                    float* eps_w, float* eps_z, uint64_t* rng_ctr, void* workspace,
                    int64_t workspace_bytes, void* stream);
+/* clv_train_step followed by the optimizer update of the same step, as ONE schedule (the reference's
+ * train_function = gradients + AdamWithWeightnorm updates in one session.run, cl_vrnn/train.py:66-71
+ * + utils/weightnorm.py:75-143).  For the single-GPU case, where nothing sits between backward and
+ * update: Adam-WN is launched per tensor range as soon as that range's gradients are final and no
+ * later kernel of the step reads those parameters, so most of the update overlaps the encoder BPTT
+ * and the weight-gradient kernels.  Result identical to clv_train_step + clv_adamwn_step.
+ * Requires do_backward=1, accumulate=0. */
+typedef struct clv_adam_args {
+  float* state;                 /* clv_adamwn_state_floats() floats, initialised by clv_adamwn_init */
+  double lr, beta_1, beta_2, epsilon, grad_scale;
+  int32_t weightnorm;
+} clv_adam_args;
+int clv_train_step_opt(const clv_cfg* cfg, float* params, float* grads, float* loss_acc,
+                       const uint8_t* roll, const int32_t* win_off, const int32_t* labels,
+                       float* eps_w, float* eps_z, uint64_t* rng_ctr, void* workspace,
+                       int64_t workspace_bytes, const clv_adam_args* opt, void* stream);
 /* Named views into the workspace after a step (for parity tests): returns the float offset of
  * e.g. "W", "Zargs", "h_e", "h_d", "logits" or -1. */
 int64_t clv_workspace_offset(const clv_cfg* cfg, const char* name);

@@ -71,6 +71,29 @@ def test_vrnn_training_trajectory_and_graph_replay():
         assert util.rel_err(a[k], b[k]) < 1e-4   # atomics order differs between eager and graph replays
 
 
+@pytest.mark.parametrize("model", ["vrnn", "vae"])
+def test_step_with_scheduled_optimizer_equals_step_then_adam(model):
+    """clv_train_step_opt (Adam-WN launched per tensor range inside the step's schedule) gives the same
+    parameters, optimizer state and `iterations` as clv_train_step followed by clv_adamwn_step."""
+    if model == "vrnn":
+        case = util.make_vrnn_case(123, 48, 9, C=5, Z=2, use_x_prev=True)
+    else:
+        case = util.make_vae_case(77, 64, C=5, Z=3, use_x_prev=True)
+    a = util.engine_for(case, model, use_graph=False, fused_optimizer=True)
+    b = util.engine_for(case, model, use_graph=False, fused_optimizer=False)
+    for _ in range(4):
+        a.run(train=True, gen_noise=False)
+        b.run(train=True, gen_noise=False)
+    pa, pb = a.get_params(), b.get_params()
+    for k in pa:
+        assert util.rel_err(pa[k], pb[k]) < 2e-5, k
+    n = a.opt_state.numel()
+    assert util.rel_err(a.opt_state[:n - 2].cpu().numpy(), b.opt_state[:n - 2].cpu().numpy()) < 2e-5
+    ia = a.opt_state[n - 2:].view(torch.int32).cpu().tolist()
+    ib = b.opt_state[n - 2:].view(torch.int32).cpu().tolist()
+    assert ia == ib == [4, 0]          # iterations advanced once per step, done-counter back at zero
+
+
 def test_in_kernel_noise_is_standard_normal_and_fresh():
     case = util.make_vrnn_case(5, 256, 8, C=10, Z=2)
     e = util.engine_for(case, "vrnn", use_graph=True)
