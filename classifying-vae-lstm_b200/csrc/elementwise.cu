@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256) gauss_heads_bwd_kernel(
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
       const int k = lane + 32 * i;
-      if (k < H) dh[row * H + k] = (relu_input && !(hk[i] > 0.f)) ? 0.f : dhk[i];
+      if (dh && k < H) dh[row * H + k] = (relu_input && !(hk[i] > 0.f)) ? 0.f : dhk[i];
     }
   }
   // block-level reduction in shared memory (reusing the transposed-kernel buffer), then one global
@@ -364,7 +364,7 @@ extern "C" int clv_gauss_heads_bwd(const float* h, const float* Km, const float*
                                     float* dh, float* dKm, float* dbm, float* dKv, float* dbv,
                                     int64_t R, int32_t H, int32_t Z, float klw_scale,
                                     int32_t relu_input, void* stream) {
-  if (!h || !Km || !Kv || !eps || !Zargs || !dZ || !dh || !dKm || !dbm || !dKv || !dbv)
+  if (!h || !Km || !Kv || !eps || !Zargs || !dZ || !dKm || !dbm || !dKv || !dbv)   // dh may be null
     return CLV_E_INVALID;
   if (H < 1 || H > 32 * KMAX || Z < 1 || Z > 16) return CLV_E_UNSUPPORTED;
   if (R <= 0) return CLV_OK;

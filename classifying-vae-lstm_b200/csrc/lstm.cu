@@ -43,7 +43,14 @@ struct LstmExtra {
   float* dZ;           // bwd only: [B,L,Z] out (dLoss/dZ) or null
   float* dW_ext;       // bwd only: [B,C] (+)= dAsum @ Ww^T or null
   int C, Z, has_xproj, dW_accumulate;
+  // bwd, Z-head exchange of the CL-VRNN (cl_vrnn/model.py:200-216) fused in:
+  //   decoder side: with dZ also emit dZa_out[B,L,2Z] = dLoss/d(Z_mean | Z_log_var)
+  //                 (reparametrisation backward + kl term; needs Zargs, eps_z, klw)
+  //   encoder side: dLoss/dh_t (+)= dZa_in[b,t,:] @ [Kzm | Kzv]^T, computed per cell (ZH <= ZB)
+  const float* Zargs; const float* eps_z; float klw; float* dZa_out;
+  const float* dZa_in; const float* Kzm; const float* Kzv; int ZH;
 };
+constexpr int ZB = 2;     // latent dimensions of the encoder-side head dgrad kept in registers
 constexpr int ZMAX = 16;
 constexpr int ZR = 2;     // latent values per step kept / prefetched in registers (forward)
 constexpr int ZQ = 8;     // latent dimensions folded into the backward mat-vec as extra output quads
@@ -231,6 +238,19 @@ lstm_fwd_kernel(float* __restrict__ gates, const float* __restrict__ U, float* _
   }
 }
 
+// dZ of one (row-step, latent) and, for the fused Z-head exchange, dLoss/d(Z_mean | Z_log_var):
+// Z = mu + exp(lv/2) eps and the kl term (same maths as gauss_heads_bwd_kernel)
+__device__ __forceinline__ void emit_dz(const LstmExtra& ex, const size_t bt, const int z, const int Z,
+                                        const float dz) {
+  ex.dZ[bt * Z + z] = dz;
+  if (ex.dZa_out) {
+    const float mu = __ldg(ex.Zargs + bt * 2 * Z + z), lv = __ldg(ex.Zargs + bt * 2 * Z + Z + z);
+    const float e = __ldg(ex.eps_z + bt * Z + z);
+    ex.dZa_out[bt * 2 * Z + z] = dz + ex.klw * mu;
+    ex.dZa_out[bt * 2 * Z + Z + z] = dz * e * 0.5f * expf(lv * 0.5f) + ex.klw * 0.5f * (expf(lv) - 1.0f);
+  }
+}
+
 // backward: thread (kq, ns) owns a 4 x 22 tile of U^T: outputs k = 4kq..4kq+3 (kq < H/4) -- or rows
 // z = 4(kq-H/4).. of Kz, which turns dZ = dA @ Kz^T into four more outputs of the same mat-vec --
 // and the n-slice ns (22 of the 4H gate columns).  The reduce-scatter over the 16 ns lanes leaves
@@ -280,14 +300,23 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
   pdl_launch_dependents();
   for (int i = tid; i < 2 * RMAX * G; i += blockDim.x) (&da_s[0][0][0])[i] = 0.f;
 
+  float kzm[ZB], kzv[ZB];
+#pragma unroll
+  for (int z = 0; z < ZB; ++z) {
+    const bool v = ex.dZa_in && is_u && z < ex.ZH;
+    kzm[z] = v ? __ldg(ex.Kzm + (size_t)j * ex.ZH + z) : 0.f;
+    kzv[z] = v ? __ldg(ex.Kzv + (size_t)j * ex.ZH + z) : 0.f;
+  }
   float dc[NP], dhrec[NP], asum[NP][4];
   // software pipeline: operands of the cell phase of step t-1 are loaded during step t
-  float pg[NP][4], pct[NP], pc2[NP], pdh[NP];
+  float pg[NP][4], pct[NP], pc2[NP], pdh[NP], pza[NP][2 * ZB];
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
     dc[p] = dhrec[p] = 0.f;
     asum[p][0] = asum[p][1] = asum[p][2] = asum[p][3] = 0.f;
     pg[p][0] = pg[p][1] = pg[p][2] = pg[p][3] = pct[p] = pc2[p] = pdh[p] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2 * ZB; ++i) pza[p][i] = 0.f;
     const int r = p * RC + q_c;
     if (is_u && lane_on && r < nrows) {
       const size_t base = (size_t)(b0 + r) * L + (L - 1);
@@ -295,7 +324,15 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
       pg[p][0] = gp[0]; pg[p][1] = gp[H]; pg[p][2] = gp[2 * H]; pg[p][3] = gp[3 * H];
       pct[p] = __ldg(c + base * H + j);
       pc2[p] = (L > 1) ? __ldg(c + (base - 1) * H + j) : 0.f;
-      pdh[p] = __ldg(dh_out + base * H + j);
+      if (dh_out) pdh[p] = __ldg(dh_out + base * H + j);
+      if (ex.dZa_in) {
+#pragma unroll
+        for (int z = 0; z < ZB; ++z)
+          if (z < ex.ZH) {
+            pza[p][z] = __ldg(ex.dZa_in + base * 2 * ex.ZH + z);
+            pza[p][ZB + z] = __ldg(ex.dZa_in + base * 2 * ex.ZH + ex.ZH + z);
+          }
+      }
     }
   }
   __syncthreads();
@@ -312,13 +349,23 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
         float* gp = gates + base * G + j;
         const float ig = pg[p][0], fg = pg[p][1], gg = pg[p][2], og = pg[p][3];
         const float ct = pct[p], cprev = pc2[p];
-        const float dh = pdh[p] + dhrec[p];
+        float dh = pdh[p] + dhrec[p];
+#pragma unroll
+        for (int z = 0; z < ZB; ++z) dh = fmaf(pza[p][z], kzm[z], fmaf(pza[p][ZB + z], kzv[z], dh));
         if (t > 0) {   // issue next step's loads now; they land during the mat-vec below
           const float* gq = gp - G;
           pg[p][0] = gq[0]; pg[p][1] = gq[H]; pg[p][2] = gq[2 * H]; pg[p][3] = gq[3 * H];
           pct[p] = cprev;
           pc2[p] = (t > 1) ? __ldg(c + (base - 2) * H + j) : 0.f;
-          pdh[p] = __ldg(dh_out + (base - 1) * H + j);
+          if (dh_out) pdh[p] = __ldg(dh_out + (base - 1) * H + j);
+          if (ex.dZa_in) {
+#pragma unroll
+            for (int z = 0; z < ZB; ++z)
+              if (z < ex.ZH) {
+                pza[p][z] = __ldg(ex.dZa_in + (base - 1) * 2 * ex.ZH + z);
+                pza[p][ZB + z] = __ldg(ex.dZa_in + (base - 1) * 2 * ex.ZH + ex.ZH + z);
+              }
+          }
         }
         const float tc = tanhf(ct);
         const float d_o = dh * tc;
@@ -366,7 +413,7 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
       if (is_u) {
         dhrec[p] = val;
       } else if (lane_on && zo < Z && zo < ZQ && r0 + q_c < nrows) {
-        ex.dZ[((size_t)(b0 + r0 + q_c) * L + t) * Z + zo] = val;
+        emit_dz(ex, ((size_t)(b0 + r0 + q_c) * L + t), zo, Z, val);
       }
     }
     // latent dimensions beyond the folded ones: one warp per (row, z) dot product
@@ -375,7 +422,7 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
       float p = 0.f;
       for (int i = lane; i < G; i += 32) p = fmaf(da_s[buf][r][i], __ldg(ex.Kz + (size_t)zz * G + i), p);
       p = warp_sum(p);
-      if (lane == 0) ex.dZ[((size_t)(b0 + r) * L + t) * Z + zz] = p;
+      if (lane == 0) emit_dz(ex, ((size_t)(b0 + r) * L + t), zz, Z, p);
     }
     buf ^= 1;
   }
@@ -428,8 +475,8 @@ int lstm_fwd_launch(float* gates, const float* U, float* h, float* c, const floa
 
 int lstm_bwd_launch(float* gates, const float* U, const float* c, const float* dh_out, float* dAsum,
                     int B, int L, int H, const LstmExtra& ex, cudaStream_t st) {
-  if (!gates || !U || !c || !dh_out || !dAsum) return CLV_E_INVALID;
-  if (H != 88 || ex.Z > ZMAX) return CLV_E_UNSUPPORTED;
+  if (!gates || !U || !c || (!dh_out && !ex.dZa_in) || !dAsum) return CLV_E_INVALID;
+  if (H != 88 || ex.Z > ZMAX || (ex.dZa_in && ex.ZH > ZB)) return CLV_E_UNSUPPORTED;
   // float2 parameter loads (true for clv_param_layout offsets: every tensor before U / Kz has even size)
   if (((uintptr_t)U & 7) || (ex.dZ && ((uintptr_t)ex.Kz & 7))) return CLV_E_UNSUPPORTED;
   if (B <= 0 || L <= 0) return CLV_OK;
@@ -480,5 +527,22 @@ extern "C" int clv_lstm_bwd_fused(float* gates, const float* U, const float* c, 
   ex.Ww = Ww; ex.C = C; ex.dW_ext = dW_ext; ex.dW_accumulate = dW_accumulate;
   ex.Kz = Kz; ex.Z = Z; ex.dZ = dZ;
   if ((dW_ext && (!Ww || C < 1)) || (dZ && (!Kz || Z < 1))) return CLV_E_INVALID;
+  return lstm_bwd_launch(gates, U, c, dh_out, dAsum, B, L, H, ex, (cudaStream_t)stream);
+}
+
+extern "C" int clv_lstm_bwd_heads(float* gates, const float* U, const float* c, const float* dh_out,
+                                  float* dAsum, const float* Ww, int32_t C, float* dW_ext,
+                                  int32_t dW_accumulate, const float* Kz, int32_t Z, float* dZ,
+                                  const float* Zargs, const float* eps_z, float klw_scale, float* dZargs_out,
+                                  const float* dZargs_in, const float* Kzm, const float* Kzv, int32_t Zh,
+                                  int32_t B, int32_t L, int32_t H, void* stream) {
+  LstmExtra ex = {};
+  ex.Ww = Ww; ex.C = C; ex.dW_ext = dW_ext; ex.dW_accumulate = dW_accumulate;
+  ex.Kz = Kz; ex.Z = Z; ex.dZ = dZ;
+  ex.Zargs = Zargs; ex.eps_z = eps_z; ex.klw = klw_scale; ex.dZa_out = dZargs_out;
+  ex.dZa_in = dZargs_in; ex.Kzm = Kzm; ex.Kzv = Kzv; ex.ZH = Zh;
+  if ((dW_ext && (!Ww || C < 1)) || (dZ && (!Kz || Z < 1))) return CLV_E_INVALID;
+  if (dZargs_out && (!dZ || !Zargs || !eps_z)) return CLV_E_INVALID;
+  if (dZargs_in && (!Kzm || !Kzv || Zh < 1)) return CLV_E_INVALID;
   return lstm_bwd_launch(gates, U, c, dh_out, dAsum, B, L, H, ex, (cudaStream_t)stream);
 }

@@ -82,7 +82,7 @@ Ws carve(const clv_cfg* c) {
     w.add("Zargs", BL * 2 * Z); w.add("Zs", BL * Z);
     w.add("rb_d", B * G); w.add("gates_d", BL * G); w.add("h_d", BL * H); w.add("c_d", BL * H);
     w.add("logits", BL * D); w.add("dh", BL * H);
-    w.add("dAsum_d", B * G); w.add("dAsum_e", B * G); w.add("dZ", BL * Z);
+    w.add("dAsum_d", B * G); w.add("dAsum_e", B * G); w.add("dZ", BL * Z); w.add("dZa", BL * 2 * Z);
     w.add("dW_ext", B * C); w.add("dWargs", B * 2 * C1); w.add("dhW", B * D);
     w.add("wimg_e", clv_inproj_tc_scratch_bytes() / 4); w.add("wimg_d", clv_inproj_tc_scratch_bytes() / 4);
     w.add("uimg_e", clv_lstm_fwd_tc_scratch_bytes() / 4); w.add("uimg_d", clv_lstm_fwd_tc_scratch_bytes() / 4);
@@ -227,8 +227,8 @@ struct Fork {
 
 // opt != null: the optimizer is part of the schedule (single-GPU form, no exchange between backward
 // and update).  Adam-WN runs per tensor range as soon as that range's gradients are complete and
-// nothing later in the step reads those parameters: [Z heads | decoder | X head] during the encoder
-// BPTT, [key encoder] during the encoder weight gradients, [encoder LSTM] last.
+// nothing later in the step reads those parameters: [decoder | X head] during the encoder BPTT,
+// [key encoder] during the encoder weight gradients, [encoder LSTM | Z heads] last.
 int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uint8_t* roll,
               const int32_t* off, const int32_t* labels, float* eps_w, float* eps_z,
               uint64_t* ctr, float* ws, cudaStream_t st, const clv_adam_args* opt) {
@@ -248,7 +248,7 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
         *gates_e = WSP("gates_e"), *h_e = WSP("h_e"), *c_e = WSP("c_e"), *Zargs = WSP("Zargs"),
         *Zs = WSP("Zs"), *rb_d = WSP("rb_d"), *gates_d = WSP("gates_d"), *h_d = WSP("h_d"),
         *c_d = WSP("c_d"), *logits = WSP("logits"), *dh = WSP("dh"), *dAsum_d = WSP("dAsum_d"),
-        *dAsum_e = WSP("dAsum_e"), *dZ = WSP("dZ"), *dW_ext = WSP("dW_ext"),
+        *dAsum_e = WSP("dAsum_e"), *dZ = WSP("dZ"), *dZa = WSP("dZa"), *dW_ext = WSP("dW_ext"),
         *dWargs = WSP("dWargs"), *dhW = WSP("dhW"), *wimg_e = WSP("wimg_e"), *wimg_d = WSP("wimg_d"),
         *uimg_e = WSP("uimg_e"), *uimg_d = WSP("uimg_d");
 #undef WSP
@@ -360,8 +360,19 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   TRY(fk.fork());
   TRY(tn_f32(h_d, H, logits, D, gKx, D, H, D, BL, 0, 0, fk.next()));
   TRY(clv_colsum(logits, D, BL, D, gbx, 1, fk.next()));
-  if (H == 88 && D == 88) TRY_PDL(clv_lstm_bwd_fused(gates_d, Ud, c_d, dh, dAsum_d, Kd_w, C, dW_ext, 0, Kd_z, Z, dZ, B, L, H, st));
-  else TRY(clv_lstm_bwd_fused(gates_d, Ud, c_d, dh, dAsum_d, Kd_w, C, dW_ext, 0, Kd_z, Z, dZ, B, L, H, st));
+  // Z-head exchange fused into the two BPTT kernels (Z <= 2): the decoder BPTT also emits
+  // dLoss/d(Z_mean|Z_log_var), the encoder BPTT turns it into dLoss/dh_e per cell, and the head
+  // weight gradients move to a side stream -- no kernel between the two recurrences
+  const bool fuse_heads = Z <= 2;
+  const float klw = c->kl_weight * sbl;
+  g_clv_pdl = (H == 88 && D == 88) ? pdl_enabled() : 0;
+  {
+    const int rc__ = clv_lstm_bwd_heads(gates_d, Ud, c_d, dh, dAsum_d, Kd_w, C, dW_ext, 0, Kd_z, Z, dZ,
+                                        fuse_heads ? Zargs : nullptr, fuse_heads ? eps_z : nullptr, klw,
+                                        fuse_heads ? dZa : nullptr, nullptr, nullptr, nullptr, 0, B, L, H, st);
+    g_clv_pdl = 0;
+    if (rc__ != CLV_OK) return rc__;
+  }
   TRY(fk.fork());
   const bool tcw = tc && H == 88 && Z <= 8;   // tcgen05 weight gradients
   if (tcw) {
@@ -374,15 +385,25 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   }
   TRY(tn_f32(W, C, dAsum_d, G, gKd + (int64_t)(xo + Z) * G, G, C, G, B, 0, 0, fk.next()));
   TRY(clv_colsum(dAsum_d, G, B, G, gbd, 1, fk.next()));
-  // K2b bwd overwrites dh: its only reader (decoder BPTT) is ordered before it on st
-  TRY_PDL(clv_gauss_heads_bwd(h_e, Kzm, Kzv, eps_z, Zargs, dZ, dh, gKzm, gbzm, gKzv, gbzv, BL, H, Z,
-                              c->kl_weight * sbl, 0, st));
-  if (opt) {   // Z-head, decoder and X-head gradients are complete once the side branches drain
+  if (fuse_heads) {
+    // head weight gradients only (dh = null), off the critical path
+    TRY(clv_gauss_heads_bwd(h_e, Kzm, Kzv, eps_z, Zargs, dZ, nullptr, gKzm, gbzm, gKzv, gbzv, BL, H, Z, klw, 0,
+                            fk.next()));
+  } else {
+    // K2b bwd overwrites dh: its only reader (decoder BPTT) is ordered before it on st
+    TRY_PDL(clv_gauss_heads_bwd(h_e, Kzm, Kzv, eps_z, Zargs, dZ, dh, gKzm, gbzm, gKzv, gbzv, BL, H, Z, klw, 0, st));
+  }
+  if (opt) {   // decoder and X-head gradients are complete once the side branches drain; the Z heads
+               // stay out of this range: the encoder BPTT below still reads their kernels
     TRY(fk.fork());
     TRY(fk.gather());
-    TRY(adam(R_ZM_K, CLV_N_TENSORS, 0, fk.opt_stream()));
+    TRY(adam(R_DEC_K, CLV_N_TENSORS, 0, fk.opt_stream()));
   }
-  TRY_PDL(clv_lstm_bwd_fused(gates_e, Ue, c_e, dh, dAsum_e, Ke_w, C, dW_ext, 1, nullptr, 0, nullptr, B, L, H, st));
+  if (fuse_heads)
+    TRY_PDL(clv_lstm_bwd_heads(gates_e, Ue, c_e, nullptr, dAsum_e, Ke_w, C, dW_ext, 1, nullptr, 0, nullptr,
+                               nullptr, nullptr, 0.f, nullptr, dZa, Kzm, Kzv, Z, B, L, H, st));
+  else
+    TRY_PDL(clv_lstm_bwd_fused(gates_e, Ue, c_e, dh, dAsum_e, Ke_w, C, dW_ext, 1, nullptr, 0, nullptr, B, L, H, st));
   TRY(fk.fork());
   if (tcw) {
     TRY(clv_lstm_wgrad_tc(gates_e, roll, off, L, sx, D, h_e, nullptr, 0, gKe, gUe, nullptr, BL, H, fk.next()));
@@ -408,7 +429,7 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
     TRY(clv_colsum(dhW, D, B, D, gbhw, 1, fk.next()));
   }
   TRY(fk.join());
-  if (opt) TRY(adam(fused_ke ? R_ENC_K : R_HW_K, R_ZM_K, 1, st));
+  if (opt) TRY(adam(fused_ke ? R_ENC_K : R_HW_K, R_DEC_K, 1, st));
   return CLV_OK;
 }
 

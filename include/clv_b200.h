@@ -147,7 +147,7 @@ int clv_gauss_heads_fwd(const float* h, const float* Km, const float* bm, const 
                         const float* bv, float* eps, float* Zargs, float* Zs, float* loss_acc,
                         int64_t R, int32_t H, int32_t Z, float scale, int32_t gen_noise,
                         uint64_t seed, const uint64_t* ctr, void* stream);
-/* Backward: dZ[R,Z] -> dh[R,H] (overwritten; multiplied by [h>0] when relu_input, the CL-VAE case
+/* Backward: dZ[R,Z] -> dh[R,H] (overwritten; null = weight gradients only; multiplied by [h>0] when relu_input, the CL-VAE case
  * where h is a ReLU output) and atomically accumulated dKm,dbm,dKv,dbv.
  * klw_scale = kl_weight / (B_global*L). */
 int clv_gauss_heads_bwd(const float* h, const float* Km, const float* Kv, const float* eps,
@@ -179,6 +179,20 @@ int clv_lstm_bwd_fused(float* gates, const float* U, const float* c, const float
                        const float* Ww, int32_t C, float* dW_ext, int32_t dW_accumulate,
                        const float* Kz, int32_t Z, float* dZ, int32_t B, int32_t L, int32_t H,
                        void* stream);
+
+/* clv_lstm_bwd_fused with the Z-head exchange of the CL-VRNN (cl_vrnn/model.py:200-216,236-239) folded
+ * into the two BPTT kernels so that no kernel sits between them:
+ *   decoder call (dZargs_out, Zargs, eps_z non-null): besides dZ writes dZargs_out[B,L,2Z] =
+ *     dLoss/d(Z_mean | Z_log_var) = backward of Z = mu + exp(lv/2) eps plus the kl term
+ *     (klw_scale = kl_weight / (B_global L)), i.e. the first half of clv_gauss_heads_bwd;
+ *   encoder call (dZargs_in, Kzm, Kzv non-null, Zh <= 2): dh_out may be null;
+ *     dLoss/dh[b,t,:] (+)= dZargs_in[b,t,:] @ [Kzm | Kzv]^T per cell, i.e. its second half.
+ * The head weight gradients stay with clv_gauss_heads_bwd (dh = null: weight gradients only). */
+int clv_lstm_bwd_heads(float* gates, const float* U, const float* c, const float* dh_out, float* dAsum,
+                       const float* Ww, int32_t C, float* dW_ext, int32_t dW_accumulate,
+                       const float* Kz, int32_t Z, float* dZ, const float* Zargs, const float* eps_z,
+                       float klw_scale, float* dZargs_out, const float* dZargs_in, const float* Kzm,
+                       const float* Kzv, int32_t Zh, int32_t B, int32_t L, int32_t H, void* stream);
 
 /* Tensor-core form of the forward recurrence for large batches: 128 rows per CTA, h_{t-1} @ U on
  * tcgen05 (fp16 hi+lo splits of both operands, 3 products, fp32 accumulate in TMEM), cell state in
