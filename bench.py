@@ -157,7 +157,7 @@ def workload_config(n):
                         "D=H=88, C=10, z=2, use_x_prev, adam-wn",
             "global_batch": CFG["B"] * n, "seq_len": CFG["L"], "parallelism": "dp%d" % n,
             "l2": "inputs drawn from a 176 MB resident roll pool (> 126 MB L2), fresh windows every step",
-            "noise": "in-kernel Philox", "graph": "one CUDA graph per step (fwd+bwd, all-reduce, Adam-WN)"}
+            "noise": "in-kernel Philox", "graph": "one CUDA graph per step (fwd+bwd, Adam-WN scheduled inside at N=1; all-reduce then Adam-WN at N>1), programmatic dependent launches on the critical path"}
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -310,20 +310,28 @@ def main():
     bytes_tc = (D + 4 * G) * B * L                              # read uint8 roll rows, write fp32 projection
     kern = {
         "clv_lstm_bwd_fused": {"ms": t_bwd, "bytes": bytes_bwd, "GBps": bytes_bwd / t_bwd / 1e6,
-                               "launches_per_step": 2, "bound": "hbm (latency/FFMA-issue bound at this B)"},
+                               "launches_per_step": 2, "bound": "hbm (latency bound at B=200, FFMA-issue bound at large B)"},
         "clv_lstm_fwd_fused": {"ms": t_fwd, "bytes": bytes_fwd, "GBps": bytes_fwd / t_fwd / 1e6,
-                               "launches_per_step": 2, "bound": "hbm (latency/FFMA-issue bound at this B)"},
+                               "launches_per_step": 2, "bound": "hbm (latency bound at B=200, FFMA-issue bound at large B)"},
         "clv_inproj_tc (tcgen05)": {"ms": t_tc, "bytes": bytes_tc, "GBps": bytes_tc / t_tc / 1e6,
                                     "launches_per_step": 2, "bound": "hbm"},
     }
     dom = "clv_lstm_bwd_fused" if t_bwd >= t_fwd else "clv_lstm_fwd_fused"
+    # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
+    # (profiles/ncu_full_step_kernels_r1.md, B=200 L=16; profiles/ncu_full_large_batch_B16384_L32_r1.md)
+    ncu_traffic = {(200, 16): {"clv_lstm_bwd_fused": 7.01e6, "clv_lstm_fwd_fused": 4.74e6},
+                   (16384, 32): {"clv_lstm_bwd_fused": 1.845e9}}
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["GBps"], "peak": hbm_peak,
-                "unit": "GB/s", "frac": kern[dom]["GBps"] / hbm_peak, "traffic": None,
+                "unit": "GB/s", "frac": kern[dom]["GBps"] / hbm_peak,
+                "traffic": ncu_traffic.get((B, L), {}).get(dom),
                 "peak_source": peak_src,
                 "share_of_step": 2 * kern[dom]["ms"] / ms_step,
-                "note": "B=200 gives 100 CTAs x 2 rows and 16 serial steps: the recurrent kernels are "
-                        "latency/FFMA-issue bound here, not HBM bound; see profiles/ for the large-batch "
-                        "numbers (tcgen05 projection: 76% of measured HBM peak at B=16384, L=64)"}
+                "note": "algorithmic bytes = streamed operands of one launch (DESIGN.md section 3); timed alone with "
+                        "L2 flushed, so share_of_step is an upper bound (in the step the operands are L2-resident "
+                        "and the prologue overlaps the predecessor via PDL). At B=200 the recurrence is 100 CTAs x 2 "
+                        "rows x 16 serial steps: latency bound, DRAM traffic below the algorithmic bytes because "
+                        "the whole working set sits in the 126 MB L2; the HBM-bound kernel of the path is the "
+                        "tcgen05 projection (75-80% of measured peak at B>=16384, see `kernels` and profiles/)"}
 
     # ---------------- sampler: generate_sample for songs_per_gpu songs, Philox noise in-kernel
     sampler = None

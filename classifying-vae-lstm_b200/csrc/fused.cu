@@ -145,25 +145,42 @@ keyenc_fwd_kernel(const uint8_t* __restrict__ roll, const int32_t* __restrict__ 
     const uint32_t v = win_s[i];
     cnt += (v & 0xffu ? 1 : 0) + (v & 0xff00u ? 1 : 0) + (v & 0xff0000u ? 1 : 0) + (v & 0xff000000u ? 1 : 0);
   }
-  cnt_s[tid + 1] = cnt;
-  if (tid == 0) cnt_s[0] = 0;
+  // exclusive prefix over the KT per-thread counts: shuffle scan per warp + the (KT/32) warp totals
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += y;
+  }
+  if ((tid & 31) == 31) cnt_s[tid >> 5] = incl;
   __syncthreads();
-  if (tid == 0)
-    for (int i = 1; i <= KT; ++i) cnt_s[i] += cnt_s[i - 1];
-  __syncthreads();
-  int pos = cnt_s[tid];
+  int pos = incl - cnt, total = 0;
+#pragma unroll
+  for (int w = 0; w < KT / 32; ++w) {
+    const int wt = cnt_s[w];
+    if (w < (tid >> 5)) pos += wt;
+    total += wt;
+  }
   for (int i = w0; i < w1; ++i) {
     const uint32_t v = win_s[i];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       if ((v >> (8 * q)) & 0xffu) list_s[pos++] = (uint16_t)(4 * i + q);
   }
-  const int nact = cnt_s[KT];
+  const int nact = total;
   __syncthreads();
-  // ---- hW = relu(b + sum of active kernel rows)
+  // ---- hW = relu(b + sum of active kernel rows): 8 independent L2 loads in flight per thread
   if (tid < D) {
     float a0 = __ldg(bhw + tid), a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int i = 0;
+    for (; i + 8 <= nact; i += 8) {
+      const float v0 = __ldg(Khw + (size_t)list_s[i] * D + tid), v1 = __ldg(Khw + (size_t)list_s[i + 1] * D + tid);
+      const float v2 = __ldg(Khw + (size_t)list_s[i + 2] * D + tid), v3 = __ldg(Khw + (size_t)list_s[i + 3] * D + tid);
+      const float v4 = __ldg(Khw + (size_t)list_s[i + 4] * D + tid), v5 = __ldg(Khw + (size_t)list_s[i + 5] * D + tid);
+      const float v6 = __ldg(Khw + (size_t)list_s[i + 6] * D + tid), v7 = __ldg(Khw + (size_t)list_s[i + 7] * D + tid);
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+      a0 += v4; a1 += v5; a2 += v6; a3 += v7;
+    }
     for (; i + 4 <= nact; i += 4) {
       a0 += __ldg(Khw + (size_t)list_s[i] * D + tid);
       a1 += __ldg(Khw + (size_t)list_s[i + 1] * D + tid);
@@ -343,8 +360,13 @@ keyenc_bwd_full_kernel(const uint8_t* __restrict__ roll, const int32_t* __restri
     const uint32_t v = win_s[i];
     cnt += (v & 0xffu ? 1 : 0) + (v & 0xff00u ? 1 : 0) + (v & 0xff0000u ? 1 : 0) + (v & 0xff000000u ? 1 : 0);
   }
-  cnt_s[tid + 1] = cnt;
-  if (tid == 0) cnt_s[0] = 0;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += y;
+  }
+  if ((tid & 31) == 31) cnt_s[tid >> 5] = incl;
   // ---- dhW = (dWargs @ Kwa^T) * [hW > 0];  bias gradients
   if (tid < D) {
     float a = 0.f;
@@ -356,23 +378,25 @@ keyenc_bwd_full_kernel(const uint8_t* __restrict__ roll, const int32_t* __restri
   }
   if (tid < NW) atomicAdd(gbwa + tid, dwa_s[tid]);
   __syncthreads();
-  if (tid == 0)
-    for (int i = 1; i <= KT; ++i) cnt_s[i] += cnt_s[i - 1];
   // ---- dK_Wa += hW^T (x) dWargs   (outer product of this sequence)
   for (int i = tid; i < D * NW; i += KT) {
     const int j = i / NW, o = i - j * NW;
     const float hv = hw_s[j];
     if (hv != 0.f) atomicAdd(gKwa + i, hv * dwa_s[o]);
   }
-  __syncthreads();
-  int pos = cnt_s[tid];
+  int pos = incl - cnt, nact = 0;
+#pragma unroll
+  for (int w = 0; w < KT / 32; ++w) {
+    const int wt = cnt_s[w];
+    if (w < (tid >> 5)) pos += wt;
+    nact += wt;
+  }
   for (int i = w0; i < w1; ++i) {
     const uint32_t v = win_s[i];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       if ((v >> (8 * q)) & 0xffu) list_s[pos++] = (uint16_t)(4 * i + q);
   }
-  const int nact = cnt_s[KT];
   __syncthreads();
   // ---- dK_hW[p, :] += dhW for every set key p of the window (sparse scatter, coalesced rows)
   if (tid < D) {
