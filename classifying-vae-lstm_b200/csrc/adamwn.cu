@@ -4,7 +4,7 @@
 // Every >=2-D tensor is updated in its (V, g) weight-norm reparameterisation, norms taken over
 // axis 0 (per output column, incl. each of the 4H LSTM gate columns); 1-D tensors get plain Keras
 // Adam (p -= lr_t * m / (sqrt(v) + eps)) [K2-recall (7)].
-// A block owns 8 adjacent columns of one matrix (32-byte sectors per row) and 32 row lanes.
+// A block owns 8 (short tensors) or 4 (tall tensors) adjacent columns of one matrix; see below.
 #include "common.cuh"
 
 namespace {
@@ -17,7 +17,7 @@ struct AdamPlan {
   int32_t NC;
 };
 
-constexpr int CT = 8, RL = 128, NTH = CT * RL;
+constexpr int NTH = 1024;
 
 // P2P = true: the gradient all-reduce is FUSED into the optimizer.  Every rank's [grads | losses]
 // buffer lives in symmetric (peer-mapped) memory; after a cross-GPU barrier each rank's kernel reads
@@ -39,6 +39,37 @@ __device__ __forceinline__ float load_grad(const float* __restrict__ G, const Pe
   return g;
 }
 
+// Block shapes: a block owns CT adjacent columns of one matrix and RL row lanes (CT * RL = NTH).
+//   short tensors (rows <= 128; every LSTM / head kernel): CT = 8, RL = 128, one row per thread;
+//   tall tensors (the 1408-row key-encoder kernel):        CT = 4, RL = 256, up to NRF rows per thread.
+// In both cases a thread's rows of W, grad, m, v stay in REGISTERS across the three phases of the
+// update (norms -> Adam on V -> rescale), so the tensor is read once and written once; taller
+// matrices than NRF * 256 rows fall back to three passes over memory.
+constexpr int NRF = 6;
+__host__ __device__ __forceinline__ int adam_ct(int rows) { return rows > 128 ? 4 : 8; }
+
+// sum over the row lanes of a block, per column: lanes of a warp that share a column first, then
+// the 32 warp partials through shared memory.  Result valid in threads with ry == 0 (tid < ct).
+template <int NV>
+__device__ __forceinline__ void col_reduce(float (&val)[NV], float (*red)[32][8], const int ct, const int tid) {
+  const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    for (int o = ct; o < 32; o <<= 1) val[i] += __shfl_xor_sync(0xffffffffu, val[i], o);
+    if (lane < ct) red[i][wid][lane] = val[i];
+  }
+  __syncthreads();
+  if (tid < ct) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < NTH / 32; ++w) a += red[i][w][tid];
+      val[i] = a;
+    }
+  }
+}
+
 template <bool P2P>
 __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* __restrict__ W,
                                                      const float* __restrict__ G,
@@ -53,18 +84,31 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
     for (int p = 0; p < ps.n; ++p) v += ps.peers[p][pl.P + threadIdx.x];
     ps.loss_out[threadIdx.x] = v;
   }
-  __shared__ float red[2][RL][CT];
-  __shared__ float col[4][CT];
+  __shared__ float red[2][32][8];
+  __shared__ float col[4][8];
+  __shared__ float lr_s;
   float* m = state;
   float* v = state + pl.P;
   float* vsc = state + 2 * pl.P;
   float* mg = vsc + pl.NC;
   float* vg = mg + pl.NC;
-  int* iter = reinterpret_cast<int*>(vg + pl.NC);
+  int* fct = reinterpret_cast<int*>(vg + pl.NC);          // [t the cached factor is for | factor]
+  int* iter = fct + 2;
   unsigned* done = reinterpret_cast<unsigned*>(iter + 1);
+  const int tid = threadIdx.x;
 
+  // lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t): the double-precision factor is computed once per step by
+  // the block that advances `iterations` (for the NEXT step) and only re-derived here if the cache
+  // is for another t (first step) -- fp64 pow on every thread was a measurable part of this kernel
   const int t = *iter + 1;
-  const float lr_t = (float)(lr * sqrt(1.0 - pow(b2d, (double)t)) / (1.0 - pow(b1d, (double)t)));
+  if (tid == 0) {
+    float f;
+    if (fct[0] == t) f = __int_as_float(fct[1]);
+    else f = (float)(sqrt(1.0 - pow(b2d, (double)t)) / (1.0 - pow(b1d, (double)t)));
+    lr_s = (float)lr * f;
+  }
+  __syncthreads();
+  const float lr_t = lr_s;
   const float b1 = (float)b1d, b2 = (float)b2d;
 
   // block_base: first plan block of this launch (a launch may cover a sub-range of the tensors)
@@ -76,7 +120,6 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
   const int lb = gb - pl.first_block[ti];
   const int64_t off = pl.off[ti];
   const int rows = pl.rows[ti], cols = pl.cols[ti];
-  const int tid = threadIdx.x;
 
   if (rows == 0 || !weightnorm) {  // plain Adam on a flat chunk
     const int64_t n = (rows == 0) ? cols : (int64_t)rows * cols;
@@ -90,31 +133,45 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
       W[off + i] -= lr_t * mt / (sqrtf(vt) + eps);
     }
   } else {
-    const int cx = tid & (CT - 1), ry = tid >> 3;
-    const int c = lb * CT + cx;
+    const int ct = adam_ct(rows), rl = NTH / ct;
+    const int cx = tid & (ct - 1), ry = tid / ct;
+    const int c = lb * ct + cx;
     const bool cv = c < cols;
     const int sc = pl.coloff[ti] + c;
     const float vs = cv ? vsc[sc] : 1.f;
-    // pass 1: ||V||^2 and <G, V> per column
-    float svv = 0.f, sgv = 0.f;
-    if (cv)
+    const bool in_regs = rows <= NRF * rl;
+    float Wr[NRF], Gr[NRF], Mr[NRF], Vr[NRF];
+    // phase 1: ||V||^2 and <G, V> per column
+    float s2[2] = {0.f, 0.f};
+    if (in_regs) {
+#pragma unroll
+      for (int u = 0; u < NRF; ++u) {
+        const int r = ry + u * rl;
+        Wr[u] = Gr[u] = Mr[u] = Vr[u] = 0.f;
+        if (cv && r < rows) {
+          const int64_t e = off + (int64_t)r * cols + c;
+          const float graw = load_grad<P2P>(G, ps, e);
+          if (P2P) ps.gsum[e] = graw;
+          Wr[u] = W[e] / vs; Gr[u] = graw * gscale; Mr[u] = m[e]; Vr[u] = v[e];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < NRF; ++u) { s2[0] = fmaf(Wr[u], Wr[u], s2[0]); s2[1] = fmaf(Gr[u], Wr[u], s2[1]); }
+    } else if (cv) {
 #pragma unroll 4
-      for (int r = ry; r < rows; r += RL) {
+      for (int r = ry; r < rows; r += rl) {
         const int64_t e = off + (int64_t)r * cols + c;
         const float graw = load_grad<P2P>(G, ps, e);
         if (P2P) ps.gsum[e] = graw;
         const float V = W[e] / vs, g = graw * gscale;
-        svv = fmaf(V, V, svv);
-        sgv = fmaf(g, V, sgv);
+        s2[0] = fmaf(V, V, s2[0]);
+        s2[1] = fmaf(g, V, s2[1]);
       }
-    red[0][ry][cx] = svv;
-    red[1][ry][cx] = sgv;
-    __syncthreads();
+    }
+    col_reduce(s2, red, ct, tid);
     if (ry == 0) {
-#pragma unroll
-      for (int i = 1; i < RL; ++i) { svv += red[0][i][cx]; sgv += red[1][i][cx]; }
-      const float V_norm = sqrtf(svv);
-      const float grad_g = sgv / V_norm;
+      const float V_norm = sqrtf(s2[0]);
+      const float grad_g = s2[1] / V_norm;
       const float g_param = vs * V_norm;
       float new_g = g_param;
       if (cv) {
@@ -129,16 +186,32 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
     }
     __syncthreads();
     const float gg_over_norm = col[0][cx];
-    // pass 2: Adam on V; new V parked in W.  Rows are processed in explicit batches of 4 (all loads,
-    // then all stores) because W/m/v may alias as far as the compiler knows: without batching every
-    // iteration would wait a full memory round trip behind the previous iteration's stores.
-    float snn = 0.f;
-    if (cv)
-      for (int r0 = ry; r0 < rows; r0 += 4 * RL) {
+    // phase 2: Adam on V
+    float s1[1] = {0.f};
+    if (in_regs) {
+#pragma unroll
+      for (int u = 0; u < NRF; ++u) {
+        const int r = ry + u * rl;
+        if (cv && r < rows) {
+          const int64_t e = off + (int64_t)r * cols + c;
+          const float gV = vs * (Gr[u] - gg_over_norm * Wr[u]);
+          const float mt = b1 * Mr[u] + (1.0f - b1) * gV;
+          const float vt = b2 * Vr[u] + (1.0f - b2) * gV * gV;
+          m[e] = mt;
+          v[e] = vt;
+          Wr[u] = Wr[u] - lr_t * mt / (sqrtf(vt) + eps);
+          s1[0] = fmaf(Wr[u], Wr[u], s1[0]);
+        }
+      }
+    } else if (cv) {
+      // new V parked in W.  Rows in explicit batches of 4 (all loads, then all stores) because
+      // W/m/v may alias as far as the compiler knows: without batching every iteration would wait a
+      // full memory round trip behind the previous iteration's stores.
+      for (int r0 = ry; r0 < rows; r0 += 4 * rl) {
         float Wv[4], Gv[4], Mv[4], Vv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int r = r0 + u * RL;
+          const int r = r0 + u * rl;
           if (r < rows) {
             const int64_t e = off + (int64_t)r * cols + c;
             Wv[u] = W[e]; Gv[u] = P2P ? ps.gsum[e] : G[e]; Mv[u] = m[e]; Vv[u] = v[e];
@@ -146,7 +219,7 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int r = r0 + u * RL;
+          const int r = r0 + u * rl;
           if (r < rows) {
             const int64_t e = off + (int64_t)r * cols + c;
             const float V = Wv[u] / vs, g = Gv[u] * gscale;
@@ -157,44 +230,55 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
             v[e] = vt;
             const float nV = V - lr_t * mt / (sqrtf(vt) + eps);
             W[e] = nV;
-            snn = fmaf(nV, nV, snn);
+            s1[0] = fmaf(nV, nV, s1[0]);
           }
         }
       }
-    red[0][ry][cx] = snn;
-    __syncthreads();
+    }
+    __syncthreads();   // red[] is reused
+    col_reduce(s1, red, ct, tid);
     if (ry == 0) {
-#pragma unroll
-      for (int i = 1; i < RL; ++i) snn += red[0][i][cx];
-      const float ns = col[1][cx] / sqrtf(snn);
+      const float ns = col[1][cx] / sqrtf(s1[0]);
       if (cv) vsc[sc] = ns;
       col[2][cx] = ns;
     }
     __syncthreads();
-    // pass 3: W = V_scaler' * V'  (same batching)
+    // phase 3: W = V_scaler' * V'
     const float ns = col[2][cx];
-    if (cv)
-      for (int r0 = ry; r0 < rows; r0 += 4 * RL) {
+    if (in_regs) {
+#pragma unroll
+      for (int u = 0; u < NRF; ++u) {
+        const int r = ry + u * rl;
+        if (cv && r < rows) W[off + (int64_t)r * cols + c] = Wr[u] * ns;
+      }
+    } else if (cv) {
+      for (int r0 = ry; r0 < rows; r0 += 4 * rl) {
         float Wv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int r = r0 + u * RL;
+          const int r = r0 + u * rl;
           if (r < rows) Wv[u] = W[off + (int64_t)r * cols + c];
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int r = r0 + u * RL;
+          const int r = r0 + u * rl;
           if (r < rows) W[off + (int64_t)r * cols + c] = Wv[u] * ns;
         }
       }
+    }
   }
-  // last block to finish advances `iterations` (only the final launch of a step is told to)
+  // last block to finish advances `iterations` (only the final launch of a step is told to) and
+  // caches the bias-correction factor of the next step
   if (!advance) return;
   __threadfence();
   __syncthreads();
   if (tid == 0) {
     const unsigned d = atomicAdd(done, 1u);
     if (d == gridDim.x - 1) {
+      const float f = (float)(sqrt(1.0 - pow(b2d, (double)(t + 1))) / (1.0 - pow(b1d, (double)(t + 1))));
+      fct[1] = __float_as_int(f);
+      fct[0] = t + 1;
+      __threadfence();
       *iter = t;
       *done = 0u;
     }
@@ -202,7 +286,7 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
 }
 
 __global__ void adamwn_init_kernel(float* state, int64_t P, int NC) {
-  const int64_t n = 2 * P + 3 * (int64_t)NC + 2;
+  const int64_t n = 2 * P + 3 * (int64_t)NC + 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     state[i] = (i >= 2 * P && i < 2 * P + NC) ? 1.0f : 0.0f;
@@ -217,7 +301,7 @@ int make_plan(const clv_cfg* cfg, AdamPlan* pl, int weightnorm) {
     pl->coloff[i] = nc;
     pl->first_block[i] = nb;
     if (pl->rows[i] > 0) nc += pl->cols[i];
-    if (pl->rows[i] > 0 && weightnorm) nb += (pl->cols[i] + CT - 1) / CT;
+    if (pl->rows[i] > 0 && weightnorm) nb += (pl->cols[i] + adam_ct(pl->rows[i]) - 1) / adam_ct(pl->rows[i]);
     else {
       const int64_t n = pl->rows[i] > 0 ? (int64_t)pl->rows[i] * pl->cols[i] : pl->cols[i];
       nb += (int)((n + NTH - 1) / NTH);
@@ -234,7 +318,7 @@ extern "C" int64_t clv_adamwn_state_floats(const clv_cfg* cfg) {
   AdamPlan pl;
   int rc = make_plan(cfg, &pl, 1);
   if (rc != CLV_OK) return rc;
-  return 2 * pl.P + 3 * (int64_t)pl.NC + 2;
+  return 2 * pl.P + 3 * (int64_t)pl.NC + 4;
 }
 
 extern "C" int clv_adamwn_init(const clv_cfg* cfg, float* state, void* stream) {

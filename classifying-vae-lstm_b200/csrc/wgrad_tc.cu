@@ -26,16 +26,27 @@ extern "C" int clv_debug_wprof(long long* out, int reset) {
 
 namespace {
 
-constexpr int WM = 128, WN = 176, KS = 32;          // UMMA M, N (one half of 4H) and rows per stage
+constexpr int WM = 128, KS = 32;                    // UMMA M and rows per slab (= K of one slab)
+// the 4H = 352 gate columns are split over two CTAs as 192 + 160 (both multiples of 32: whole
+// epilogue chunks and whole groups of four 8-column chunks for the skewed converter below)
+constexpr int WN0 = 192, WN1 = 160, WNMAX = 192, GFULL = 352;
 constexpr int LBO = 128;                            // between the k-groups (8 rows) of a core column
 constexpr int SBO = (KS / 8) * 128;                 // between mn-groups (8 columns)
 constexpr int A_TILE = (WM / 8) * SBO;              // 8 192 B
-constexpr int B_TILE = (WN / 8) * SBO;              // 11 264 B
-constexpr int STAGE = 3 * A_TILE + 2 * B_TILE;      // X | Hhi | Hmid | Dhi | Dmid = 47 104 B
-constexpr int NSTAGE = 4;
-constexpr int NPROD = 8;                            // producer warps
-constexpr int NBATCH = 6;                           // column-group tasks a producer warp keeps in flight
-constexpr int WTHREADS = (NPROD + 1) * 32;
+constexpr int B_TILE = (WNMAX / 8) * SBO;           // 12 288 B
+constexpr int STAGE = 3 * A_TILE + 2 * B_TILE;      // X | Hhi | Hmid | Dhi | Dmid = 49 152 B
+constexpr int NSTAGE = 2;
+// fp32 staging ring filled by the bulk-copy (TMA) engine with TWO copies per 32-row slab: the dA rows
+// (full 352-column rows are contiguous: 45 056 B, of which this CTA converts its column range) and
+// the 32 h_{t-1} rows (11 264 B).  History: lane-per-row global loads cost one L1 sector request per
+// lane (3.8 k cycles per slab); one bulk copy per row segment cost ~65 cycles of issue EACH (4.1 k
+// cycles per slab, measured with clock64); two large copies per slab are issue-free.
+constexpr int RAW_D = KS * GFULL * 4;               // 45 056 B
+constexpr int RAW_H = KS * 88 * 4;                  // 11 264 B
+constexpr int RAW_STAGE = RAW_D + RAW_H;            // 56 320 B
+constexpr int NRAW = 2;
+constexpr int NPROD = 8;                            // converter warps
+constexpr int WTHREADS = (NPROD + 2) * 32;          // + MMA warp + bulk-copy warp
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -53,13 +64,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   }
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 // MN-major, no swizzle, version 1: element (mn, k) at (mn/8)*SBO + (k/8)*LBO + (k%8)*16 + (mn%8)*2
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((LBO >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((SBO >> 4) & 0x3FFF) << 32) | (1ULL << 46);
 }
 // kind::f16, D=f32, A=B=bf16, A and B MN-major (bits 15, 16)
-__device__ __forceinline__ constexpr uint32_t umma_idesc_mn(int M, int N) {
+__device__ __forceinline__ uint32_t umma_idesc_mn(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
@@ -98,16 +117,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// fp32 x8 -> bf16 hi (round-to-nearest) and mid (residual), packed as 2 x 16 bytes
+// fp32 x8 -> bf16 hi (round-to-nearest) and mid (residual), packed as 2 x 16 bytes; packed
+// two-at-a-time conversions (F2FP) instead of scalar F2F, which runs at a quarter of the rate
 __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& mid) {
   uint32_t h[4], m[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    const __nv_bfloat16 m0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-    const __nv_bfloat16 m1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    m[i] = (uint32_t)__bfloat16_as_ushort(m0) | ((uint32_t)__bfloat16_as_ushort(m1) << 16);
+    const __nv_bfloat162 hp = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hp);
+    const float r0 = v[2 * i] - __uint_as_float(hb << 16);
+    const float r1 = v[2 * i + 1] - __uint_as_float(hb & 0xffff0000u);
+    const __nv_bfloat162 mp = __floats2bfloat162_rn(r0, r1);
+    h[i] = hb;
+    m[i] = *reinterpret_cast<const uint32_t*>(&mp);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   mid = make_uint4(m[0], m[1], m[2], m[3]);
@@ -117,23 +139,31 @@ struct WgArgs {
   const float* dA; const uint8_t* roll; const int32_t* off; const float* h; const float* Zs;
   float* gKx; float* gU; float* gKz;
   int64_t R; int L, shift, D, H, Z, G;
-  int stages, stages_per_cta;
+  int stages, stages_per_cta, nsplit;
 };
 
 __global__ void __launch_bounds__(WTHREADS, 1) lstm_wgrad_tc_kernel(const WgArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bars[2 * NSTAGE + 1];   // full[4], empty[4], done
+  __shared__ __align__(8) uint64_t bars[2 * NSTAGE + 2 * NRAW + 1];   // full, empty, raw_full, raw_empty, done
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int half = blockIdx.y, n0 = half * WN;
+  // column range of this CTA: 192|160 (2-way) or 96|96|96|64 (4-way, small M: the epilogue's red.add
+  // rate is ~1.6 elements/clk per SM whatever the CTA count, so narrower tiles on more SMs finish sooner)
+  const int ny = blockIdx.y;
+  const int n0 = (a.nsplit == 2) ? ny * WN0 : ny * 96;
+  const int wn = (a.nsplit == 2) ? (ny ? WN1 : WN0) : (ny == 3 ? 64 : 96);
   WPROF(0, tid == 0);
   const uint32_t bar0 = smem_u32(&bars[0]);
   auto FULL = [&](int s) { return bar0 + 8u * s; };
   auto EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
-  const uint32_t DONE = bar0 + 8u * (2 * NSTAGE);
+  auto RAW_FULL = [&](int s) { return bar0 + 8u * (2 * NSTAGE + s); };
+  auto RAW_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + NRAW + s); };
+  const uint32_t DONE = bar0 + 8u * (2 * NSTAGE + 2 * NRAW);
+  uint8_t* raw = smem + NSTAGE * STAGE;
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(FULL(s), NPROD); mbar_init(EMPTY(s), 1); }
+    for (int s = 0; s < NRAW; ++s) { mbar_init(RAW_FULL(s), 1); mbar_init(RAW_EMPTY(s), NPROD); }
     mbar_init(DONE, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -161,13 +191,39 @@ __global__ void __launch_bounds__(WTHREADS, 1) lstm_wgrad_tc_kernel(const WgArgs
   WPROF(1, tid == 0);
   const int st0 = blockIdx.x * a.stages_per_cta;
   const int nst = max(0, min(a.stages_per_cta, a.stages - st0));
-  const int ngx = a.D / 8, ngh = a.H / 8, ngz = a.Zs ? 1 : 0, ngb = WN / 8;   // 8-column group tasks
-  const int ntask = ngb + ngx + ngh + ngz;
+  const int ngx = a.D / 8, ngh = a.H / 8, ngz = a.Zs ? 1 : 0, ngb = wn / 8;   // 8-column chunks
 
-  if (warp < NPROD) {
-    // ================= producers: lane = row of the stage, task = one 8-wide column group
+  if (warp == NPROD + 1) {
+    // ================= bulk-copy warp (one thread): two copies per slab
+    if (lane == 0) {
+      for (int it = 0; it < nst; ++it) {
+        const int rs = it % NRAW, rph = (it / NRAW) & 1;
+        const int64_t r0 = ((int64_t)(st0 + it)) * KS;
+        const int nv = (int)min((int64_t)KS, a.R - r0);            // valid rows of the slab (>= 1)
+        // h_{t-1} of row r is h row r-1: slab rows r0-1 .. r0+nv-2 land in slots 0 .. nv-1 (the very
+        // first slab has no row -1: slots 1.. are filled, slot 0 is a t == 0 row and ignored)
+        const int hskip = (r0 == 0) ? 1 : 0;
+        const uint32_t dbytes = (uint32_t)nv * GFULL * 4, hbytes = (uint32_t)(nv - hskip) * a.H * 4;
+        mbar_wait(RAW_EMPTY(rs), rph ^ 1);
+        mbar_expect_tx(RAW_FULL(rs), dbytes + hbytes);
+        uint8_t* rb = raw + rs * RAW_STAGE;
+        bulk_g2s(smem_u32(rb), a.dA + r0 * a.G, dbytes, RAW_FULL(rs));
+        if (hbytes)
+          bulk_g2s(smem_u32(rb + RAW_D + hskip * a.H * 4), a.h + (r0 - 1 + hskip) * a.H, hbytes, RAW_FULL(rs));
+        WPROF(9 + it, it < 2);
+      }
+    }
+  } else if (warp < NPROD) {
+    // ================= converters: lane = row of the slab.  The staged rows are dense (pitch = 0 mod
+    // 128 B), so a plain lane-per-row read of one 8-column chunk would be an 8-way bank conflict;
+    // instead the 8 lanes of a quarter-warp work on a GROUP of 4 chunks in 4 rotations: lane i takes
+    // chunk ((i >> 1) + rotation) & 3 and reads its two 16-byte halves in the order given by i & 1,
+    // which spreads both the reads and the MN-major 16-byte stores over all 32 banks.
+    const int i8 = lane & 7;
+    const int nsub_d = ngb, nsub_h = 4 * ((ngh + 3) / 4);    // sub-steps: 4 rotations per group of 4
     for (int it = 0; it < nst; ++it) {
       const int s = it % NSTAGE, ph = (it / NSTAGE) & 1;
+      const int rs = it % NRAW, rph = (it / NRAW) & 1;
       const int64_t r = ((int64_t)(st0 + it)) * KS + lane;
       const bool rv = r < a.R;
       int64_t xrow = 0; bool tpos = false;
@@ -176,76 +232,86 @@ __global__ void __launch_bounds__(WTHREADS, 1) lstm_wgrad_tc_kernel(const WgArgs
         xrow = (int64_t)__ldg(a.off + b) + a.shift + t;
         tpos = t > 0;
       }
+      // the small operands that still come through the LSU: piano-roll keys (88-byte rows are not a
+      // bulk-copy size) and the latent columns; issued before the waits
+      const int xt0 = warp, xt1 = warp + NPROD;     // roll chunks of this warp (ngx <= 16 = 2 NPROD)
+      uint2 q0 = make_uint2(0u, 0u), q1 = make_uint2(0u, 0u);
+      if (rv && xt0 < ngx) q0 = __ldg(reinterpret_cast<const uint2*>(a.roll + xrow * a.D + 8 * xt0));
+      if (rv && xt1 < ngx) q1 = __ldg(reinterpret_cast<const uint2*>(a.roll + xrow * a.D + 8 * xt1));
+      float zv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) zv[j] = 0.f;
+      if (ngz && warp == NPROD - 1 && rv) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < a.Z) zv[j] = __ldg(a.Zs + r * a.Z + j);
+      }
+      mbar_wait(RAW_FULL(rs), rph);
+      WPROF(11 + it, tid == 0 && it < 3);
       mbar_wait(EMPTY(s), ph ^ 1);
       uint8_t* sb = smem + s * STAGE + (lane >> 3) * LBO + (lane & 7) * 16;   // this row's slot
-      // tasks of this warp in batches of NBATCH (all of a stage's for the built shapes): issue every
-      // global load of the batch, then convert and store -- one memory round trip per stage
-      for (int task0 = warp; task0 < ntask; task0 += NBATCH * NPROD) {
-        float v[NBATCH][8];
-        uint2 q[NBATCH];
+      const uint8_t* rd = raw + rs * RAW_STAGE + lane * (GFULL * 4) + n0 * 4;
+      const uint8_t* rh = raw + rs * RAW_STAGE + RAW_D + lane * (88 * 4);
+      // at most 36 sub-steps per slab = 5 per warp; fully unrolled so the five independent
+      // load -> convert -> store chains overlap
 #pragma unroll
-        for (int u = 0; u < NBATCH; ++u) {
-          const int task = task0 + u * NPROD;
-          q[u] = make_uint2(0u, 0u);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
-          if (task >= ntask || !rv) continue;
-          if (task < ngb) {                                   // dA columns n0 + 8*task ..
-            const float4* p = reinterpret_cast<const float4*>(a.dA + r * a.G + n0 + 8 * task);
-            const float4 x = __ldg(p), y = __ldg(p + 1);
-            v[u][0] = x.x; v[u][1] = x.y; v[u][2] = x.z; v[u][3] = x.w;
-            v[u][4] = y.x; v[u][5] = y.y; v[u][6] = y.z; v[u][7] = y.w;
-          } else if (task < ngb + ngx) {                      // piano-roll keys (exact in bf16)
-            q[u] = __ldg(reinterpret_cast<const uint2*>(a.roll + xrow * a.D + 8 * (task - ngb)));
-          } else {                                            // h_{t-1} units, or the Z columns
-            const int g = task - ngb - ngx;
-            if (g < ngh) {
-              if (tpos) {
-                const float4* p = reinterpret_cast<const float4*>(a.h + (r - 1) * a.H + 8 * g);
-                const float4 x = __ldg(p), y = __ldg(p + 1);
-                v[u][0] = x.x; v[u][1] = x.y; v[u][2] = x.z; v[u][3] = x.w;
-                v[u][4] = y.x; v[u][5] = y.y; v[u][6] = y.z; v[u][7] = y.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (j < a.Z) v[u][j] = __ldg(a.Zs + r * a.Z + j);
-            }
-          }
+      for (int k = 0; k < 5; ++k) {
+        const int u = warp + k * NPROD;
+        if (u >= nsub_d + nsub_h) break;
+        const bool isd = u < nsub_d;
+        const int uu = isd ? u : u - nsub_d;
+        const int c = 4 * (uu >> 2) + (((i8 >> 1) + uu) & 3);          // this lane's chunk
+        const bool cvalid = c < (isd ? ngb : ngh);
+        const bool live = cvalid && rv && (isd || tpos);
+        const uint8_t* src = (isd ? rd : rh) + c * 32;
+        const int first = i8 & 1;
+        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+        if (cvalid) {   // stale rows beyond R / t == 0 rows are read (conflict pattern) and discarded
+          p0 = *reinterpret_cast<const float4*>(src + first * 16);
+          p1 = *reinterpret_cast<const float4*>(src + (first ^ 1) * 16);
         }
+        const float4 x = first ? p1 : p0, y = first ? p0 : p1;
+        float v[8];
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+        if (!live) {
 #pragma unroll
-        for (int u = 0; u < NBATCH; ++u) {
-          const int task = task0 + u * NPROD;
-          if (task >= ntask) continue;
-          if (task < ngb) {
-            uint4 hi, mid;
-            split8(v[u], hi, mid);
-            *reinterpret_cast<uint4*>(sb + 3 * A_TILE + task * SBO) = hi;
-            *reinterpret_cast<uint4*>(sb + 3 * A_TILE + B_TILE + task * SBO) = mid;
-          } else if (task < ngb + ngx) {
-            const uint32_t x = q[u].x, y = q[u].y;
-            const uint32_t w0 = (x & 1u) * 0x3F80u + ((x >> 8) & 1u) * 0x3F800000u;
-            const uint32_t w1 = ((x >> 16) & 1u) * 0x3F80u + ((x >> 24) & 1u) * 0x3F800000u;
-            const uint32_t w2 = (y & 1u) * 0x3F80u + ((y >> 8) & 1u) * 0x3F800000u;
-            const uint32_t w3 = ((y >> 16) & 1u) * 0x3F80u + ((y >> 24) & 1u) * 0x3F800000u;
-            *reinterpret_cast<uint4*>(sb + (task - ngb) * SBO) = make_uint4(w0, w1, w2, w3);
-          } else {
-            const int g = task - ngb - ngx;
-            uint4 hi, mid;
-            split8(v[u], hi, mid);
-            *reinterpret_cast<uint4*>(sb + A_TILE + g * SBO) = hi;
-            *reinterpret_cast<uint4*>(sb + 2 * A_TILE + g * SBO) = mid;
-          }
+          for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+        if (cvalid) {
+          uint4 hi, mid;
+          split8(v, hi, mid);
+          uint8_t* dst = sb + (isd ? 3 * A_TILE : A_TILE) + c * SBO;
+          *reinterpret_cast<uint4*>(dst) = hi;
+          *reinterpret_cast<uint4*>(dst + (isd ? B_TILE : A_TILE)) = mid;
+        }
+      }
+      if (ngz && warp == NPROD - 1) {     // the Z columns: one more chunk of the H tile
+        uint4 hi, mid;
+        split8(zv, hi, mid);
+        *reinterpret_cast<uint4*>(sb + A_TILE + ngh * SBO) = hi;
+        *reinterpret_cast<uint4*>(sb + 2 * A_TILE + ngh * SBO) = mid;
+      }
+      // piano-roll keys (exact in bf16)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int task = u ? xt1 : xt0;
+        if (task < ngx) {
+          const uint32_t x = u ? q1.x : q0.x, y = u ? q1.y : q0.y;
+          const uint32_t w0 = (x & 1u) * 0x3F80u + ((x >> 8) & 1u) * 0x3F800000u;
+          const uint32_t w1 = ((x >> 16) & 1u) * 0x3F80u + ((x >> 24) & 1u) * 0x3F800000u;
+          const uint32_t w2 = (y & 1u) * 0x3F80u + ((y >> 8) & 1u) * 0x3F800000u;
+          const uint32_t w3 = ((y >> 16) & 1u) * 0x3F80u + ((y >> 24) & 1u) * 0x3F800000u;
+          *reinterpret_cast<uint4*>(sb + task * SBO) = make_uint4(w0, w1, w2, w3);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(FULL(s));
+      if (lane == 0) { mbar_arrive(FULL(s)); mbar_arrive(RAW_EMPTY(rs)); }
       WPROF(2 + it, tid == 0 && it < 4);
     }
-  } else if (lane == 0) {
+  } else if (warp == NPROD && lane == 0) {
     // ================= MMA thread
-    const uint32_t idesc = umma_idesc_mn(WM, WN);
+    const uint32_t idesc = umma_idesc_mn(WM, wn);
     const bool has_x = a.gKx != nullptr;
     for (int it = 0; it < nst; ++it) {
       const int s = it % NSTAGE, ph = (it / NSTAGE) & 1;
@@ -282,7 +348,7 @@ __global__ void __launch_bounds__(WTHREADS, 1) lstm_wgrad_tc_kernel(const WgArgs
     // (red.add.v2 was measured slower than scalar red here: the L2 cost is per element)
     const int quad = warp & 3;
     float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 33);   // operand stages are free now
-    constexpr int NCH = (WN + 31) / 32;
+    const int NCH = wn / 32;
     for (int tile = (a.gKx ? 0 : 1); tile < 2; ++tile) {
       const uint32_t tacc = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tile * 256);
       const int mvalid = (tile == 0) ? a.D : a.H + a.Z;      // rows of this accumulator that exist
@@ -291,7 +357,7 @@ __global__ void __launch_bounds__(WTHREADS, 1) lstm_wgrad_tc_kernel(const WgArgs
 #pragma unroll 1
       for (int ci = (warp >> 2); ci < NCH; ci += 2) {
         const int c0 = 32 * ((ci + (int)blockIdx.x) % NCH);
-        const int ncol = min(32, WN - c0);
+        const int ncol = 32;
         uint32_t r[32];
         if (ncol == 32) {
           tmem_ld32(tacc + c0, r);
@@ -343,7 +409,7 @@ extern "C" int clv_lstm_wgrad_tc(const float* dA, const uint8_t* roll, const int
     return CLV_E_UNSUPPORTED;
   if (R <= 0) return CLV_OK;
   static bool attr_set = false;
-  const int smem = NSTAGE * STAGE + 1024;
+  const int smem = NSTAGE * STAGE + NRAW * RAW_STAGE + 1024;
   if (!attr_set) {
     CLV_CUDA(cudaFuncSetAttribute(lstm_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
@@ -352,13 +418,15 @@ extern "C" int clv_lstm_wgrad_tc(const float* dA, const uint8_t* roll, const int
   a.dA = dA; a.roll = roll; a.off = win_off; a.h = h; a.Zs = Zs; a.gKx = gKx; a.gU = gU; a.gKz = gKz;
   a.R = R; a.L = L; a.shift = shift; a.D = gKx ? D : 0; a.H = H; a.Z = Zs ? Z : 0; a.G = 4 * H;
   a.stages = (int)((R + KS - 1) / KS);
-  int gx = a.stages / 4;                    // >= 4 stages (128 rows) per CTA to amortise the epilogue
-  const int cap = clv_num_sms() / 2;
+  // small problems: 4 column ranges x (>= 4 slabs per CTA); large ones: 2 column ranges x SMs/2 CTAs
+  a.nsplit = (a.stages <= 16 * (clv_num_sms() / 4)) ? 4 : 2;
+  int gx = a.stages / 4;
+  const int cap = clv_num_sms() / a.nsplit;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   a.stages_per_cta = (a.stages + gx - 1) / gx;
   gx = (a.stages + a.stages_per_cta - 1) / a.stages_per_cta;
-  lstm_wgrad_tc_kernel<<<dim3(gx, 2), WTHREADS, smem, (cudaStream_t)stream>>>(a);
+  lstm_wgrad_tc_kernel<<<dim3(gx, a.nsplit), WTHREADS, smem, (cudaStream_t)stream>>>(a);
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }

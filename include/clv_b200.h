@@ -246,7 +246,8 @@ int clv_keyenc_bwd_full(const uint8_t* roll, const int32_t* win_off, int32_t shi
 
 /* ---------------------------------------------------------------- K6: Adam + weight-norm -- */
 /* AdamWithWeightnorm.get_updates (utils/weightnorm.py:75-143,146-178) on the flat buffers.
- * state = [ m (P) | v (P) | V_scaler (ncols) | m_g (ncols) | v_g (ncols) | iterations (1) ], ncols =
+ * state = [ m (P) | v (P) | V_scaler (ncols) | m_g (ncols) | v_g (ncols) | cached bias-correction
+ * factor (2) | iterations (1) | retired-block counter (1) ], ncols =
  * total number of matrix columns; clv_adamwn_state_floats gives its size, clv_adamwn_init fills
  * V_scaler with ones and the rest with zeros.  grad_scale multiplies the gradient (1/N after a
  * sum-allreduce is already folded into B_global, so normally 1). */

@@ -22,3 +22,4 @@ for rep in range(3):
     L_.clv_debug_wprof(out, 0)
     v = list(out)
     print("cycles from start: setup %d | stage0 %d stage1 %d stage2 %d stage3 %d | mma done %d | epilogue done %d | all warps %d" % tuple(x - v[0] for x in v[1:9]))
+    print("   bulk copies of slab 0 / 1 issued at %d / %d; raw slab 0 / 1 / 2 landed at %d / %d / %d" % tuple(x - v[0] for x in v[9:14]))
