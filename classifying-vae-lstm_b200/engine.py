@@ -108,6 +108,7 @@ class Engine:
         self.labels = torch.zeros(B, dtype=torch.int32, device=self.dev)
         self._win_off_seq = (torch.arange(B, dtype=torch.int32, device=self.dev) * self.W).contiguous()
         self.win_off = self._win_off_seq.clone()
+        self._win_off_is_seq = True
         self.win_buf = torch.zeros(B * self.W * D, dtype=torch.uint8, device=self.dev)
         self.roll = self.win_buf                                       # or a resident dataset roll
         self.loss_host = torch.zeros(8, dtype=torch.float32).pin_memory()
@@ -137,6 +138,7 @@ class Engine:
         self.W, self.x_shift = frames, x_shift
         self._win_off_seq = (torch.arange(self.B, dtype=torch.int32, device=self.dev) * self.W).contiguous()
         self.win_off.copy_(self._win_off_seq)
+        self._win_off_is_seq = True
         self.win_buf = torch.zeros(self.B * self.W * self.D, dtype=torch.uint8, device=self.dev)
         self.roll = self.win_buf
         self._graphs.clear()
@@ -197,11 +199,14 @@ class Engine:
     def stage_windows(self, win_u8, labels_i32, non_blocking=True):
         """H2D of one batch given as materialised windows [B, W, D] uint8 + int32 labels."""
         self.roll = self.win_buf
-        self.win_off.copy_(self._win_off_seq)                          # window b = frames [b*W, (b+1)*W)
+        if not self._win_off_is_seq:                                   # window b = frames [b*W, (b+1)*W)
+            self.win_off.copy_(self._win_off_seq)
+            self._win_off_is_seq = True
         self.win_buf.copy_(win_u8.reshape(-1), non_blocking=non_blocking)
         self.labels.copy_(labels_i32, non_blocking=non_blocking)
 
     def stage_offsets(self, off_i32, labels_i32, non_blocking=True):
+        self._win_off_is_seq = False
         self.win_off.copy_(off_i32, non_blocking=non_blocking)
         self.labels.copy_(labels_i32, non_blocking=non_blocking)
 
