@@ -80,7 +80,7 @@ PROTOTYPES = {
     "clv_adamwn_state_floats": (_I64, [_CFG]),
     "clv_adamwn_init": (C.c_int, [_CFG, _P, _P]),
     "clv_adamwn_step": (C.c_int, [_CFG, _P, _P, _P, _D, _D, _D, _D, _D, _I32, _P]),
-    "clv_adamwn_step_range": (C.c_int, [_CFG, _P, _P, _P, _D, _D, _D, _D, _D, _I32, _I32, _I32, _P]),
+    "clv_adamwn_step_range": (C.c_int, [_CFG, _P, _P, _P, _D, _D, _D, _D, _D, _I32, _I32, _I32, _I32, _P]),
     "clv_adamwn_step_p2p": (C.c_int, [_CFG, _P, _P, _I32, _P, _P, _P, _D, _D, _D, _D, _I32, _P]),
     "clv_step_begin": (C.c_int, [_P, _P, _I32, _I32, _P]),
     "clv_workspace_bytes": (_I64, [_CFG]),

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
                                                      const double b1d, const double b2d,
                                                      const float eps, const float gscale,
                                                      const int weightnorm, const PeerSet ps,
-                                                     const int block_base, const int total_blocks) {
+                                                     const int block_base, const int advance) {
   pdl_wait();   // no-op unless launched as a programmatic dependent
   if (P2P && blockIdx.x == 0 && threadIdx.x < 8) {
     float v = 0.f;
@@ -267,14 +267,14 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
       }
     }
   }
-  // the block that retires LAST among all launches of this step (together they cover every plan block
-  // exactly once) advances `iterations` and caches the bias-correction factor of the next step; no
-  // launch has to know that it is the final one, so ranges may finish in any order on any stream
+  // last block to finish advances `iterations` (only the final launch of a step is told to) and
+  // caches the bias-correction factor of the next step
+  if (!advance) return;
   __threadfence();
   __syncthreads();
   if (tid == 0) {
     const unsigned d = atomicAdd(done, 1u);
-    if (d == (unsigned)total_blocks - 1u) {
+    if (d == gridDim.x - 1) {
       const float f = (float)(sqrt(1.0 - pow(b2d, (double)(t + 1))) / (1.0 - pow(b1d, (double)(t + 1))));
       fct[1] = __float_as_int(f);
       fct[0] = t + 1;
@@ -334,7 +334,7 @@ extern "C" int clv_adamwn_init(const clv_cfg* cfg, float* state, void* stream) {
 extern "C" int clv_adamwn_step_range(const clv_cfg* cfg, float* params, const float* grads, float* state,
                                      double lr, double beta_1, double beta_2, double epsilon,
                                      double grad_scale, int32_t weightnorm, int32_t t_first,
-                                     int32_t t_last, void* stream) {
+                                     int32_t t_last, int32_t advance, void* stream) {
   if (!cfg || !params || !grads || !state) return CLV_E_INVALID;
   if (t_first < 0 || t_last > CLV_N_TENSORS || t_first >= t_last) return CLV_E_INVALID;
   AdamPlan pl;
@@ -345,7 +345,7 @@ extern "C" int clv_adamwn_step_range(const clv_cfg* cfg, float* params, const fl
   if (nb <= 0) return CLV_OK;
   CLV_CUDA(clv_launch(adamwn_kernel<false>, nb, NTH, 0, (cudaStream_t)stream, pl, params, grads, state, lr,
                       beta_1, beta_2, (float)epsilon, (float)grad_scale, (int)weightnorm, ps,
-                      pl.first_block[t_first], pl.first_block[CLV_N_TENSORS]));
+                      pl.first_block[t_first], (int)advance));
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }
@@ -354,7 +354,7 @@ extern "C" int clv_adamwn_step(const clv_cfg* cfg, float* params, const float* g
                                double lr, double beta_1, double beta_2, double epsilon,
                                double grad_scale, int32_t weightnorm, void* stream) {
   return clv_adamwn_step_range(cfg, params, grads, state, lr, beta_1, beta_2, epsilon, grad_scale,
-                               weightnorm, 0, CLV_N_TENSORS, stream);
+                               weightnorm, 0, CLV_N_TENSORS, 1, stream);
 }
 
 extern "C" int clv_adamwn_step_p2p(const clv_cfg* cfg, float* params, const float* const* peer_grads,
@@ -368,8 +368,7 @@ extern "C" int clv_adamwn_step_p2p(const clv_cfg* cfg, float* params, const floa
   if (rc != CLV_OK) return rc;
   PeerSet ps = {peer_grads, n_peers, gsum, loss_out};
   adamwn_kernel<true><<<pl.first_block[CLV_N_TENSORS], NTH, 0, (cudaStream_t)stream>>>(
-      pl, params, nullptr, state, lr, beta_1, beta_2, (float)epsilon, 1.0f, weightnorm, ps, 0,
-      pl.first_block[CLV_N_TENSORS]);
+      pl, params, nullptr, state, lr, beta_1, beta_2, (float)epsilon, 1.0f, weightnorm, ps, 0, 1);
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }

@@ -232,9 +232,9 @@ struct Fork {
 int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uint8_t* roll,
               const int32_t* off, const int32_t* labels, float* eps_w, float* eps_z,
               uint64_t* ctr, float* ws, cudaStream_t st, const clv_adam_args* opt) {
-  auto adam = [&](int t0, int t1, cudaStream_t s_) {
+  auto adam = [&](int t0, int t1, int advance, cudaStream_t s_) {
     return clv_adamwn_step_range(c, const_cast<float*>(P), Gr, opt->state, opt->lr, opt->beta_1, opt->beta_2,
-                                 opt->epsilon, opt->grad_scale, opt->weightnorm, t0, t1, s_);
+                                 opt->epsilon, opt->grad_scale, opt->weightnorm, t0, t1, advance, s_);
   };
   int64_t po[CLV_N_TENSORS]; int32_t pr[CLV_N_TENSORS], pc[CLV_N_TENSORS];
   clv_param_layout(c, po, pr, pc);
@@ -397,7 +397,7 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
                // stay out of this range: the encoder BPTT below still reads their kernels
     TRY(fk.fork());
     TRY(fk.gather());
-    TRY(adam(R_DEC_K, CLV_N_TENSORS, fk.opt_stream()));
+    TRY(adam(R_DEC_K, CLV_N_TENSORS, 0, fk.opt_stream()));
   }
   if (fuse_heads)
     TRY_PDL(clv_lstm_bwd_heads(gates_e, Ue, c_e, nullptr, dAsum_e, Ke_w, C, dW_ext, 1, nullptr, 0, nullptr,
@@ -418,7 +418,7 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
     TRY_PDL(clv_keyenc_bwd_full(roll, off, sx, L, D, Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, gKhw,
                                 gbhw, gKwa, gbwa, B, C, c->w_log_var_prior, c->class_weight * sb,
                                 c->w_kl_weight * sb, st));
-    if (opt) TRY_PDL(adam(R_HW_K, R_ENC_K, st));   // key-encoder tensors: overlaps the encoder wgrads
+    if (opt) TRY_PDL(adam(R_HW_K, R_ENC_K, 0, st));   // key-encoder tensors: overlaps the encoder wgrads
   } else {
     TRY(clv_keyenc_bwd(Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, B, C, D,
                        c->w_log_var_prior, c->class_weight * sb, c->w_kl_weight * sb, st));
@@ -429,8 +429,7 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
     TRY(clv_colsum(dhW, D, B, D, gbhw, 1, fk.next()));
   }
   TRY(fk.join());
-  // (running this range on the optimizer stream next to the key-encoder range measured 2 us slower)
-  if (opt) TRY(adam(fused_ke ? R_ENC_K : R_HW_K, R_DEC_K, st));
+  if (opt) TRY(adam(fused_ke ? R_ENC_K : R_HW_K, R_DEC_K, 1, st));
   return CLV_OK;
 }
 
@@ -513,7 +512,7 @@ int vae_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uin
   TRY(clv_colsum(dh_w, Hc, B, Hc, gbhw, 1, st));
   if (opt)
     TRY(clv_adamwn_step_range(c, const_cast<float*>(P), Gr, opt->state, opt->lr, opt->beta_1, opt->beta_2,
-                              opt->epsilon, opt->grad_scale, opt->weightnorm, 0, CLV_N_TENSORS, st));
+                              opt->epsilon, opt->grad_scale, opt->weightnorm, 0, CLV_N_TENSORS, 1, st));
   return CLV_OK;
 }
 

@@ -257,12 +257,13 @@ int clv_adamwn_step(const clv_cfg* cfg, float* params, const float* grads, float
                     double beta_1, double beta_2, double epsilon, double grad_scale, int32_t weightnorm,
                     void* stream);
 /* The same update restricted to the tensors [t_first, t_last) of clv_param_layout's order (weight-norm
- * is per tensor column, so ranges are independent).  The launches of one step must together cover
- * every tensor exactly once; they may run on different streams and finish in any order: whichever
- * block retires last increments `iterations`. */
+ * is per tensor column, so ranges are independent).  `advance` != 0 on exactly one -- the last -- call
+ * of a step: it increments `iterations` when its last block retires; all ranges of a step must be
+ * issued before that call completes. */
 int clv_adamwn_step_range(const clv_cfg* cfg, float* params, const float* grads, float* state, double lr,
                           double beta_1, double beta_2, double epsilon, double grad_scale,
-                          int32_t weightnorm, int32_t t_first, int32_t t_last, void* stream);
+                          int32_t weightnorm, int32_t t_first, int32_t t_last, int32_t advance,
+                          void* stream);
 
 /* Data-parallel form: gradient all-reduce FUSED into the optimizer over NVLink peer memory.
  * peer_grads = device array of n_peers pointers to every rank's [grads(P) | losses(8)] buffer in
