@@ -132,9 +132,9 @@ struct TcArgs {
 //   warps 4-7  epilogue  : TMEM accumulator [stage] -> registers -> smem transpose -> 128-byte row stores
 //   warp  8    MMA       : bulk-TMA the weight image once, then 18 tcgen05.mma per tile, commits
 // mbarriers: a_full/a_empty per A stage, acc_full/acc_empty per TMEM accumulator.
-constexpr int TC_THREADS = 288;
+constexpr int TC_THREADS = 416;   // 4 producer + 4 epilogue warps, the MMA warp, 4 more epilogue warps
 constexpr int ACC_STRIDE = 256;                     // TMEM columns between the two accumulators
-constexpr int STAGE_BYTES = 4 * 32 * 36 * 4;        // epilogue transpose buffers (one per warp)
+constexpr int STAGE_BYTES = 8 * 32 * 36 * 4;   // one transpose buffer per epilogue warp        // epilogue transpose buffers (one per warp)
 
 __global__ void __launch_bounds__(TC_THREADS, 1) inproj_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) inproj_tc_kernel(const TcArgs a
       mbar_init(BAR(A_FULL + s), 4);      // one arrive per producer warp
       mbar_init(BAR(A_EMPTY + s), 1);     // tcgen05.commit
       mbar_init(BAR(ACC_FULL + s), 1);    // tcgen05.commit
-      mbar_init(BAR(ACC_EMPTY + s), 4);   // one arrive per epilogue warp
+      mbar_init(BAR(ACC_EMPTY + s), 8);   // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -202,12 +202,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) inproj_tc_kernel(const TcArgs a
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(A_FULL + s));
     }
-  } else if (warp < 8) {
-    // ================= epilogue: warp q owns TMEM lanes 32q..32q+31 (rows of the tile)
+  } else if (warp != 8) {
+    // ================= epilogue (warps 4-7 and 9-12): a warp may touch TMEM lanes 32(warp%4)..+31 (rows
+    // of the tile); the two warps of a quadrant take alternate 32-column chunks.  One epilogue warp
+    // per SM sub-partition was latency-bound in the addend form (0.38 vs 0.16 ms at 524 k rows).
     // TMEM -> registers (row per lane) -> smem transpose (stride 36: conflict-free 128-bit) ->
     // 128-bit stores, 8 lanes per 128-byte row segment, 4 rows per warp instruction.
-    const int q = warp - 4;
-    float* stage = stage_all + q * (32 * 36);
+    const int q = warp & 3, cpart = (warp > 8) ? 1 : 0;
+    float* stage = stage_all + (q + 4 * cpart) * (32 * 36);
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     for (int it = 0; it < ntile; ++it) {
       const int s = it & 1, ph = (it >> 1) & 1;
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) inproj_tc_kernel(const TcArgs a
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * ACC_STRIDE);
 #pragma unroll 1
-      for (int c0 = 0; c0 < TN; c0 += 32) {
+      for (int c0 = 32 * cpart; c0 < TN; c0 += 64) {
         const int ncol = min(32, TN - c0);          // 32,32,32,32,32,16
         uint32_t r[32];
         if (ncol == 32) {

@@ -95,3 +95,15 @@ lacc = torch.zeros(8, device=dev); dlg = torch.zeros(M, D, device=dev); dhx = to
 timeit("xhead fwd+bwd", lambda: check(L_.clv_xhead_fwd_bwd(ptr(hh), ptr(Kxh), ptr(bxh), ptr(roll), ptr(off), L, 1, ptr(lacc),
                                                         ptr(dlg), ptr(dhx), M, H, D, 1.0 / M, 1, st)))
 print("   2 x 88x88 FMA per row: %.2f GFMA -> at 36 TFMA/s: %.1f us" % (M * 2 * H * D / 1e9, M * 2 * H * D / 36e6))
+
+# ---- Adam-WN per tensor range (the scheduled optimizer's three launches) and whole.  The partial
+#      ranges do not advance `iterations`, so they re-derive the fp64 bias correction on every launch
+#      here (in the step it is cached by the advancing launch): their numbers are upper bounds.
+from clvae_b200.engine import Engine
+eng = Engine("vrnn", 200, L=16, D=88, H=88, Z=2, n_classes=10, use_x_prev=True, use_graph=False)
+cfgA = eng.cfg()
+gr = torch.randn_like(eng.grads) * 1e-3
+for name, t0, t1 in [("adam-wn [key encoder] 0..4", 0, 4), ("adam-wn [enc LSTM | Z heads] 4..11", 4, 11),
+                     ("adam-wn [decoder | X head] 11..16", 11, 16), ("adam-wn all 0..16", 0, 16)]:
+    timeit(name, lambda: check(L_.clv_adamwn_step_range(C.byref(cfgA), ptr(eng.params), ptr(gr), ptr(eng.opt_state),
+                                                        1e-3, 0.9, 0.999, 1e-8, 1.0, 1, t0, t1, 1 if t1 == 16 else 0, st)))
