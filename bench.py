@@ -254,9 +254,16 @@ def main():
     value = B * world / (ms_step / 1e3)
 
     # ---------------- end to end: pinned host windows -> train_on_batch -> host loss scalars
-    win_host = [torch.from_numpy(np.ascontiguousarray(
-        (rng.random((B, L + 1, D)) < 0.05).astype(np.uint8))).pin_memory() for _ in range(8)]
-    lab_host = [torch.from_numpy(rng.integers(0, Cc, B).astype(np.int32)).pin_memory() for _ in range(8)]
+    # 8 host batches in pinned memory, each as ONE buffer [windows uint8 | labels int32] (the layout
+    # the public call stages with a single H2D copy; separate tensors work too, with two copies)
+    win_host, lab_host = [], []
+    nw = B * (L + 1) * D
+    for _ in range(8):
+        buf = torch.empty(nw + 4 * B, dtype=torch.uint8).pin_memory()
+        buf[:nw] = torch.from_numpy((rng.random(nw) < 0.05).astype(np.uint8))
+        lab = buf[nw:].view(torch.int32) if nw % 4 == 0 else torch.empty(B, dtype=torch.int32).pin_memory()
+        lab.copy_(torch.from_numpy(rng.integers(0, Cc, B).astype(np.int32)))
+        win_host.append(buf[:nw].view(B, L + 1, D)); lab_host.append(lab)
     for i in range(Wm):
         model.train_on_batch_windows(win_host[i % 8], lab_host[i % 8])
     barrier()

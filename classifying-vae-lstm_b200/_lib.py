@@ -80,7 +80,7 @@ PROTOTYPES = {
     "clv_adamwn_state_floats": (_I64, [_CFG]),
     "clv_adamwn_init": (C.c_int, [_CFG, _P, _P]),
     "clv_adamwn_step": (C.c_int, [_CFG, _P, _P, _P, _D, _D, _D, _D, _D, _I32, _P]),
-    "clv_adamwn_step_range": (C.c_int, [_CFG, _P, _P, _P, _D, _D, _D, _D, _D, _I32, _I32, _I32, _I32, _P]),
+    "clv_adamwn_step_range": (C.c_int, [_CFG, _P, _P, _P, _D, _D, _D, _D, _D, _I32, _I32, _I32, _I32, _P, _P]),
     "clv_adamwn_step_p2p": (C.c_int, [_CFG, _P, _P, _I32, _P, _P, _P, _D, _D, _D, _D, _I32, _P]),
     "clv_step_begin": (C.c_int, [_P, _P, _I32, _I32, _P]),
     "clv_workspace_bytes": (_I64, [_CFG]),
@@ -96,7 +96,8 @@ PROTOTYPES = {
 class clv_adam_args(C.Structure):
     """include/clv_b200.h: clv_adam_args (optimizer settings of clv_train_step_opt)."""
     _fields_ = [("state", C.c_void_p), ("lr", C.c_double), ("beta_1", C.c_double), ("beta_2", C.c_double),
-                ("epsilon", C.c_double), ("grad_scale", C.c_double), ("weightnorm", C.c_int32)]
+                ("epsilon", C.c_double), ("grad_scale", C.c_double), ("weightnorm", C.c_int32),
+                ("loss_mirror", C.c_void_p)]
 
 
 _lib = None

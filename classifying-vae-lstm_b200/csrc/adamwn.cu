@@ -77,13 +77,18 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
                                                      const double b1d, const double b2d,
                                                      const float eps, const float gscale,
                                                      const int weightnorm, const PeerSet ps,
-                                                     const int block_base, const int advance) {
+                                                     const int block_base, const int advance,
+                                                     float* __restrict__ loss_mirror) {
   pdl_wait();   // no-op unless launched as a programmatic dependent
   if (P2P && blockIdx.x == 0 && threadIdx.x < 8) {
     float v = 0.f;
     for (int p = 0; p < ps.n; ++p) v += ps.peers[p][pl.P + threadIdx.x];
     ps.loss_out[threadIdx.x] = v;
   }
+  // the advancing (last) launch of a step also mirrors the 8 loss scalars that follow the gradients
+  // to `loss_mirror` (host-mapped pinned memory: the caller then needs a stream sync, not a D2H copy)
+  if (!P2P && loss_mirror && advance && blockIdx.x == 0 && threadIdx.x < 8)
+    loss_mirror[threadIdx.x] = G[pl.P + threadIdx.x];
   __shared__ float red[2][32][8];
   __shared__ float col[4][8];
   __shared__ float lr_s;
@@ -334,7 +339,7 @@ extern "C" int clv_adamwn_init(const clv_cfg* cfg, float* state, void* stream) {
 extern "C" int clv_adamwn_step_range(const clv_cfg* cfg, float* params, const float* grads, float* state,
                                      double lr, double beta_1, double beta_2, double epsilon,
                                      double grad_scale, int32_t weightnorm, int32_t t_first,
-                                     int32_t t_last, int32_t advance, void* stream) {
+                                     int32_t t_last, int32_t advance, float* loss_mirror, void* stream) {
   if (!cfg || !params || !grads || !state) return CLV_E_INVALID;
   if (t_first < 0 || t_last > CLV_N_TENSORS || t_first >= t_last) return CLV_E_INVALID;
   AdamPlan pl;
@@ -345,7 +350,7 @@ extern "C" int clv_adamwn_step_range(const clv_cfg* cfg, float* params, const fl
   if (nb <= 0) return CLV_OK;
   CLV_CUDA(clv_launch(adamwn_kernel<false>, nb, NTH, 0, (cudaStream_t)stream, pl, params, grads, state, lr,
                       beta_1, beta_2, (float)epsilon, (float)grad_scale, (int)weightnorm, ps,
-                      pl.first_block[t_first], (int)advance));
+                      pl.first_block[t_first], (int)advance, loss_mirror));
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }
@@ -354,7 +359,7 @@ extern "C" int clv_adamwn_step(const clv_cfg* cfg, float* params, const float* g
                                double lr, double beta_1, double beta_2, double epsilon,
                                double grad_scale, int32_t weightnorm, void* stream) {
   return clv_adamwn_step_range(cfg, params, grads, state, lr, beta_1, beta_2, epsilon, grad_scale,
-                               weightnorm, 0, CLV_N_TENSORS, 1, stream);
+                               weightnorm, 0, CLV_N_TENSORS, 1, nullptr, stream);
 }
 
 extern "C" int clv_adamwn_step_p2p(const clv_cfg* cfg, float* params, const float* const* peer_grads,
@@ -368,7 +373,7 @@ extern "C" int clv_adamwn_step_p2p(const clv_cfg* cfg, float* params, const floa
   if (rc != CLV_OK) return rc;
   PeerSet ps = {peer_grads, n_peers, gsum, loss_out};
   adamwn_kernel<true><<<pl.first_block[CLV_N_TENSORS], NTH, 0, (cudaStream_t)stream>>>(
-      pl, params, nullptr, state, lr, beta_1, beta_2, (float)epsilon, 1.0f, weightnorm, ps, 0, 1);
+      pl, params, nullptr, state, lr, beta_1, beta_2, (float)epsilon, 1.0f, weightnorm, ps, 0, 1, nullptr);
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }

@@ -234,7 +234,8 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
               uint64_t* ctr, float* ws, cudaStream_t st, const clv_adam_args* opt) {
   auto adam = [&](int t0, int t1, int advance, cudaStream_t s_) {
     return clv_adamwn_step_range(c, const_cast<float*>(P), Gr, opt->state, opt->lr, opt->beta_1, opt->beta_2,
-                                 opt->epsilon, opt->grad_scale, opt->weightnorm, t0, t1, advance, s_);
+                                 opt->epsilon, opt->grad_scale, opt->weightnorm, t0, t1, advance,
+                                 advance ? opt->loss_mirror : nullptr, s_);
   };
   int64_t po[CLV_N_TENSORS]; int32_t pr[CLV_N_TENSORS], pc[CLV_N_TENSORS];
   clv_param_layout(c, po, pr, pc);
@@ -512,7 +513,8 @@ int vae_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uin
   TRY(clv_colsum(dh_w, Hc, B, Hc, gbhw, 1, st));
   if (opt)
     TRY(clv_adamwn_step_range(c, const_cast<float*>(P), Gr, opt->state, opt->lr, opt->beta_1, opt->beta_2,
-                              opt->epsilon, opt->grad_scale, opt->weightnorm, 0, CLV_N_TENSORS, 1, st));
+                              opt->epsilon, opt->grad_scale, opt->weightnorm, 0, CLV_N_TENSORS, 1,
+                              opt->loss_mirror, st));
   return CLV_OK;
 }
 

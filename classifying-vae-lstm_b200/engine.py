@@ -105,15 +105,25 @@ class Engine:
         self.eps_w = torch.zeros(B * (self.C - 1), **f32)
         self.eps_z = torch.zeros(B * self.L * Z, **f32)
         self.rng_ctr = torch.zeros(1, dtype=torch.int64, device=self.dev)
-        self.labels = torch.zeros(B, dtype=torch.int32, device=self.dev)
         self._win_off_seq = (torch.arange(B, dtype=torch.int32, device=self.dev) * self.W).contiguous()
         self.win_off = self._win_off_seq.clone()
         self._win_off_is_seq = True
-        self.win_buf = torch.zeros(B * self.W * D, dtype=torch.uint8, device=self.dev)
+        self._graphs = {}
+        self._alloc_window_staging()
         self.roll = self.win_buf                                       # or a resident dataset roll
         self.loss_host = torch.zeros(8, dtype=torch.float32).pin_memory()
-        self._graphs = {}
+        self._loss_mirrored = False      # loss_host already holds the last step's scalars
         self.launches_per_step = 0
+
+    def _alloc_window_staging(self):
+        """One device allocation [windows uint8 | pad | labels int32]: a host batch whose labels sit
+        right behind its windows in ONE pinned buffer is staged with a single H2D copy."""
+        nw = self.B * self.W * self.D
+        self._win_pad = (-nw) % 4
+        self._winlab = torch.zeros(nw + self._win_pad + 4 * self.B, dtype=torch.uint8, device=self.dev)
+        self.win_buf = self._winlab[:nw]
+        self.labels = self._winlab[nw + self._win_pad:].view(torch.int32)
+        self._graphs.clear()
 
     # ------------------------------------------------------------------ configuration
     def cfg(self, **over):
@@ -139,7 +149,7 @@ class Engine:
         self._win_off_seq = (torch.arange(self.B, dtype=torch.int32, device=self.dev) * self.W).contiguous()
         self.win_off.copy_(self._win_off_seq)
         self._win_off_is_seq = True
-        self.win_buf = torch.zeros(self.B * self.W * self.D, dtype=torch.uint8, device=self.dev)
+        self._alloc_window_staging()
         self.roll = self.win_buf
         self._graphs.clear()
 
@@ -202,8 +212,17 @@ class Engine:
         if not self._win_off_is_seq:                                   # window b = frames [b*W, (b+1)*W)
             self.win_off.copy_(self._win_off_seq)
             self._win_off_is_seq = True
-        self.win_buf.copy_(win_u8.reshape(-1), non_blocking=non_blocking)
-        self.labels.copy_(labels_i32, non_blocking=non_blocking)
+        w = win_u8.reshape(-1)
+        nw = w.numel()
+        if (self._win_pad == 0 and not w.is_cuda and not labels_i32.is_cuda and labels_i32.dtype == torch.int32
+                and labels_i32.is_contiguous() and w.is_contiguous()
+                and labels_i32.data_ptr() == w.data_ptr() + nw
+                and labels_i32.untyped_storage().data_ptr() == w.untyped_storage().data_ptr()):
+            # labels packed behind the windows in one host buffer: one copy for both
+            self._winlab.copy_(w.as_strided((nw + 4 * self.B,), (1,)), non_blocking=non_blocking)
+        else:
+            self.win_buf.copy_(w, non_blocking=non_blocking)
+            self.labels.copy_(labels_i32, non_blocking=non_blocking)
 
     def stage_offsets(self, off_i32, labels_i32, non_blocking=True):
         self._win_off_is_seq = False
@@ -217,7 +236,8 @@ class Engine:
             # single GPU: nothing sits between backward and update, so the optimizer is part of the
             # step's schedule (Adam-WN per tensor range, overlapped with the encoder BPTT / wgrads)
             opt = clv_adam_args(state=self.opt_state.data_ptr(), lr=self.lr, beta_1=self.b1, beta_2=self.b2,
-                                epsilon=self.eps, grad_scale=1.0, weightnorm=int(self.optimizer == "adam-wn"))
+                                epsilon=self.eps, grad_scale=1.0, weightnorm=int(self.optimizer == "adam-wn"),
+                                loss_mirror=self.loss_host.data_ptr())   # pinned => device-visible (UVA)
             check(lib().clv_train_step_opt(C.byref(cfg), ptr(self.params), ptr(self.grads), ptr(self.loss_acc),
                                            ptr(self.roll), ptr(self.win_off), ptr(self.labels),
                                            ptr(self.eps_w), ptr(self.eps_z), ptr(self.rng_ctr),
@@ -253,6 +273,8 @@ class Engine:
         (train, gen_noise, roll buffer) and replayed."""
         # where the (globally reduced) loss scalars of this step end up
         self._loss_src = self.loss_red if (train and self.symm is not None) else self.loss_acc
+        # the scheduled-optimizer step mirrors its loss scalars into loss_host from its last kernel
+        self._loss_mirrored = bool(train and self.world_size == 1 and self.fused_optimizer)
         if not self.use_graph:
             n0 = lib().clv_launch_count()
             self._launch_step(train, gen_noise)
@@ -278,7 +300,8 @@ class Engine:
 
     def read_losses(self):
         """D2H of the 5 scalars (already global means) -> dict incl. Keras' weighted total."""
-        self.loss_host.copy_(self._loss_src, non_blocking=True)
+        if not self._loss_mirrored:
+            self.loss_host.copy_(self._loss_src, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         v = self.loss_host.tolist()
         d = dict(zip(LOSS_NAMES, v[:5]))

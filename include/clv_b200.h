@@ -259,11 +259,13 @@ int clv_adamwn_step(const clv_cfg* cfg, float* params, const float* grads, float
 /* The same update restricted to the tensors [t_first, t_last) of clv_param_layout's order (weight-norm
  * is per tensor column, so ranges are independent).  `advance` != 0 on exactly one -- the last -- call
  * of a step: it increments `iterations` when its last block retires; all ranges of a step must be
- * issued before that call completes. */
+ * issued before that call completes.  loss_mirror (nullable, used by the advancing call): the 8 loss
+ * scalars stored behind the gradients (grads[P..P+8), the [grads | losses] buffer) are copied there --
+ * pass host-mapped pinned memory and the host needs only a stream sync to read the step's losses. */
 int clv_adamwn_step_range(const clv_cfg* cfg, float* params, const float* grads, float* state, double lr,
                           double beta_1, double beta_2, double epsilon, double grad_scale,
                           int32_t weightnorm, int32_t t_first, int32_t t_last, int32_t advance,
-                          void* stream);
+                          float* loss_mirror, void* stream);
 
 /* Data-parallel form: gradient all-reduce FUSED into the optimizer over NVLink peer memory.
  * peer_grads = device array of n_peers pointers to every rank's [grads(P) | losses(8)] buffer in
@@ -302,6 +304,7 @@ typedef struct clv_adam_args {
   float* state;                 /* clv_adamwn_state_floats() floats, initialised by clv_adamwn_init */
   double lr, beta_1, beta_2, epsilon, grad_scale;
   int32_t weightnorm;
+  float* loss_mirror;           /* nullable: host-mapped copy of the step's 8 loss scalars (see above) */
 } clv_adam_args;
 int clv_train_step_opt(const clv_cfg* cfg, float* params, float* grads, float* loss_acc,
                        const uint8_t* roll, const int32_t* win_off, const int32_t* labels,

@@ -106,4 +106,4 @@ gr = torch.randn_like(eng.grads) * 1e-3
 for name, t0, t1 in [("adam-wn [key encoder] 0..4", 0, 4), ("adam-wn [enc LSTM | Z heads] 4..11", 4, 11),
                      ("adam-wn [decoder | X head] 11..16", 11, 16), ("adam-wn all 0..16", 0, 16)]:
     timeit(name, lambda: check(L_.clv_adamwn_step_range(C.byref(cfgA), ptr(eng.params), ptr(gr), ptr(eng.opt_state),
-                                                        1e-3, 0.9, 0.999, 1e-8, 1.0, 1, t0, t1, 1 if t1 == 16 else 0, st)))
+                                                        1e-3, 0.9, 0.999, 1e-8, 1.0, 1, t0, t1, 1 if t1 == 16 else 0, None, st)))

@@ -117,6 +117,36 @@ def test_keras_style_train_on_batch_with_independent_history():
     assert len(res) == len(model.metrics_names) == 6 and np.all(np.isfinite(res))
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_packed_pinned_batch_and_mirrored_losses(use_graph):
+    """train_on_batch_windows: a batch given as ONE pinned buffer [windows | labels] (single H2D copy) and
+    as two separate tensors stages the same data, and the losses the scheduled-optimizer step mirrors
+    into pinned host memory equal the ones copied back explicitly (eval pass, fused_optimizer off)."""
+    from clvae_b200.cl_vrnn import model as M
+    B, L, C = 16, 6, 4
+    rng = np.random.default_rng(5)
+    nw = B * (L + 1) * 88
+    buf = torch.empty(nw + 4 * B, dtype=torch.uint8).pin_memory()
+    buf[:nw] = torch.from_numpy((rng.random(nw) < 0.08).astype(np.uint8))
+    lab = buf[nw:].view(torch.int32)
+    lab.copy_(torch.from_numpy(rng.integers(0, C, B).astype(np.int32)))
+    win = buf[:nw].view(B, L + 1, 88)
+    models = []
+    for fused in (True, False):
+        m, _ = M.get_model(B, 88, 88, 2, L, C, True, "adam-wn", seed=3, use_graph=use_graph, fused_optimizer=fused)
+        models.append(m)
+    a, b = models
+    b.engine.set_params(a.engine.get_params())
+    for step in range(3):
+        for m in (a, b):
+            m.engine.rng_ctr.fill_(step)            # same Philox stream in both engines
+        la = a.train_on_batch_windows(win, lab)                        # packed: one copy, mirrored losses
+        lb = b.train_on_batch_windows(win.clone().pin_memory(), lab.clone().pin_memory())   # two copies, D2H
+        assert torch.equal(a.engine.win_buf, b.engine.win_buf) and torch.equal(a.engine.labels, b.engine.labels)
+        for k in la:
+            assert abs(la[k] - lb[k]) <= 2e-5 * max(1.0, abs(lb[k])), (step, k, la[k], lb[k])
+
+
 def test_vae_cli_train_then_sample_readme_example(tmp_path):
     """README.md:33-34: train a CL-VAE (latent_dim 4, --use_x_prev) on JSB Chorales_Cs, then sample."""
     from clvae_b200.cl_vae import train as T, sample as S

@@ -379,6 +379,53 @@ def test_lstm_fused_input_terms_and_extra_gradients(B_, L, Z, Cc, has_x):
     assert util.rel_err(dWe.cpu().numpy(), base + dA.sum(1) @ Ww.T) < TOL
 
 
+@pytest.mark.parametrize("B_,L,Z", [(200, 16, 2), (5, 7, 1), (37, 4, 2)])
+def test_lstm_bwd_with_fused_z_head_exchange(B_, L, Z):
+    """clv_lstm_bwd_heads: the decoder BPTT emits dLoss/d(Z_mean|Z_log_var) (reparametrisation backward +
+    kl term), the encoder BPTT consumes it as dLoss/dh_e = dZargs @ [Kzm|Kzv]^T per cell -- against the
+    numpy derivation (oracle/manual_bwd.py) of the same chain (cl_vrnn/model.py:200-216,236-239)."""
+    _lib, Lb, check, ptr, st = _env()
+    rng = np.random.default_rng(B_ * 7 + L + Z)
+    H, G = 88, 352
+    U_d = rng.normal(0, 0.15, (H, G)); U_e = rng.normal(0, 0.15, (H, G))
+    Kz = rng.normal(0, 0.4, (Z, G)); Kzm = rng.normal(0, 0.3, (H, Z)); Kzv = rng.normal(0, 0.3, (H, Z))
+    Zargs = rng.normal(0, 0.5, (B_, L, 2 * Z)); eps = rng.normal(size=(B_, L, Z))
+    klw = 0.3 / (B_ * L)
+    # two independent forward recurrences give consistent stashes for the two BPTTs
+    xp_d = rng.normal(size=(B_, L, G)); xp_e = rng.normal(size=(B_, L, G))
+    hs_d, cs_d, a_d = M.lstm_fwd(xp_d, U_d)
+    hs_e, cs_e, a_e = M.lstm_fwd(xp_e, U_e)
+    dh_d = rng.normal(size=(B_, L, H))
+    dA_d = M.lstm_bwd(dh_d, hs_d, cs_d, a_d, U_d)
+    dZ = dA_d @ Kz.T
+    mu, lv = Zargs[..., :Z], Zargs[..., Z:]
+    dmu = dZ + klw * mu
+    dlv = dZ * eps * 0.5 * np.exp(0.5 * lv) + klw * 0.5 * (np.exp(lv) - 1.0)
+    dh_e = dmu @ Kzm.T + dlv @ Kzv.T
+    dA_e = M.lstm_bwd(dh_e, hs_e, cs_e, a_e, U_e)
+
+    def run_fwd(xp, U):
+        g = dev(xp); hd = torch.zeros(B_, L, H, device="cuda"); cd = torch.zeros(B_, L, H, device="cuda")
+        check(Lb.clv_lstm_fwd(ptr(g), ptr(dev(U)), ptr(hd), ptr(cd), None, None, B_, L, H, st))
+        return g, cd
+    g_d, c_d = run_fwd(xp_d, U_d)
+    g_e, c_e = run_fwd(xp_e, U_e)
+    dAs_d = torch.zeros(B_, G, device="cuda"); dAs_e = torch.zeros(B_, G, device="cuda")
+    dZd = torch.zeros(B_, L, Z, device="cuda"); dZa = torch.zeros(B_, L, 2 * Z, device="cuda")
+    check(Lb.clv_lstm_bwd_heads(ptr(g_d), ptr(dev(U_d)), ptr(c_d), ptr(dev(dh_d)), ptr(dAs_d), None, 0, None, 0,
+                                ptr(dev(Kz)), Z, ptr(dZd), ptr(dev(Zargs)), ptr(dev(eps)), klw, ptr(dZa),
+                                None, None, None, 0, B_, L, H, st))
+    check(Lb.clv_lstm_bwd_heads(ptr(g_e), ptr(dev(U_e)), ptr(c_e), None, ptr(dAs_e), None, 0, None, 0,
+                                None, 0, None, None, None, 0.0, None,
+                                ptr(dZa), ptr(dev(Kzm)), ptr(dev(Kzv)), Z, B_, L, H, st))
+    torch.cuda.synchronize()
+    assert util.rel_err(dZd.cpu().numpy(), dZ) < TOL
+    assert util.rel_err(dZa.cpu().numpy(), np.concatenate([dmu, dlv], -1)) < TOL
+    assert util.rel_err(g_d.cpu().numpy(), dA_d) < TOL
+    assert util.rel_err(g_e.cpu().numpy(), dA_e) < TOL
+    assert util.rel_err(dAs_e.cpu().numpy(), dA_e.sum(1)) < TOL
+
+
 # ---------------------------------------------------------------------------- tcgen05 path
 @pytest.mark.parametrize("B_,Lq,shift", [(200, 16, 1), (3, 5, 0), (1000, 33, 1)])
 def test_inproj_tcgen05_is_fp32_exact(B_, Lq, shift):
