@@ -113,6 +113,100 @@ xhead_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const fl
   if (tid == 0) atomicAdd(loss_acc + 0, t * scale);
 }
 
+// Large-R form: 64-row tiles, thread = (column PAIR, 8 rows).  The 8x1 tile above spends 3 shared
+// loads per 8 FMAs (shared pipe 67 % busy at 524 k rows); 8x2 spends 3 per 16.
+constexpr int XR2 = 64, XRP2 = 68;
+__global__ void __launch_bounds__(XT, 2)
+xhead2_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const float* __restrict__ bx,
+              const uint8_t* __restrict__ roll, const int32_t* __restrict__ x_off, const int x_grp,
+              const int x_shift, float* __restrict__ loss_acc, float* __restrict__ dlogits,
+              float* __restrict__ dh, const int64_t R, const float scale, const int do_backward) {
+  extern __shared__ __align__(16) float sm[];
+  float* K_s = sm;                    // [k][d]
+  float* KT_s = K_s + XD * XD;        // [d][k]
+  float* h_s = KT_s + XD * XD;        // [XD][XRP2] transposed h tile, later the dlogits tile
+  __shared__ float red[32];
+  const int tid = threadIdx.x, jp = tid % (XD / 2), rq = tid / (XD / 2), j0 = 2 * jp;   // rows 8rq..8rq+7
+  for (int i = tid; i < XD * XD; i += XT) {
+    const float v = __ldg(Kx + i);
+    K_s[i] = v;
+    KT_s[(i % XD) * XD + (i / XD)] = v;
+  }
+  const float b0 = __ldg(bx + j0), b1 = __ldg(bx + j0 + 1);
+  float lsum = 0.f;
+  pdl_wait();                 // everything above reads parameters only
+  pdl_launch_dependents();
+  for (int64_t row0 = (int64_t)blockIdx.x * XR2; row0 < R; row0 += (int64_t)gridDim.x * XR2) {
+    __syncthreads();
+    for (int i = tid; i < XR2 * XD; i += XT) {
+      const int rr = i / XD, k = i - rr * XD;
+      const int64_t r = row0 + rr;
+      h_s[k * XRP2 + rr] = (r < R) ? __ldg(h + r * XD + k) : 0.f;
+    }
+    __syncthreads();
+    float a0[8], a1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a0[i] = b0; a1[i] = b1; }
+#pragma unroll 4
+    for (int k = 0; k < XD; ++k) {
+      const float2 w = *reinterpret_cast<const float2*>(K_s + k * XD + j0);
+      const float4 h0 = *reinterpret_cast<const float4*>(h_s + k * XRP2 + rq * 8);
+      const float4 h1 = *reinterpret_cast<const float4*>(h_s + k * XRP2 + rq * 8 + 4);
+      const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a0[i] = fmaf(hv[i], w.x, a0[i]); a1[i] = fmaf(hv[i], w.y, a1[i]); }
+    }
+    __syncthreads();   // all reads of the h tile done; it becomes the dlogits tile
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = row0 + rq * 8 + i;
+      float d0 = 0.f, d1 = 0.f;
+      if (r < R) {
+        const int64_t g = r / x_grp;
+        const int64_t xrow = (int64_t)__ldg(x_off + g) + x_shift + (r - g * x_grp);
+        const uint32_t xx = *reinterpret_cast<const uint16_t*>(roll + xrow * XD + j0);   // 2 keys
+        const float x[2] = {(float)(xx & 0xffu), (float)(xx >> 8)};
+        const float lg[2] = {a0[i], a1[i]};
+        float dl[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float p = sigmoid_f(lg[c]);
+          const float pc = fminf(fmaxf(p, CLV_EPS), 1.0f - CLV_EPS);
+          const float l = logf(pc / (1.0f - pc));
+          lsum += fmaxf(l, 0.f) - l * x[c] + log1pf(expf(-fabsf(l)));
+          const bool pass = (p >= CLV_EPS) && (p <= 1.0f - CLV_EPS);
+          dl[c] = pass ? scale * (pc - x[c]) : 0.f;
+        }
+        d0 = dl[0]; d1 = dl[1];
+        if (do_backward) *reinterpret_cast<float2*>(dlogits + r * XD + j0) = make_float2(d0, d1);
+      }
+      h_s[j0 * XRP2 + rq * 8 + i] = d0;
+      h_s[(j0 + 1) * XRP2 + rq * 8 + i] = d1;
+    }
+    if (!do_backward) continue;
+    __syncthreads();   // the dlogits tile is complete
+    // dh[r][k] = sum_d dlogits[r][d] * Kx[k][d], this thread: k = j0, j0 + 1
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
+#pragma unroll 4
+    for (int d = 0; d < XD; ++d) {
+      const float2 w = *reinterpret_cast<const float2*>(KT_s + d * XD + j0);
+      const float4 g0 = *reinterpret_cast<const float4*>(h_s + d * XRP2 + rq * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(h_s + d * XRP2 + rq * 8 + 4);
+      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a0[i] = fmaf(gv[i], w.x, a0[i]); a1[i] = fmaf(gv[i], w.y, a1[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = row0 + rq * 8 + i;
+      if (r < R) *reinterpret_cast<float2*>(dh + r * XD + j0) = make_float2(a0[i], a1[i]);
+    }
+  }
+  const float t = block_sum(lsum, red);
+  if (tid == 0) atomicAdd(loss_acc + 0, t * scale);
+}
+
 // ------------------------------------------------------------------------------ key encoder fwd
 constexpr int KT = 128;   // threads per sequence
 
@@ -427,7 +521,22 @@ extern "C" int clv_xhead_fwd_bwd(const float* h, const float* Kx, const float* b
     attr_set = true;
   }
   int64_t xgrid = (R + XR - 1) / XR;
-  if (xgrid <= clv_num_sms()) {
+  const bool al8 = (((uintptr_t)dlogits | (uintptr_t)dh) & 7) == 0 && (((uintptr_t)roll) & 1) == 0;
+  if ((R + XR2 - 1) / XR2 > clv_num_sms() && al8) {
+    // large R: 64-row tiles, 8x2 register tile, 2 CTAs (86 KB smem each) per SM
+    const size_t smem2 = sizeof(float) * (2 * XD * XD + XD * XRP2);
+    static bool attr2 = false;
+    if (!attr2) {
+      CLV_CUDA(cudaFuncSetAttribute(xhead2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      CLV_CUDA(cudaFuncSetAttribute(xhead2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    (int)cudaSharedmemCarveoutMaxShared));
+      attr2 = true;
+    }
+    int64_t g2 = (R + XR2 - 1) / XR2;
+    if (g2 > 2LL * clv_num_sms()) g2 = 2LL * clv_num_sms();
+    CLV_CUDA(clv_launch(xhead2_kernel, (unsigned)g2, XT, smem2, (cudaStream_t)stream,
+                        h, Kx, bx, roll, x_off, x_grp, x_shift, loss_acc, dlogits, dh, R, scale, do_backward));
+  } else if (xgrid <= clv_num_sms()) {
     CLV_CUDA(clv_launch(xhead_kernel<1>, (unsigned)xgrid, XT, smem, (cudaStream_t)stream,
                         h, Kx, bx, roll, x_off, x_grp, x_shift, loss_acc, dlogits, dh, R, scale, do_backward));
   } else {

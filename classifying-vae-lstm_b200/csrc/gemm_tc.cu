@@ -132,11 +132,14 @@ struct TcArgs {
 //   warps 4-7  epilogue  : TMEM accumulator [stage] -> registers -> smem transpose -> 128-byte row stores
 //   warp  8    MMA       : bulk-TMA the weight image once, then 18 tcgen05.mma per tile, commits
 // mbarriers: a_full/a_empty per A stage, acc_full/acc_empty per TMEM accumulator.
-constexpr int TC_THREADS = 416;   // 4 producer + 4 epilogue warps, the MMA warp, 4 more epilogue warps
+constexpr int TC_THREADS = 288;      // 4 producer + 4 epilogue warps + the MMA warp
+constexpr int TC_THREADS_RA = 416;   // addend form: 4 more epilogue warps
 constexpr int ACC_STRIDE = 256;                     // TMEM columns between the two accumulators
 constexpr int STAGE_BYTES = 8 * 32 * 36 * 4;   // one transpose buffer per epilogue warp        // epilogue transpose buffers (one per warp)
 
-__global__ void __launch_bounds__(TC_THREADS, 1) inproj_tc_kernel(const TcArgs a) {
+// RA: per-sequence addend form (a.rowadd != null), eight epilogue warps
+template <bool RA>
+__global__ void __launch_bounds__(RA ? TC_THREADS_RA : TC_THREADS, 1) inproj_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* a_s = smem;                               // 2 x A tile
   uint8_t* b_s = smem + 2 * A_BYTES;                 // 3 split images of this N-half
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) inproj_tc_kernel(const TcArgs a
       mbar_init(BAR(A_FULL + s), 4);      // one arrive per producer warp
       mbar_init(BAR(A_EMPTY + s), 1);     // tcgen05.commit
       mbar_init(BAR(ACC_FULL + s), 1);    // tcgen05.commit
-      mbar_init(BAR(ACC_EMPTY + s), 8);   // one arrive per epilogue warp
+      mbar_init(BAR(ACC_EMPTY + s), RA ? 8 : 4);   // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -208,7 +211,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) inproj_tc_kernel(const TcArgs a
     // per SM sub-partition was latency-bound in the addend form (0.38 vs 0.16 ms at 524 k rows).
     // TMEM -> registers (row per lane) -> smem transpose (stride 36: conflict-free 128-bit) ->
     // 128-bit stores, 8 lanes per 128-byte row segment, 4 rows per warp instruction.
+    // (the plain form is HBM-store bound with four warps -- eight cost it 6 % -- so it keeps four)
     const int q = warp & 3, cpart = (warp > 8) ? 1 : 0;
+    constexpr int cstep = RA ? 64 : 32;
     float* stage = stage_all + (q + 4 * cpart) * (32 * 36);
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     for (int it = 0; it < ntile; ++it) {
@@ -218,12 +223,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) inproj_tc_kernel(const TcArgs a
       uint32_t ragrp[8];                         // per-sequence addend row of the 8 rows this lane stores
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        ragrp[i] = a.rowadd ? (uint32_t)(m0 + 4 * i + rsub) / (uint32_t)a.ra_grp : 0u;
+        ragrp[i] = RA ? (uint32_t)(m0 + 4 * i + rsub) / (uint32_t)a.ra_grp : 0u;
       mbar_wait(BAR(ACC_FULL + s), ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * ACC_STRIDE);
 #pragma unroll 1
-      for (int c0 = 32 * cpart; c0 < TN; c0 += 64) {
+      for (int c0 = 32 * cpart; c0 < TN; c0 += cstep) {
         const int ncol = min(32, TN - c0);          // 32,32,32,32,32,16
         uint32_t r[32];
         if (ncol == 32) {
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) inproj_tc_kernel(const TcArgs a
         if (c4 < ncol) {
           const int n = half * TN + c0 + c4;
           float* crow = a.C + (m0 + rsub) * a.ldc + n;
-          if (!a.rowadd) {
+          if (!RA) {
 #pragma unroll
             for (int rr = 0; rr < 32; rr += 4) {
               if (rr + rsub < rows_valid)
@@ -337,7 +342,8 @@ extern "C" int clv_inproj_tc(const uint8_t* roll, const int32_t* win_off, int32_
   static bool attr_set = false;
   const int smem = 2 * A_BYTES + B_BYTES + STAGE_BYTES + 1024;
   if (!attr_set) {
-    CLV_CUDA(cudaFuncSetAttribute(inproj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CLV_CUDA(cudaFuncSetAttribute(inproj_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CLV_CUDA(cudaFuncSetAttribute(inproj_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   TcArgs a;
@@ -347,7 +353,8 @@ extern "C" int clv_inproj_tc(const uint8_t* roll, const int32_t* win_off, int32_
   int gx = clv_num_sms() / 2;
   if (gx > a.tiles) gx = a.tiles;
   if (gx < 1) gx = 1;
-  inproj_tc_kernel<<<dim3(gx, 2), TC_THREADS, smem, st>>>(a);
+  if (rowadd) inproj_tc_kernel<true><<<dim3(gx, 2), TC_THREADS_RA, smem, st>>>(a);
+  else inproj_tc_kernel<false><<<dim3(gx, 2), TC_THREADS, smem, st>>>(a);
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }

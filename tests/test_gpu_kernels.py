@@ -286,7 +286,7 @@ def test_adamwn_matches_oracle_trajectory(weightnorm):
 
 
 # ---------------------------------------------------------------------------- fused kernels
-@pytest.mark.parametrize("R,grp", [(3200, 16), (45, 5)])
+@pytest.mark.parametrize("R,grp", [(3200, 16), (45, 5), (20031 // 33 * 33, 33)])   # last: the 64-row-tile kernel
 def test_xhead_fused_matches_gemm_plus_bernoulli(R, grp):
     _lib, L, check, ptr, st = _env()
     rng = np.random.default_rng(R)
