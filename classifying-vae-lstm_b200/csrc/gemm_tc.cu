@@ -8,9 +8,10 @@
 //     cp.async.bulk (TMA) copies completing on an mbarrier;
 //   * warp-specialised persistent CTAs (grid = 2 N-halves x SMs/2): four producer warps gather and
 //     convert the A tile, one elected thread issues the 18 MMAs (3 splits x 6 k-steps of 16) per
-//     128x176 tile and commits to mbarriers, four epilogue warps read TMEM with tcgen05.ld, add the
-//     optional per-sequence addend and store 128-bit coalesced rows; A tiles and TMEM accumulators
-//     are double-buffered so the store-bound epilogue runs back to back.  Replaces the MatMul of `x @ kernel` inside Keras' LSTM preprocess_input
+//     128x176 tile and commits to mbarriers, four epilogue warps (eight in the per-sequence-addend
+//     form) read TMEM with tcgen05.ld, add the optional addend and store 128-bit coalesced rows;
+//     A tiles and TMEM accumulators are double-buffered so the store-bound epilogue runs back to back.
+// Replaces the MatMul of `x @ kernel` inside Keras' LSTM preprocess_input
 // (cl_vrnn/model.py:196-199,225-228 [K2-recall]).
 #include <cuda_bf16.h>
 #include "common.cuh"

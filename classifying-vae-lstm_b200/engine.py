@@ -1,8 +1,9 @@
 """
 Device-side engine behind the Keras-like model objects: owns the flat parameter / gradient /
 optimizer-state / workspace buffers (PyTorch is only the allocator and the stream/NCCL plumbing) and
-drives libclv_b200's fused train step, the NCCL gradient all-reduce and the Adam-WN update, optionally
-replayed as one CUDA graph.  One process per GPU; data parallel = batch sharded across ranks.
+drives libclv_b200's train step -- on one GPU with the Adam-WN update scheduled inside it
+(clv_train_step_opt), with N > 1 as step -> NCCL gradient all-reduce -> Adam-WN -- optionally replayed
+as one CUDA graph.  One process per GPU; data parallel = batch sharded across ranks.
 
 Replaces what Keras' `train_function` / `test_function` do for the reference (cl_vrnn/train.py:66-71;
 graph cl_vrnn/model.py:169-264; optimizer utils/weightnorm.py:75-143).
