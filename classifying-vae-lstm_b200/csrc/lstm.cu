@@ -62,6 +62,20 @@ constexpr int ZQ = 8;     // latent dimensions folded into the backward mat-vec 
 // the threads, and the cross-lane reduction is a reduce-scatter that leaves each lane with exactly
 // the one (row, unit) cell whose state it owns in registers.
 
+// Two fp32 FMAs in one instruction (Blackwell FFMA2, PTX fma.rn.f32x2): acc.{x,y} += s * v.{x,y}.  ptxas
+// folds the scalar into a broadcast operand (FFMA2 R, Rs.F32, Rv.F32x2, Racc.F32x2): no packing
+// moves, the same round-to-nearest result per lane, half the issue slots of two FFMAs -- which is
+// what these issue-bound mat-vecs need.  The smem operands are laid out [k][row] so that the rows of
+// one k arrive as the register pair(s) of one LDS.
+__device__ __forceinline__ void ffma2(float2& acc, const float s, const float2 v) {
+  unsigned long long a, b, c, r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(s));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(v.x), "f"(v.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc.x), "f"(acc.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(r));
+}
+
 // Sum v[0..N) over the lane group {lane ^ m : m < 2N} so that the lane whose low bits are e ends
 // with the total of element e (N shuffles instead of N log N).
 template <int N>
@@ -88,10 +102,10 @@ __global__ void __launch_bounds__(4 * H, 1)
 lstm_fwd_kernel(float* __restrict__ gates, const float* __restrict__ U, float* __restrict__ hout,
                 float* __restrict__ cout, const float* __restrict__ h0, const float* __restrict__ c0,
                 const int B, const int L, const int R, const LstmExtra ex) {
-  constexpr int G = 4 * H, KS = 4, KSZ = H / KS, NT = 4 * H, NP = RMAX / RC;
+  constexpr int G = 4 * H, KS = 4, KSZ = H / KS, NT = 4 * H, NP = 1;   // one pass of RC rows (R <= RC)
   static_assert(KSZ % 2 == 0, "H must be a multiple of 8");
   static_assert(RC == 2 || RC == 4, "RC");
-  __shared__ __align__(16) float h_s[2][RMAX][H];
+  __shared__ __align__(16) float h_s[2][H][RC];       // [buffer][k][row]: the rows of one k are one LDS
   __shared__ float kz_s[ZMAX][G];
   const int tid = threadIdx.x, j = tid >> 2, ks = tid & 3;
   const int b0 = blockIdx.x * R;
@@ -131,10 +145,10 @@ lstm_fwd_kernel(float* __restrict__ gates, const float* __restrict__ U, float* _
     }
     creg[p] = (on && c0) ? c0[(size_t)(b0 + r) * H + j] : 0.f;
   }
-  for (int i = tid; i < RMAX * H; i += NT) {
+  for (int i = tid; i < RC * H; i += NT) {
     const int r = i / H, jj = i - r * H;
-    h_s[0][r][jj] = (r < nrows && h0) ? h0[(size_t)(b0 + r) * H + jj] : 0.f;
-    h_s[1][r][jj] = 0.f;
+    h_s[0][jj][r] = (r < nrows && h0) ? h0[(size_t)(b0 + r) * H + jj] : 0.f;
+    h_s[1][jj][r] = 0.f;
   }
 
   // software pipeline: the hoisted projection and the Z row of step t+1 are loaded while step t computes
@@ -176,22 +190,33 @@ lstm_fwd_kernel(float* __restrict__ gates, const float* __restrict__ U, float* _
         for (int z = 0; z < ZR; ++z)
           if (z < Z) zpre[p][z] = __ldg(ex.Zs + (bt + 1) * Z + z);
       }
-      // ---- partial h_{t-1} @ U over this lane's k-slice, 4 gates x RC rows
-      float acc[4 * RC];
+      // ---- partial h_{t-1} @ U over this lane's k-slice, 4 gates x RC rows (row pairs: FFMA2)
+      float2 acc2[4][RC / 2];
 #pragma unroll
-      for (int i = 0; i < 4 * RC; ++i) acc[i] = 0.f;
+      for (int g = 0; g < 4; ++g)
 #pragma unroll
-      for (int i2 = 0; i2 < KSZ / 2; ++i2) {
+        for (int pp = 0; pp < RC / 2; ++pp) acc2[g][pp] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int qq = 0; qq < RC; ++qq) {
-          const float2 hv = *reinterpret_cast<const float2*>(&h_s[cur][r0 + qq][ks * KSZ + 2 * i2]);
+      for (int i = 0; i < KSZ; ++i) {
+        const float* hp = &h_s[cur][ks * KSZ + i][0];
+        if (RC == 2) {
+          const float2 hv = *reinterpret_cast<const float2*>(hp);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) ffma2(acc2[g][0], Ureg[g][i], hv);
+        } else {
+          const float4 hv = *reinterpret_cast<const float4*>(hp);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            acc[g * RC + qq] = fmaf(Ureg[g][2 * i2], hv.x, acc[g * RC + qq]);
-            acc[g * RC + qq] = fmaf(Ureg[g][2 * i2 + 1], hv.y, acc[g * RC + qq]);
+            ffma2(acc2[g][0], Ureg[g][i], make_float2(hv.x, hv.y));
+            ffma2(acc2[g][RC / 2 - 1], Ureg[g][i], make_float2(hv.z, hv.w));
           }
         }
       }
+      float acc[4 * RC];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int pp = 0; pp < RC / 2; ++pp) { acc[g * RC + 2 * pp] = acc2[g][pp].x; acc[g * RC + 2 * pp + 1] = acc2[g][pp].y; }
       // ---- reduce over the 4 k-slices; lane ks keeps row q of every gate
       float a[4];
 #pragma unroll
@@ -224,7 +249,7 @@ lstm_fwd_kernel(float* __restrict__ gates, const float* __restrict__ U, float* _
         const float c = fmaf(fg, creg[p], ig * gg);
         const float h = og * tanhf(c);
         creg[p] = c;
-        h_s[cur ^ 1][r][j] = h;
+        h_s[cur ^ 1][j][r] = h;
         float* gp = gates + bt * G + j;
         gp[0] = ig; gp[H] = fg; gp[2 * H] = gg; gp[3 * H] = og;
         hout[bt * H + j] = h;
@@ -261,10 +286,10 @@ __global__ void __launch_bounds__(16 * (H / 4 + ZQ / 4), 1)
 lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const float* __restrict__ c,
                 const float* __restrict__ dh_out, float* __restrict__ dAsum, const int B,
                 const int L, const int R, const LstmExtra ex) {
-  constexpr int G = 4 * H, NS = 16, NSZ = G / NS, NKU = H / 4, NP = RMAX / RC;
+  constexpr int G = 4 * H, NS = 16, NSZ = G / NS, NKU = H / 4, NP = 1;   // one pass of RC rows (R <= RC)
   static_assert(NSZ % 2 == 0 && H % 4 == 0, "H must be a multiple of 8");
   static_assert(RC == 2 || RC == 4, "RC");
-  __shared__ __align__(16) float da_s[2][RMAX][G];
+  __shared__ __align__(16) float da_s[2][G][RC];      // [buffer][gate column][row]
   const int tid = threadIdx.x, kq = tid >> 4, ns = tid & 15;
   const int lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
   const int Z = ex.dZ ? ex.Z : 0;
@@ -278,10 +303,11 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
   const int j = 4 * kq + kk_c;                 // unit (is_u)
   const int zo = 4 * (kq - NKU) + kk_c;        // latent index (!is_u)
 
-  // n-slice ns = the column PAIRS {2(16 i2 + ns), +1 : i2 < 11}: for a fixed register the 16 lanes of a
-  // quad read 128 contiguous bytes of a U row (4 sectors per row instead of one sector per lane --
-  // the contiguous-slice mapping made this prologue cost ~8 steps), and the matching dA reads are
-  // conflict-free LDS.64.  U and Kz are 8-byte aligned (every tensor before them has an even size).
+  // n-slice ns = 22 columns INTERLEAVED over the 16 lanes of a quad (mapping below): for a fixed
+  // register the lanes read 64-128 contiguous bytes of a U row (a contiguous slice per lane cost one
+  // sector per lane and made this prologue as long as ~8 steps), and the matching dA reads from
+  // shared memory are conflict-free.  U and Kz are 8-byte aligned (every tensor before them has an
+  // even size).
   float Ureg[4][NSZ];
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
@@ -290,15 +316,21 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
                              : ((zz < Z && zz < ZQ) ? ex.Kz + (size_t)zz * G : nullptr);
 #pragma unroll
     for (int i2 = 0; i2 < NSZ / 2; ++i2) {
-      float2 u = make_float2(0.f, 0.f);
-      if (rowp) u = __ldg(reinterpret_cast<const float2*>(rowp + (i2 * NS + ns) * 2));
-      Ureg[kk][2 * i2] = u.x;
-      Ureg[kk][2 * i2 + 1] = u.y;
+      if (RC == 2) {          // columns 2(16 i2 + ns), +1: one conflict-free LDS.128 of dA per i2
+        float2 u = make_float2(0.f, 0.f);
+        if (rowp) u = __ldg(reinterpret_cast<const float2*>(rowp + (i2 * NS + ns) * 2));
+        Ureg[kk][2 * i2] = u.x;
+        Ureg[kk][2 * i2 + 1] = u.y;
+      } else {                // columns 32 i2 + ns and 32 i2 + 16 + ns: each of the two LDS.128 (4 rows
+                              // of one column) then covers 16 consecutive 16-byte chunks per half-warp
+        Ureg[kk][2 * i2] = rowp ? __ldg(rowp + i2 * 2 * NS + ns) : 0.f;
+        Ureg[kk][2 * i2 + 1] = rowp ? __ldg(rowp + i2 * 2 * NS + NS + ns) : 0.f;
+      }
     }
   }
   pdl_wait();                 // everything above reads parameters only
   pdl_launch_dependents();
-  for (int i = tid; i < 2 * RMAX * G; i += blockDim.x) (&da_s[0][0][0])[i] = 0.f;
+  for (int i = tid; i < 2 * RC * G; i += blockDim.x) (&da_s[0][0][0])[i] = 0.f;
 
   float kzm[ZB], kzv[ZB];
 #pragma unroll
@@ -377,8 +409,8 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
         const float daf = (fg > 0.f && fg < 1.f) ? 0.2f * dcc * cprev : 0.f;
         const float dag = dcc * ig * (1.0f - gg * gg);
         const float dao = (og > 0.f && og < 1.f) ? 0.2f * d_o : 0.f;
-        float* ds = &da_s[buf][r][j];
-        ds[0] = dai; ds[H] = daf; ds[2 * H] = dag; ds[3 * H] = dao;
+        float* ds = &da_s[buf][j][r];
+        ds[0] = dai; ds[H * RC] = daf; ds[2 * H * RC] = dag; ds[3 * H * RC] = dao;
         gp[0] = dai; gp[H] = daf; gp[2 * H] = dag; gp[3 * H] = dao;
         asum[p][0] += dai; asum[p][1] += daf; asum[p][2] += dag; asum[p][3] += dao;
       }
@@ -390,21 +422,39 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
     for (int p = 0; p < NP; ++p) {
       const int r0 = p * RC;
       if (r0 >= nrows) break;
-      float acc[4 * RC];
+      float2 acc2[4][RC / 2];
 #pragma unroll
-      for (int i = 0; i < 4 * RC; ++i) acc[i] = 0.f;
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int pp = 0; pp < RC / 2; ++pp) acc2[kk][pp] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i2 = 0; i2 < NSZ / 2; ++i2) {
-#pragma unroll
-        for (int qq = 0; qq < RC; ++qq) {
-          const float2 dv = *reinterpret_cast<const float2*>(&da_s[buf][r0 + qq][(i2 * NS + ns) * 2]);
+        // this lane's column pair n, n+1 of dA_t for all RC rows: RC = 2 -> one LDS.128, RC = 4 -> two
+        const float* dp = &da_s[buf][(i2 * NS + ns) * 2][0];
+        if (RC == 2) {
+          const float4 dv = *reinterpret_cast<const float4*>(dp);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            acc[kk * RC + qq] = fmaf(Ureg[kk][2 * i2], dv.x, acc[kk * RC + qq]);
-            acc[kk * RC + qq] = fmaf(Ureg[kk][2 * i2 + 1], dv.y, acc[kk * RC + qq]);
+            ffma2(acc2[kk][0], Ureg[kk][2 * i2], make_float2(dv.x, dv.y));
+            ffma2(acc2[kk][0], Ureg[kk][2 * i2 + 1], make_float2(dv.z, dv.w));
+          }
+        } else {
+          const float4 d0 = *reinterpret_cast<const float4*>(&da_s[buf][i2 * 2 * NS + ns][0]);
+          const float4 d1 = *reinterpret_cast<const float4*>(&da_s[buf][i2 * 2 * NS + NS + ns][0]);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            ffma2(acc2[kk][0], Ureg[kk][2 * i2], make_float2(d0.x, d0.y));
+            ffma2(acc2[kk][RC / 2 - 1], Ureg[kk][2 * i2], make_float2(d0.z, d0.w));
+            ffma2(acc2[kk][0], Ureg[kk][2 * i2 + 1], make_float2(d1.x, d1.y));
+            ffma2(acc2[kk][RC / 2 - 1], Ureg[kk][2 * i2 + 1], make_float2(d1.z, d1.w));
           }
         }
       }
+      float acc[4 * RC];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int pp = 0; pp < RC / 2; ++pp) { acc[kk * RC + 2 * pp] = acc2[kk][pp].x; acc[kk * RC + 2 * pp + 1] = acc2[kk][pp].y; }
       if (RC == 2) {
 #pragma unroll
         for (int i = 0; i < 4 * RC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
@@ -420,7 +470,7 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
     for (int pz = wid; pz < nrows * (Z - ZQ); pz += nwarps) {
       const int r = pz / (Z - ZQ), zz = ZQ + pz - r * (Z - ZQ);
       float p = 0.f;
-      for (int i = lane; i < G; i += 32) p = fmaf(da_s[buf][r][i], __ldg(ex.Kz + (size_t)zz * G + i), p);
+      for (int i = lane; i < G; i += 32) p = fmaf(da_s[buf][i][r], __ldg(ex.Kz + (size_t)zz * G + i), p);
       p = warp_sum(p);
       if (lane == 0) emit_dz(ex, ((size_t)(b0 + r) * L + t), zz, Z, p);
     }
@@ -433,8 +483,8 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
     if (is_u && lane_on && r < nrows) {
       float* ap = dAsum + (size_t)(b0 + r) * G + j;
       ap[0] = asum[p][0]; ap[H] = asum[p][1]; ap[2 * H] = asum[p][2]; ap[3 * H] = asum[p][3];
-      float* ds = &da_s[0][r][j];
-      ds[0] = asum[p][0]; ds[H] = asum[p][1]; ds[2 * H] = asum[p][2]; ds[3 * H] = asum[p][3];
+      float* ds = &da_s[0][j][r];
+      ds[0] = asum[p][0]; ds[H * RC] = asum[p][1]; ds[2 * H * RC] = asum[p][2]; ds[3 * H * RC] = asum[p][3];
     }
   }
   if (ex.dW_ext) {   // dW[b,:] (+)= (sum_t da[b,t,:]) @ Ww^T : gradient to the simplex W
@@ -442,7 +492,7 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
     for (int pc = wid; pc < nrows * ex.C; pc += nwarps) {
       const int r = pc / ex.C, cc = pc - r * ex.C;
       float p = 0.f;
-      for (int i = lane; i < G; i += 32) p = fmaf(da_s[0][r][i], __ldg(ex.Ww + (size_t)cc * G + i), p);
+      for (int i = lane; i < G; i += 32) p = fmaf(da_s[0][i][r], __ldg(ex.Ww + (size_t)cc * G + i), p);
       p = warp_sum(p);
       if (lane == 0) {
         float* o = ex.dW_ext + (size_t)(b0 + r) * ex.C + cc;
