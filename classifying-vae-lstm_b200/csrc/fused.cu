@@ -56,20 +56,21 @@ xhead_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const fl
       h_s[k * XRP + rr] = (r < R) ? __ldg(h + r * XD + k) : 0.f;
     }
     __syncthreads();
-    float acc[8];
+    float2 acc2[4];               // row pairs: FFMA2
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = b;
+    for (int i = 0; i < 4; ++i) acc2[i] = make_float2(b, b);
 #pragma unroll 4
     for (int k = 0; k < XD; ++k) {
       const float w = K_s[k * XD + j];
       const float4 h0 = *reinterpret_cast<const float4*>(h_s + k * XRP + rq * 8);
       const float4 h1 = *reinterpret_cast<const float4*>(h_s + k * XRP + rq * 8 + 4);
-      acc[0] = fmaf(h0.x, w, acc[0]); acc[1] = fmaf(h0.y, w, acc[1]);
-      acc[2] = fmaf(h0.z, w, acc[2]); acc[3] = fmaf(h0.w, w, acc[3]);
-      acc[4] = fmaf(h1.x, w, acc[4]); acc[5] = fmaf(h1.y, w, acc[5]);
-      acc[6] = fmaf(h1.z, w, acc[6]); acc[7] = fmaf(h1.w, w, acc[7]);
+      ffma2(acc2[0], w, make_float2(h0.x, h0.y)); ffma2(acc2[1], w, make_float2(h0.z, h0.w));
+      ffma2(acc2[2], w, make_float2(h1.x, h1.y)); ffma2(acc2[3], w, make_float2(h1.z, h1.w));
     }
     __syncthreads();   // all reads of the h tile done; it becomes the dlogits tile
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[2 * i] = acc2[i].x; acc[2 * i + 1] = acc2[i].y; }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int64_t r = row0 + rq * 8 + i;
@@ -92,21 +93,19 @@ xhead_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const fl
     __syncthreads();   // the dlogits tile is complete
     // dh[r][k] = sum_d dlogits[r][d] * Kx[k][d]
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 4; ++i) acc2[i] = make_float2(0.f, 0.f);
 #pragma unroll 4
     for (int d = 0; d < XD; ++d) {
       const float w = KT_s[d * XD + j];
       const float4 g0 = *reinterpret_cast<const float4*>(h_s + d * XRP + rq * 8);
       const float4 g1 = *reinterpret_cast<const float4*>(h_s + d * XRP + rq * 8 + 4);
-      acc[0] = fmaf(g0.x, w, acc[0]); acc[1] = fmaf(g0.y, w, acc[1]);
-      acc[2] = fmaf(g0.z, w, acc[2]); acc[3] = fmaf(g0.w, w, acc[3]);
-      acc[4] = fmaf(g1.x, w, acc[4]); acc[5] = fmaf(g1.y, w, acc[5]);
-      acc[6] = fmaf(g1.z, w, acc[6]); acc[7] = fmaf(g1.w, w, acc[7]);
+      ffma2(acc2[0], w, make_float2(g0.x, g0.y)); ffma2(acc2[1], w, make_float2(g0.z, g0.w));
+      ffma2(acc2[2], w, make_float2(g1.x, g1.y)); ffma2(acc2[3], w, make_float2(g1.z, g1.w));
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int64_t r = row0 + rq * 8 + i;
-      if (r < R) dh[r * XD + j] = acc[i];
+      if (r < R) dh[r * XD + j] = (i & 1) ? acc2[i >> 1].y : acc2[i >> 1].x;
     }
   }
   const float t = block_sum(lsum, red);
@@ -144,9 +143,9 @@ xhead2_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const f
       h_s[k * XRP2 + rr] = (r < R) ? __ldg(h + r * XD + k) : 0.f;
     }
     __syncthreads();
-    float a0[8], a1[8];
+    float2 ac[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a0[i] = b0; a1[i] = b1; }
+    for (int i = 0; i < 8; ++i) ac[i] = make_float2(b0, b1);
 #pragma unroll 4
     for (int k = 0; k < XD; ++k) {
       const float2 w = *reinterpret_cast<const float2*>(K_s + k * XD + j0);
@@ -154,8 +153,11 @@ xhead2_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const f
       const float4 h1 = *reinterpret_cast<const float4*>(h_s + k * XRP2 + rq * 8 + 4);
       const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { a0[i] = fmaf(hv[i], w.x, a0[i]); a1[i] = fmaf(hv[i], w.y, a1[i]); }
+      for (int i = 0; i < 8; ++i) ffma2(ac[i], hv[i], w);       // (column j0, j0+1) pair: one FFMA2
     }
+    float a0[8], a1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a0[i] = ac[i].x; a1[i] = ac[i].y; }
     __syncthreads();   // all reads of the h tile done; it becomes the dlogits tile
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -187,7 +189,7 @@ xhead2_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const f
     __syncthreads();   // the dlogits tile is complete
     // dh[r][k] = sum_d dlogits[r][d] * Kx[k][d], this thread: k = j0, j0 + 1
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a0[i] = 0.f; a1[i] = 0.f; }
+    for (int i = 0; i < 8; ++i) ac[i] = make_float2(0.f, 0.f);
 #pragma unroll 4
     for (int d = 0; d < XD; ++d) {
       const float2 w = *reinterpret_cast<const float2*>(KT_s + d * XD + j0);
@@ -195,12 +197,12 @@ xhead2_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const f
       const float4 g1 = *reinterpret_cast<const float4*>(h_s + d * XRP2 + rq * 8 + 4);
       const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { a0[i] = fmaf(gv[i], w.x, a0[i]); a1[i] = fmaf(gv[i], w.y, a1[i]); }
+      for (int i = 0; i < 8; ++i) ffma2(ac[i], gv[i], w);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int64_t r = row0 + rq * 8 + i;
-      if (r < R) *reinterpret_cast<float2*>(dh + r * XD + j0) = make_float2(a0[i], a1[i]);
+      if (r < R) *reinterpret_cast<float2*>(dh + r * XD + j0) = ac[i];
     }
   }
   const float t = block_sum(lsum, red);

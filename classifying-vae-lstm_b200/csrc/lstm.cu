@@ -62,20 +62,6 @@ constexpr int ZQ = 8;     // latent dimensions folded into the backward mat-vec 
 // the threads, and the cross-lane reduction is a reduce-scatter that leaves each lane with exactly
 // the one (row, unit) cell whose state it owns in registers.
 
-// Two fp32 FMAs in one instruction (Blackwell FFMA2, PTX fma.rn.f32x2): acc.{x,y} += s * v.{x,y}.  ptxas
-// folds the scalar into a broadcast operand (FFMA2 R, Rs.F32, Rv.F32x2, Racc.F32x2): no packing
-// moves, the same round-to-nearest result per lane, half the issue slots of two FFMAs -- which is
-// what these issue-bound mat-vecs need.  The smem operands are laid out [k][row] so that the rows of
-// one k arrive as the register pair(s) of one LDS.
-__device__ __forceinline__ void ffma2(float2& acc, const float s, const float2 v) {
-  unsigned long long a, b, c, r;
-  asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(s));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(v.x), "f"(v.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc.x), "f"(acc.y));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(r));
-}
-
 // Sum v[0..N) over the lane group {lane ^ m : m < 2N} so that the lane whose low bits are e ends
 // with the total of element e (N shuffles instead of N log N).
 template <int N>

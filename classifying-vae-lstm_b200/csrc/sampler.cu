@@ -49,17 +49,17 @@ __device__ __forceinline__ void gate_rows(float (&acc)[4][BT], const float* __re
   // acc[g][:] += W[row][g*H + j] * state[:]   for the 4 gates
   const float w0 = __ldg(Wrow + j), w1 = __ldg(Wrow + SH + j), w2 = __ldg(Wrow + 2 * SH + j),
               w3 = __ldg(Wrow + 3 * SH + j);
+  const float wg[4] = {w0, w1, w2, w3};
 #pragma unroll
   for (int q = 0; q < BT / 4; ++q) {
     const float4 v = *reinterpret_cast<const float4*>(srow + 4 * q);
-    acc[0][4 * q] = fmaf(w0, v.x, acc[0][4 * q]); acc[0][4 * q + 1] = fmaf(w0, v.y, acc[0][4 * q + 1]);
-    acc[0][4 * q + 2] = fmaf(w0, v.z, acc[0][4 * q + 2]); acc[0][4 * q + 3] = fmaf(w0, v.w, acc[0][4 * q + 3]);
-    acc[1][4 * q] = fmaf(w1, v.x, acc[1][4 * q]); acc[1][4 * q + 1] = fmaf(w1, v.y, acc[1][4 * q + 1]);
-    acc[1][4 * q + 2] = fmaf(w1, v.z, acc[1][4 * q + 2]); acc[1][4 * q + 3] = fmaf(w1, v.w, acc[1][4 * q + 3]);
-    acc[2][4 * q] = fmaf(w2, v.x, acc[2][4 * q]); acc[2][4 * q + 1] = fmaf(w2, v.y, acc[2][4 * q + 1]);
-    acc[2][4 * q + 2] = fmaf(w2, v.z, acc[2][4 * q + 2]); acc[2][4 * q + 3] = fmaf(w2, v.w, acc[2][4 * q + 3]);
-    acc[3][4 * q] = fmaf(w3, v.x, acc[3][4 * q]); acc[3][4 * q + 1] = fmaf(w3, v.y, acc[3][4 * q + 1]);
-    acc[3][4 * q + 2] = fmaf(w3, v.z, acc[3][4 * q + 2]); acc[3][4 * q + 3] = fmaf(w3, v.w, acc[3][4 * q + 3]);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {   // song pairs: two FFMA2 instead of four FFMA
+      float2 lo = make_float2(acc[g][4 * q], acc[g][4 * q + 1]), hi = make_float2(acc[g][4 * q + 2], acc[g][4 * q + 3]);
+      ffma2(lo, wg[g], make_float2(v.x, v.y));
+      ffma2(hi, wg[g], make_float2(v.z, v.w));
+      acc[g][4 * q] = lo.x; acc[g][4 * q + 1] = lo.y; acc[g][4 * q + 2] = hi.x; acc[g][4 * q + 3] = hi.y;
+    }
   }
 }
 
@@ -184,8 +184,10 @@ __global__ void __launch_bounds__(SAMP_T, 4) vrnn_sample_kernel(const VrnnSampAr
 #pragma unroll
         for (int q = 0; q < BT / 4; ++q) {
           const float4 v = *reinterpret_cast<const float4*>(&hdT[k][4 * q]);
-          lo[4 * q] = fmaf(wk, v.x, lo[4 * q]); lo[4 * q + 1] = fmaf(wk, v.y, lo[4 * q + 1]);
-          lo[4 * q + 2] = fmaf(wk, v.z, lo[4 * q + 2]); lo[4 * q + 3] = fmaf(wk, v.w, lo[4 * q + 3]);
+          float2 l0 = make_float2(lo[4 * q], lo[4 * q + 1]), l1 = make_float2(lo[4 * q + 2], lo[4 * q + 3]);
+          ffma2(l0, wk, make_float2(v.x, v.y));
+          ffma2(l1, wk, make_float2(v.z, v.w));
+          lo[4 * q] = l0.x; lo[4 * q + 1] = l0.y; lo[4 * q + 2] = l1.x; lo[4 * q + 3] = l1.y;
         }
       }
 #pragma unroll
