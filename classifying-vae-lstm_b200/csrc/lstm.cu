@@ -121,12 +121,19 @@ lstm_fwd_kernel(float* __restrict__ gates, const float* __restrict__ U, float* _
   for (int p = 0; p < NP; ++p) {
     const int r = p * RC + q;
     const bool on = lane_on && r < nrows;
+    // all loads of the W term issued at once (C <= 16): with a runtime-bounded loop every iteration
+    // waited a full L2 round trip -- 6 000 cycles of prologue on the step's critical path
+    constexpr int CM = 16;
+    const bool wterm = ex.Wv && on;
+    float wv[CM];
+#pragma unroll
+    for (int c = 0; c < CM; ++c) wv[c] = (wterm && c < ex.C) ? __ldg(ex.Wv + (size_t)(b0 + r) * ex.C + c) : 0.f;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float v = ex.bias ? __ldg(ex.bias + g * H + j) : 0.f;
-      if (ex.Wv && on)
-        for (int c = 0; c < ex.C; ++c)
-          v = fmaf(__ldg(ex.Wv + (size_t)(b0 + r) * ex.C + c), __ldg(ex.Ww + (size_t)c * G + g * H + j), v);
+#pragma unroll
+      for (int c = 0; c < CM; ++c)
+        if (wterm && c < ex.C) v = fmaf(wv[c], __ldg(ex.Ww + (size_t)c * G + g * H + j), v);
       cb[p][g] = v;
     }
     creg[p] = (on && c0) ? c0[(size_t)(b0 + r) * H + j] : 0.f;
@@ -478,7 +485,11 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ U, const fl
     for (int pc = wid; pc < nrows * ex.C; pc += nwarps) {
       const int r = pc / ex.C, cc = pc - r * ex.C;
       float p = 0.f;
-      for (int i = lane; i < G; i += 32) p = fmaf(da_s[0][i][r], __ldg(ex.Ww + (size_t)cc * G + i), p);
+#pragma unroll
+      for (int i0 = 0; i0 < G; i0 += 32) {      // G / 32 = 11 independent loads in flight
+        const int i = i0 + lane;
+        p = fmaf(da_s[0][i][r], __ldg(ex.Ww + (size_t)cc * G + i), p);
+      }
       p = warp_sum(p);
       if (lane == 0) {
         float* o = ex.dW_ext + (size_t)(b0 + r) * ex.C + cc;
@@ -499,7 +510,7 @@ int pick_rows(int B) {
 int lstm_fwd_launch(float* gates, const float* U, float* h, float* c, const float* h0,
                     const float* c0, int B, int L, int H, const LstmExtra& ex, cudaStream_t st) {
   if (!gates || !U || !h || !c) return CLV_E_INVALID;
-  if (H != 88 || ex.Z > ZMAX) return CLV_E_UNSUPPORTED;
+  if (H != 88 || ex.Z > ZMAX || (ex.Wv && ex.C > 16)) return CLV_E_UNSUPPORTED;
   if (B <= 0 || L <= 0) return CLV_OK;
   const int R = pick_rows(B);
   const int grid = (B + R - 1) / R;
