@@ -229,7 +229,11 @@ keyenc_fwd_kernel(const uint8_t* __restrict__ roll, const int32_t* __restrict__ 
   __shared__ int cnt_s[KT + 1];
   __shared__ float hw_s[128];
   __shared__ float wa_s[32];
+  __shared__ float kwa_s[128 * 30];    // the Wargs kernel [D, 2(C-1)]: staged up front, its L2 round trip
+                                       // hides behind the window compaction (a global load per k of the
+                                       // 88-long dot product below cost ~6 us of serialised latency)
   const int tid = threadIdx.x, b = blockIdx.x;
+  for (int i = tid; i < D * 2 * (C - 1); i += KT) kwa_s[i] = __ldg(Kwa + i);
   const uint32_t* src = reinterpret_cast<const uint32_t*>(roll + ((size_t)__ldg(off + b) + shift) * D);
   for (int i = tid; i < nwords; i += KT) win_s[i] = __ldg(src + i);
   __syncthreads();
@@ -293,7 +297,7 @@ keyenc_fwd_kernel(const uint8_t* __restrict__ roll, const int32_t* __restrict__ 
   const int C1 = C - 1, NW = 2 * C1;
   if (tid < NW) {
     float a = __ldg(bwa + tid);
-    for (int k = 0; k < D; ++k) a = fmaf(hw_s[k], __ldg(Kwa + (size_t)k * NW + tid), a);
+    for (int k = 0; k < D; ++k) a = fmaf(hw_s[k], kwa_s[k * NW + tid], a);
     wa_s[tid] = a;
     Wargs[(size_t)b * NW + tid] = a;
   }
@@ -414,8 +418,10 @@ keyenc_bwd_full_kernel(const uint8_t* __restrict__ roll, const int32_t* __restri
   __shared__ float dwa_s[32];
   __shared__ float dhw_s[128];
   __shared__ float hw_s[128];
+  __shared__ float kwa_s[128 * 30];    // Wargs kernel, staged before the dependency wait
   const int tid = threadIdx.x, b = blockIdx.x;
   const int C1 = C - 1, NW = 2 * C1;
+  for (int i = tid; i < D * NW; i += KT) kwa_s[i] = __ldg(Kwa + i);
   const uint32_t* src = reinterpret_cast<const uint32_t*>(roll + ((size_t)__ldg(off + b) + shift) * D);
   for (int i = tid; i < nwords; i += KT) win_s[i] = __ldg(src + i);
   if (tid < D) hw_s[tid] = __ldg(hW + (size_t)b * D + tid);
@@ -466,7 +472,7 @@ keyenc_bwd_full_kernel(const uint8_t* __restrict__ roll, const int32_t* __restri
   // ---- dhW = (dWargs @ Kwa^T) * [hW > 0];  bias gradients
   if (tid < D) {
     float a = 0.f;
-    for (int o = 0; o < NW; ++o) a = fmaf(dwa_s[o], __ldg(Kwa + (size_t)tid * NW + o), a);
+    for (int o = 0; o < NW; ++o) a = fmaf(dwa_s[o], kwa_s[tid * NW + o], a);
     a = (hw_s[tid] > 0.f) ? a : 0.f;
     dhw_s[tid] = a;
     dhW[(size_t)b * D + tid] = a;
