@@ -159,14 +159,26 @@ xhead2_kernel(const float* __restrict__ h, const float* __restrict__ Kx, const f
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a0[i] = ac[i].x; a1[i] = ac[i].y; }
     __syncthreads();   // all reads of the h tile done; it becomes the dlogits tile
+    // the two target keys of each row first (two dependent global loads each: window offset -> key
+    // bytes), so their latencies overlap instead of chaining through the loop below (measured: helps
+    // here, hurts the small-R kernel above)
+    uint32_t xk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = row0 + rq * 8 + i;
+      xk[i] = 0u;
+      if (r < R) {
+        const uint32_t g = (uint32_t)r / (uint32_t)x_grp;
+        const int64_t xrow = (int64_t)__ldg(x_off + g) + x_shift + (int64_t)((uint32_t)r - g * (uint32_t)x_grp);
+        xk[i] = *reinterpret_cast<const uint16_t*>(roll + xrow * XD + j0);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int64_t r = row0 + rq * 8 + i;
       float d0 = 0.f, d1 = 0.f;
       if (r < R) {
-        const int64_t g = r / x_grp;
-        const int64_t xrow = (int64_t)__ldg(x_off + g) + x_shift + (r - g * x_grp);
-        const uint32_t xx = *reinterpret_cast<const uint16_t*>(roll + xrow * XD + j0);   // 2 keys
+        const uint32_t xx = xk[i];   // 2 keys
         const float x[2] = {(float)(xx & 0xffu), (float)(xx >> 8)};
         const float lg[2] = {a0[i], a1[i]};
         float dl[2];
@@ -516,7 +528,7 @@ extern "C" int clv_xhead_fwd_bwd(const float* h, const float* Kx, const float* b
                                  int32_t H, int32_t D, float scale, int32_t do_backward, void* stream) {
   if (!h || !Kx || !bx || !roll || !x_off || !loss_acc || x_grp <= 0) return CLV_E_INVALID;
   if (do_backward && (!dlogits || !dh)) return CLV_E_INVALID;
-  if (H != XD || D != XD) return CLV_E_UNSUPPORTED;
+  if (H != XD || D != XD || R >= (1LL << 32)) return CLV_E_UNSUPPORTED;
   if (R <= 0) return CLV_OK;
   const size_t smem = sizeof(float) * (2 * XD * XD + XD * XRP);
   static bool attr_set = false;
@@ -569,7 +581,9 @@ extern "C" int clv_keyenc_fwd(const uint8_t* roll, const int32_t* win_off, int32
   if (gen_noise && !ctr) return CLV_E_INVALID;
   if (B <= 0) return CLV_OK;
   const size_t smem = (size_t)L * D + 2 * (size_t)L * D + 16;
-  static size_t attr_smem = 48 * 1024;
+  // opt in above 28 KB of dynamic smem: the kernel also has ~17 KB static (staged Wargs kernel), and
+  // static + dynamic beyond 48 KB needs the attribute
+  static size_t attr_smem = 28 * 1024;
   if (smem > attr_smem) {
     if (smem > 227 * 1024) return CLV_E_UNSUPPORTED;
     CLV_CUDA(cudaFuncSetAttribute(keyenc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -612,7 +626,9 @@ extern "C" int clv_keyenc_bwd_full(const uint8_t* roll, const int32_t* win_off, 
   if (C < 2 || C > 16 || D > 128 || (D & 3) || (int64_t)L * D > 65535) return CLV_E_UNSUPPORTED;
   if (B <= 0) return CLV_OK;
   const size_t smem = (size_t)L * D + 2 * (size_t)L * D + 16;
-  static size_t attr_smem = 48 * 1024;
+  // opt in above 28 KB of dynamic smem: the kernel also has ~17 KB static (staged Wargs kernel), and
+  // static + dynamic beyond 48 KB needs the attribute
+  static size_t attr_smem = 28 * 1024;
   if (smem > attr_smem) {
     if (smem > 227 * 1024) return CLV_E_UNSUPPORTED;
     CLV_CUDA(cudaFuncSetAttribute(keyenc_bwd_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

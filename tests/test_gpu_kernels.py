@@ -311,7 +311,7 @@ def test_xhead_fused_matches_gemm_plus_bernoulli(R, grp):
     assert util.rel_err(dh.cpu().numpy(), dh_ref) < TOL
 
 
-@pytest.mark.parametrize("B_,Lq,Cc,dens", [(200, 16, 10, 0.05), (7, 3, 2, 0.5), (3, 64, 16, 0.0)])
+@pytest.mark.parametrize("B_,Lq,Cc,dens", [(200, 16, 10, 0.05), (7, 3, 2, 0.5), (3, 64, 16, 0.0), (5, 128, 10, 0.004)])   # last: 34 KB dynamic + 17 KB static smem (opt-in path)
 def test_keyenc_fused_fwd_bwd(B_, Lq, Cc, dens):
     _lib, L, check, ptr, st = _env()
     rng = np.random.default_rng(B_ + Lq)
