@@ -28,6 +28,36 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert L.clv_error_string(-2).decode().startswith("unsupported")
 
 
+def _c_kind(decl):
+    """Coarse ctypes class of one C parameter declaration."""
+    d = decl.strip()
+    if "*" in d:
+        return "ptr"
+    t = d.rsplit(None, 1)[0] if " " in d else d
+    return {"int32_t": "i32", "int": "i32", "int64_t": "i64", "uint64_t": "u64", "float": "f32",
+            "double": "f64"}.get(t.replace("const ", "").strip(), t)
+
+
+def test_ctypes_prototypes_match_the_header_signatures():
+    """Every entry point: the number of parameters and the class of each (pointer / int32 / int64 /
+    uint64 / float / double) in include/clv_b200.h equals the ctypes prototype of _lib.py (an
+    argument added on one side only is silent memory corruption at call time)."""
+    src = open(os.path.join(ROOT, "include", "clv_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    kinds = {ctypes.c_int32: "i32", ctypes.c_int: "i32", ctypes.c_int64: "i64", ctypes.c_uint64: "u64",
+             ctypes.c_float: "f32", ctypes.c_double: "f64", ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr"}
+    checked = 0
+    for m in re.finditer(r"\b(?:int|int64_t|const char\*)\s+(clv_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        name, params = m.group(1), m.group(2).strip()
+        want = [] if params in ("", "void") else [_c_kind(p) for p in params.split(",")]
+        restype, argtypes = _lib.PROTOTYPES[name]
+        got = [kinds.get(a, "ptr" if hasattr(a, "contents") or "LP_" in getattr(a, "__name__", "") else str(a))
+               for a in argtypes]
+        assert got == want, (name, got, want)
+        checked += 1
+    assert checked >= 30
+
+
 def test_param_layout_matches_oracle_tables():
     for (L_, C, Z, xp) in [(16, 10, 2, True), (16, 10, 2, False), (32, 12, 4, True)]:
         cfg = _lib.make_cfg(0, 200, L_, 88, 88, Z, C, xp)
