@@ -411,16 +411,19 @@ def main():
     # teardown: NCCL kernels captured in CUDA graphs must be released before the communicator goes
     # away; a watchdog guarantees the process exits even if the communicator teardown stalls
     sys.stdout.flush()
+    torch.cuda.synchronize()
     if world > 1:
         import threading
-        threading.Timer(30.0, lambda: os._exit(0)).start()
-        torch.cuda.synchronize()
+        wd = threading.Timer(60.0, lambda: os._exit(0))   # fallback only: fires if the NCCL teardown stalls
+        wd.daemon = True
+        wd.start()
         dist.barrier()
         e._graphs.clear()
         del model
         torch.cuda.synchronize()
         dist.destroy_process_group()
-    os._exit(0)
+        wd.cancel()
+    # normal return: interpreter exit hooks (atexit, the harness's loaded-library record) run
 
 
 if __name__ == "__main__":

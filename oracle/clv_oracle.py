@@ -193,10 +193,11 @@ def categorical_accuracy(w_true, w):
 # CL-VRNN training graph (cl_vrnn/model.py:164-267)
 # --------------------------------------------------------------------------------------
 def vrnn_forward(p, X, Xp, w_true, eps_w, eps_z, C, use_x_prev, class_weight=1.0, kl_weight=1.0,
-                 w_kl_weight=1.0, w_log_var_prior=0.0):
+                 w_kl_weight=1.0, w_log_var_prior=0.0, Y=None):
     """X=current [B,L,D], Xp=history [B,L,D] or None, w_true one-hot [B,C], eps_w [B,C-1],
-    eps_z [B,L,Z].  Returns dict with total loss, the 4 per-output mean losses, accuracy and
-    intermediates."""
+    eps_z [B,L,Z]; Y = reconstruction target (cl_vrnn/train.py:51-63: y == current except with
+    --predict_next, where the input is frames 0..L-1 and the target frames 1..L).  Returns dict with
+    total loss, the 4 per-output mean losses, accuracy and intermediates."""
     B, L, D = X.shape
     hW = torch.relu(X.reshape(B, L * D) @ p["hW.kernel"] + p["hW.bias"])          # model.py:174
     Wargs = hW @ p["Wargs.kernel"] + p["Wargs.bias"]                              # model.py:175
@@ -215,7 +216,7 @@ def vrnn_forward(p, X, Xp, w_true, eps_w, eps_z, C, use_x_prev, class_weight=1.0
     logits = h_d @ p["X_decoded_mean.kernel"] + p["X_decoded_mean.bias"]
     P = torch.sigmoid(logits)                                                     # model.py:229-234
     W2 = W + 1e-10                                                                # model.py:255
-    l_vae = vae_loss(X, P, D).mean()
+    l_vae = vae_loss(X if Y is None else Y, P, D).mean()
     l_wkl = w_kl_loss(W_mean, W_log_var, w_log_var_prior).mean()
     l_wrec = w_rec_loss(w_true, W2, C).mean()
     l_zkl = z_kl_loss(Z_mean, Z_log_var).mean()

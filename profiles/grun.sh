@@ -1,0 +1,10 @@
+#!/bin/bash
+# gpurun wrapper: retries while the pod answers "busy" (exit 3).  usage: profiles/grun.sh LOG [gpurun args...]
+log=$1; shift
+for i in $(seq 1 30); do
+  /usr/local/graft/bin/gpurun "$@" > "$log" 2>&1
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  sleep 90
+done
+exit 3

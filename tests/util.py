@@ -76,3 +76,49 @@ def engine_for(case, model, **kw):
     e.eps_w.copy_(torch.tensor(case["eps_w"], dtype=torch.float32).reshape(-1))
     e.eps_z.copy_(torch.tensor(case["eps_z"], dtype=torch.float32).reshape(-1))
     return e
+
+
+# ---------------------------------------------------------------------------------- golden fixtures
+def golden_weight(seed, name, shape, scale=1.0):
+    """Weights of the tests/golden/*_train.npz / *_sampler.npz cases: regenerated from (seed, tensor
+    name) instead of being stored (random float32 does not compress); the fixture keeps a SHA-256 of
+    each tensor so a drift of the numpy stream is caught.  Non-default values so that every branch is
+    exercised (hard-sigmoid clips, relu on/off, non-zero biases); float32-representable."""
+    import zlib
+    rng = np.random.default_rng([int(seed), zlib.crc32(name.encode())])
+    layer, wname = name.rsplit(".", 1)
+    if wname == "bias":
+        s = 0.25
+    else:
+        s = scale * 0.9 / np.sqrt(max(shape[0], 1))
+        if layer in ("Z_mean", "Z_log_var", "z_mean", "z_log_var", "Wargs", "w_mean", "w_log_var"):
+            s *= 0.5
+    return rng.normal(0, s, shape).astype(np.float32)
+
+
+def sha256(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def load_golden(fname):
+    import json, os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", fname))
+    cases = {}
+    for k in z.files:
+        case, rest = k.split("/", 1)
+        cases.setdefault(case, {})[rest] = z[k]
+    for c in cases.values():
+        c["cfg"] = json.loads(str(c["cfg"]))
+    return cases
+
+
+def golden_params(case, names_shapes, prefix=""):
+    """regenerate + verify the weights of one golden case; names_shapes: [(tensor name, shape)]"""
+    cfg = case["cfg"]
+    out = {}
+    for name, shape in names_shapes:
+        w = golden_weight(cfg["wseed"], prefix + name, shape, cfg["wscale"])
+        assert sha256(w) == cfg["wsha"][prefix + name], "numpy stream drift: regenerate tests/golden"
+        out[name] = w
+    return out
