@@ -24,6 +24,7 @@ class clv_cfg(C.Structure):
                 ("w_log_var_prior", C.c_float),
                 ("gen_noise", C.c_int32), ("do_backward", C.c_int32), ("accumulate", C.c_int32),
                 ("gemm_algo", C.c_int32), ("x_shift", C.c_int32), ("gemm_algo_tc_lstm_min", C.c_int32), ("overlap_wgrad", C.c_int32),
+                ("y_shift", C.c_int32), ("reserved0", C.c_int32),
                 ("seed", C.c_uint64)]
 
 
@@ -131,13 +132,13 @@ def ptr(t):
 
 def make_cfg(model, B, L, D, H, Z, C_, use_x_prev, Hc=0, B_global=None, class_weight=1.0,
              kl_weight=1.0, w_kl_weight=1.0, w_log_var_prior=0.0, gen_noise=0, do_backward=1,
-             accumulate=0, gemm_algo=0, seed=0, x_shift=0, overlap_wgrad=0, tc_lstm_min=0):
+             accumulate=0, gemm_algo=0, seed=0, x_shift=0, overlap_wgrad=0, tc_lstm_min=0, y_shift=0):
     return clv_cfg(model=model, B=B, B_global=B if B_global is None else B_global, L=L, D=D, H=H,
                    Hc=Hc, Z=Z, C=C_, use_x_prev=int(bool(use_x_prev)), class_weight=class_weight,
                    kl_weight=kl_weight, w_kl_weight=w_kl_weight, w_log_var_prior=w_log_var_prior,
                    gen_noise=gen_noise, do_backward=do_backward, accumulate=accumulate,
                    gemm_algo=gemm_algo, x_shift=x_shift, gemm_algo_tc_lstm_min=tc_lstm_min,
-                   overlap_wgrad=overlap_wgrad, seed=seed)
+                   overlap_wgrad=overlap_wgrad, y_shift=y_shift, seed=seed)
 
 
 def param_layout(cfg):

@@ -12,6 +12,7 @@ from .. import _lib
 from .._lib import lib, check, ptr
 from ..engine import Engine, _stream
 from ..keras_like import BaseModel, _binary_u8
+from ..devops import dense, as_dev_f32
 from ..cl_vrnn.model import sample_w, sample_z  # identical numpy helpers (cl_vae/model.py:47-74)
 
 
@@ -40,9 +41,17 @@ class CLVAE(BaseModel):
                                 + (["concatenate_2"] if xp else []) + ["concatenate_3", "decoder_h",
                                  "x_decoded_mean", "w2", "z_args"])
 
-    def _windows_from_inputs(self, x):
-        """[x, history] ([n, D] each) -> uint8 windows [n, 2, D] = [history | x]; x alone -> [n,1,D]."""
+    def _overlaps(self, x, y=None):
+        return True            # one storage form only: [history | x] / [x | y] / [x]
+
+    def _windows_from_inputs(self, x, y=None, overlap=None):
+        """[x, history] ([n, D] each) -> uint8 windows [n, 2, D] = [history | x]; x alone -> [n,1,D];
+        --predict_next (cl_vae/train.py:18,63-69): [x | y] with the target y[0] = the next frame."""
         e = self.engine
+        if e.predict_next:
+            cur = _binary_u8(x[0] if isinstance(x, (list, tuple)) else x, "x")
+            tgt = cur if y is None else _binary_u8(y[0], "target")
+            return np.ascontiguousarray(np.stack([cur, tgt], axis=1))
         if e.use_x_prev:
             cur, hist = _binary_u8(x[0], "x"), _binary_u8(x[1], "history")
             return np.ascontiguousarray(np.stack([hist, cur], axis=1))
@@ -65,6 +74,7 @@ def get_model(batch_size, original_dim, latent_dims, class_dims, optimizer, clas
                       epsilon=optimizer.epsilon)
     seed = engine_kw.pop("seed", None)
     seed = np.random.randint(0, 2 ** 31 - 1) if seed is None else seed
+    engine_kw["predict_next"] = bool(engine_kw.pop("predict_next", False))
     eng = Engine("vae", batch_size, L=1, D=int(original_dim), H=latent_dim_0, Z=latent_dim,
                  n_classes=class_dim, use_x_prev=use_x_prev, Hc=class_dim_0,
                  class_weight=float(class_weight), kl_weight=float(kl_weight),
@@ -93,8 +103,25 @@ def load_model(model_file, optimizer='adam', batch_size=1, no_x_prev=False):
 
 
 class EncModel:
+    """`enc_model = Model([x, xp], [z_mean, w_mean])` (cl_vae/model.py:213-222): forward only, same weights
+    (w inside the graph is the sampled simplex, so z_mean depends on this call's noise draw)."""
     def __init__(self, model):
         self.model = model
+
+    def predict(self, x, batch_size=None):
+        e = self.model.engine
+        win = self.model._windows_from_inputs(x)
+        n = win.shape[0]
+        if n % e.B:
+            raise ValueError("the graph has a static batch size (%d): got %d samples" % (e.B, n))
+        lab = torch.zeros(e.B, dtype=torch.int32)
+        zm, wm = [], []
+        for i in range(0, n, e.B):
+            e.stage_windows(torch.from_numpy(np.ascontiguousarray(win[i:i + e.B])), lab)
+            e.run(train=False, gen_noise=True)
+            zm.append(e.ws_view("Zargs", (e.B, 2 * e.Z)).cpu().numpy()[:, :e.Z].copy())
+            wm.append(e.ws_view("Wargs", (e.B, 2 * (e.C - 1))).cpu().numpy()[:, :e.C - 1].copy())
+        return [np.concatenate(zm), np.concatenate(wm)]
 
 
 class _Sub:
@@ -105,16 +132,49 @@ class _Sub:
         pass
 
 
+class WEncoder(_Sub):
+    """make_w_encoder (cl_vae/model.py:76-85): x [S, D] -> [w_mean, w_log_var]."""
+    def predict(self, x):
+        e = self.model.engine
+        h_w = dense(as_dev_f32(x, e.dev), e.view("h_w.kernel"), e.view("h_w.bias"), act=1)
+        return [dense(h_w, e.view("w_mean.kernel"), e.view("w_mean.bias")).cpu().numpy(),
+                dense(h_w, e.view("w_log_var.kernel"), e.view("w_log_var.bias")).cpu().numpy()]
+
+
+class ZEncoder(_Sub):
+    """make_z_encoder (cl_vae/model.py:87-102): [x [S,D], w [S,C]] -> [z_mean, z_log_var]."""
+    def predict(self, x):
+        e = self.model.engine
+        xw = torch.cat([as_dev_f32(x[0], e.dev), as_dev_f32(x[1], e.dev)], dim=-1).contiguous()
+        h = dense(xw, e.view("h.kernel"), e.view("h.bias"), act=1)
+        return [dense(h, e.view("z_mean.kernel"), e.view("z_mean.bias")).cpu().numpy(),
+                dense(h, e.view("z_log_var.kernel"), e.view("z_log_var.bias")).cpu().numpy()]
+
+
+class Decoder(_Sub):
+    """make_decoder (cl_vae/model.py:104-128): inputs [w, z, xp] (or [w, z]); the Dense sees [w | xp | z]."""
+    def __init__(self, model, use_x_prev):
+        super().__init__(model)
+        self.use_x_prev = bool(use_x_prev)
+
+    def predict(self, x):
+        e = self.model.engine
+        w, z = as_dev_f32(x[0], e.dev), as_dev_f32(x[1], e.dev)
+        parts = [w] + ([as_dev_f32(x[2], e.dev)] if self.use_x_prev else []) + [z]
+        hd = dense(torch.cat(parts, dim=-1).contiguous(), e.view("decoder_h.kernel"), e.view("decoder_h.bias"), act=1)
+        return dense(hd, e.view("x_decoded_mean.kernel"), e.view("x_decoded_mean.bias"), act=2).cpu().numpy()
+
+
 def make_w_encoder(model, original_dim, batch_size=1):
-    return _Sub(model)
+    return WEncoder(model)
 
 
 def make_z_encoder(model, original_dim, class_dim, latent_dims, batch_size=1):
-    return _Sub(model)
+    return ZEncoder(model)
 
 
 def make_decoder(model, latent_dims, class_dim, original_dim=88, use_x_prev=False, batch_size=1):
-    return _Sub(model)
+    return Decoder(model, use_x_prev)
 
 
 def infer_w_device(model, x_seeds_u8, w_sample=False):
@@ -137,8 +197,9 @@ def infer_w_device(model, x_seeds_u8, w_sample=False):
                                C=Wargs.data_ptr() + 4 * j * C1, ldc=2 * C1,
                                bias=e.view(nm + ".bias").data_ptr(), split_k=1)
         check(lib().clv_gemm(C.byref(a), _stream()), "clv_gemm")
-    eps = (torch.from_numpy(np.random.randn(S, C1).astype(np.float32)).to(e.dev) if w_sample
-           else torch.zeros(S, C1, device=e.dev))
+    # sample_w draws np.random.randn(1, C-1) per frame also with add_noise=False (cl_vae/model.py:47-58)
+    draws = np.stack([np.random.randn(1, C1)[0] for _ in range(S)]).astype(np.float32)
+    eps = torch.from_numpy(draws if w_sample else 0 * draws).to(e.dev)
     W = torch.empty(S, e.C, device=e.dev)
     scratch = torch.zeros(8, device=e.dev)
     labels = torch.zeros(S, dtype=torch.int32, device=e.dev)

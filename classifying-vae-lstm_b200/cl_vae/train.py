@@ -35,8 +35,6 @@ def train(args):
     wtr = to_categorical(P.train_song_keys, args.n_classes)
     wva = to_categorical(P.valid_song_keys, args.n_classes)
     assert not (args.predict_next and args.use_x_prev), "Can't use --predict_next if using --use_x_prev"
-    if args.predict_next:
-        raise NotImplementedError("--predict_next is not built; the README configuration uses --use_x_prev")
     callbacks = get_callbacks(args, patience=args.patience, min_epoch=max(args.kl_anneal, args.w_kl_anneal) + 1,
                               do_log=args.do_log)
     if args.kl_anneal > 0:
@@ -56,7 +54,7 @@ def train(args):
     model, enc_model = get_model(args.batch_size, args.original_dim, (args.intermediate_dim, args.latent_dim),
                                  (args.intermediate_class_dim, args.n_classes), args.optimizer, args.class_weight,
                                  kl_weight, use_x_prev=args.use_x_prev, w_kl_weight=w_kl_weight,
-                                 w_log_var_prior=args.w_log_var_prior)
+                                 w_log_var_prior=args.w_log_var_prior, predict_next=args.predict_next)
     args.optimizer = 'adam-wn' if was_adam_wn else args.optimizer
     os.makedirs(args.model_dir, exist_ok=True)
     save_model_in_pieces(model, args)

@@ -13,6 +13,7 @@ from .. import _lib
 from .._lib import lib, check, ptr
 from ..engine import Engine, _stream
 from ..keras_like import BaseModel, _binary_u8
+from ..devops import dense, as_dev_f32, StatefulLSTM
 
 
 class CLVRNN(BaseModel):
@@ -39,13 +40,41 @@ class CLVRNN(BaseModel):
                                 + (["concatenate_2"] if xp else []) + ["repeat_vector_2", "concatenate_3",
                                  "decoder_h", "X_decoded_mean", "W2", "Z_args"])
 
-    def _windows_from_inputs(self, x):
-        """[current, history] ([n,L,D] each) -> uint8 windows.  PianoData windows overlap
-        (history[:,1:] == current[:,:-1]) -> [n, L+1, D]; otherwise stored as [history | current]."""
+    def _overlaps(self, x, y=None):
+        """True when the two arrays a window is built from are shifted copies of each other (PianoData
+        windows): they are then stored once, as [n, L+1, D]; otherwise as [first | second], [n, 2L, D]."""
         e = self.engine
+        if e.predict_next:
+            if y is None:
+                return True
+            cur = _binary_u8(x[0] if isinstance(x, (list, tuple)) else x, "current")
+            return bool(np.array_equal(cur[:, 1:], _binary_u8(y[0], "target")[:, :-1]))
+        if e.use_x_prev:
+            return bool(np.array_equal(_binary_u8(x[1], "history")[:, 1:], _binary_u8(x[0], "current")[:, :-1]))
+        return True
+
+    def _windows_from_inputs(self, x, y=None, overlap=None):
+        """[current, history] ([n,L,D] each) -> uint8 windows.  PianoData windows overlap
+        (history[:,1:] == current[:,:-1]) -> [n, L+1, D]; otherwise stored as [history | current].
+        --predict_next (cl_vrnn/train.py:55-57): input x = frames 0..L-1, target y[0] = frames 1..L of
+        the same L+1 window (or [x | y] when they do not overlap).  `overlap` forces the storage form
+        (fit decides it once for the training and the validation split)."""
+        e = self.engine
+        if overlap is None:
+            overlap = self._overlaps(x, y)
+        if e.predict_next:
+            cur = _binary_u8(x[0] if isinstance(x, (list, tuple)) else x, "current")
+            tgt = np.concatenate([cur[:, 1:], cur[:, -1:]], axis=1) if y is None else _binary_u8(y[0], "target")
+            if overlap:
+                if (e.W, e.x_shift, e.y_shift) != (e.L + 1, 0, 1):
+                    e.set_window(e.L + 1, 0, 1)
+                return np.ascontiguousarray(np.concatenate([cur[:, :1], tgt], axis=1))
+            if (e.W, e.x_shift, e.y_shift) != (2 * e.L, 0, e.L):
+                e.set_window(2 * e.L, 0, e.L)
+            return np.ascontiguousarray(np.concatenate([cur, tgt], axis=1))
         if e.use_x_prev:
             cur, hist = _binary_u8(x[0], "current"), _binary_u8(x[1], "history")
-            if np.array_equal(hist[:, 1:], cur[:, :-1]):
+            if overlap:
                 if e.x_shift != 0:
                     e.set_window(e.L + 1, 0)
                 return np.ascontiguousarray(np.concatenate([hist[:, :1], cur], axis=1))
@@ -64,6 +93,7 @@ def get_model(batch_size, original_dim, intermediate_dim, latent_dim, seq_length
     X -> [Z_mean, Z_log_var, W] view of the same weights."""
     if dropout:
         raise NotImplementedError("dropout is never set by the reference CLI (cl_vrnn/train.py:46)")
+    predict_next = bool(engine_kw.pop("predict_next", False))
     opt_name = optimizer if isinstance(optimizer, str) else getattr(optimizer, "name", "adam-wn")
     opt_kw = {}
     if not isinstance(optimizer, str):
@@ -74,7 +104,8 @@ def get_model(batch_size, original_dim, intermediate_dim, latent_dim, seq_length
                  n_classes=n_classes, use_x_prev=use_x_prev, class_weight=float(class_weight),
                  kl_weight=float(kl_weight), w_kl_weight=float(w_kl_weight),
                  w_log_var_prior=float(w_log_var_prior), optimizer=opt_name,
-                 seed=np.random.randint(0, 2 ** 31 - 1) if seed is None else seed, **opt_kw, **engine_kw)
+                 seed=np.random.randint(0, 2 ** 31 - 1) if seed is None else seed, predict_next=predict_next,
+                 **opt_kw, **engine_kw)
     eng.init_params(np.random.default_rng(np.random.randint(0, 2 ** 31 - 1) if seed is None else seed))
     margs = dict(batch_size=batch_size, original_dim=original_dim, intermediate_dim=intermediate_dim,
                  latent_dim=latent_dim, seq_length=seq_length, n_classes=n_classes,
@@ -98,8 +129,29 @@ def load_model(model_file, batch_size=None, seq_length=None, optimizer='adam'):
 
 # ---------------------------------------------------------------------- sampler sub-models
 class EncoderView:
+    """`encoder = Model(X, [Z_mean, Z_log_var, W])` (cl_vrnn/model.py:266): same weights, forward only.
+    W is the SAMPLED simplex (the Lambda draws noise on every call, as in the reference)."""
     def __init__(self, model):
         self.model = model
+
+    def predict(self, x, batch_size=None):
+        e = self.model.engine
+        cur = _binary_u8(x[0] if isinstance(x, (list, tuple)) else x, "current")
+        n = cur.shape[0]
+        if n % e.B:
+            raise ValueError("the graph has a static batch size (%d): got %d samples" % (e.B, n))
+        win = cur if not e.use_x_prev else np.concatenate([np.zeros_like(cur[:, :1]), cur], axis=1)
+        if e.x_shift != 0:
+            e.set_window(e.L + 1 if e.use_x_prev else e.L, 0)
+        lab = torch.zeros(e.B, dtype=torch.int32)
+        zm, zv, w = [], [], []
+        for i in range(0, n, e.B):
+            e.stage_windows(torch.from_numpy(np.ascontiguousarray(win[i:i + e.B])), lab)
+            e.run(train=False, gen_noise=True)
+            za = e.ws_view("Zargs", (e.B, e.L, 2 * e.Z)).cpu().numpy()
+            zm.append(za[..., :e.Z].copy()); zv.append(za[..., e.Z:].copy())
+            w.append(e.ws_view("W", (e.B, e.C)).cpu().numpy().copy())
+        return [np.concatenate(zm), np.concatenate(zv), np.concatenate(w)]
 
 
 class WEncoder:
@@ -118,18 +170,12 @@ class WEncoder:
         C1 = e.C - 1
         off = (torch.arange(M, dtype=torch.int32, device=e.dev) * L).contiguous()
         hW = torch.empty(M, D, device=e.dev)
-        Wargs = torch.empty(M, 2 * C1, device=e.dev)
         a = _lib.clv_gemm_args(M=M, N=D, K=L * D, A=chunks_u8.data_ptr(), lda=D, a_u8=1, a_kmajor=1,
                                a_off=off.data_ptr(), a_grp=1, Bm=e.view("hW.kernel").data_ptr(), ldb=D,
                                b_nmajor=1, C=hW.data_ptr(), ldc=D, bias=e.view("hW.bias").data_ptr(),
                                relu=1, split_k=1)
         check(lib().clv_gemm(C.byref(a), _stream()), "clv_gemm")
-        a = _lib.clv_gemm_args(M=M, N=2 * C1, K=D, A=hW.data_ptr(), lda=D, a_kmajor=1,
-                               Bm=e.view("Wargs.kernel").data_ptr(), ldb=2 * C1, b_nmajor=1,
-                               C=Wargs.data_ptr(), ldc=2 * C1, bias=e.view("Wargs.bias").data_ptr(),
-                               split_k=1)
-        check(lib().clv_gemm(C.byref(a), _stream()), "clv_gemm")
-        return Wargs
+        return dense(hW, e.view("Wargs.kernel"), e.view("Wargs.bias"))
 
     def predict(self, x):
         e = self.model.engine
@@ -138,14 +184,32 @@ class WEncoder:
         return [Wargs[:, :e.C - 1], Wargs[:, e.C - 1:]]
 
 
+class _LstmWeights:
+    """get_layer('encoder_h') of the z-encoder: get_weights / set_weights on its own LSTM tensors."""
+    def __init__(self, owner):
+        self.owner, self.name = owner, "encoder_h"
+
+    def get_weights(self):
+        return [t.detach().cpu().numpy().copy() for t in self.owner.lstm_tensors()]
+
+    def set_weights(self, ws):
+        e = self.owner.model.engine
+        shapes = [(e.D + e.C, 4 * e.H), (e.H, 4 * e.H), (4 * e.H,)]
+        assert len(ws) == 3 and all(tuple(np.shape(w)) == s for w, s in zip(ws, shapes))
+        self.owner.lstm = [torch.tensor(np.asarray(w), dtype=torch.float32, device=e.dev).contiguous() for w in ws]
+        self.owner._cell = None
+
+
 class ZEncoder:
-    """make_z_encoder (cl_vrnn/model.py:116-136).  QUIRK Q1: the reference builds a FRESH encoder_h
-    LSTM here and copies only the Z heads, so its sampling-time encoder LSTM is randomly initialised.
-    Default here is the documented fix (use the trained encoder_h); copy_encoder_weights=False
-    reproduces the reference by drawing fresh Keras-default LSTM weights."""
+    """make_z_encoder (cl_vrnn/model.py:116-136): [x [S,1,D], w [S,C]] -> [z_mean, z_log_var], stateful.
+    QUIRK Q1: the reference builds a FRESH encoder_h LSTM here and copies only the Z heads, so its
+    sampling-time encoder LSTM is randomly initialised.  Default here is the documented fix (use the
+    trained encoder_h); copy_encoder_weights=False reproduces the reference by drawing fresh
+    Keras-default LSTM weights (get_layer('encoder_h').set_weights(...) installs given ones)."""
     def __init__(self, model, copy_encoder_weights=True, rng=None):
         self.model = model
         self.lstm = None
+        self._cell = None
         if not copy_encoder_weights:
             e = model.engine
             rng = rng or np.random.default_rng(np.random.randint(0, 2 ** 31 - 1))
@@ -157,17 +221,58 @@ class ZEncoder:
                          torch.tensor(vt if vt.shape == (e.H, c) else u, dtype=torch.float32, device=e.dev).contiguous(),
                          torch.tensor(bias, device=e.dev)]
 
+    def lstm_tensors(self):
+        e = self.model.engine
+        return self.lstm or [e.view("encoder_h.kernel"), e.view("encoder_h.recurrent_kernel"), e.view("encoder_h.bias")]
+
+    def get_layer(self, name):
+        if name == "encoder_h":
+            return _LstmWeights(self)
+        return self.model.get_layer(name)
+
     def reset_states(self):
-        pass
+        if self._cell is not None:
+            self._cell.reset_states()
+
+    def predict(self, x):
+        e = self.model.engine
+        xs, w = as_dev_f32(x[0], e.dev), as_dev_f32(x[1], e.dev)
+        S, L, _ = xs.shape
+        if self._cell is None:
+            self._cell = StatefulLSTM(*self.lstm_tensors())
+        xw = torch.cat([xs, w.reshape(S, 1, e.C).expand(S, L, e.C)], dim=-1).contiguous()   # concat = layout only
+        h = self._cell(xw).reshape(S * L, e.H)
+        zm = dense(h, e.view("Z_mean.kernel"), e.view("Z_mean.bias")).reshape(S, L, e.Z)
+        zv = dense(h, e.view("Z_log_var.kernel"), e.view("Z_log_var.bias")).reshape(S, L, e.Z)
+        return [zm.cpu().numpy(), zv.cpu().numpy()]
 
 
 class Decoder:
-    """make_decoder (cl_vrnn/model.py:138-162): shares decoder_h and X_decoded_mean weights."""
-    def __init__(self, model):
+    """make_decoder (cl_vrnn/model.py:138-162): [Z, Xp, W] (or [Z, W]) -> X_decoded_mean, stateful;
+    shares decoder_h and X_decoded_mean weights with the trained model."""
+    def __init__(self, model, use_x_prev=None):
         self.model = model
+        self.use_x_prev = model.engine.use_x_prev if use_x_prev is None else bool(use_x_prev)
+        self._cell = None
 
     def reset_states(self):
-        pass
+        if self._cell is not None:
+            self._cell.reset_states()
+
+    def predict(self, x):
+        e = self.model.engine
+        if self.use_x_prev:
+            z, xp, w = (as_dev_f32(t, e.dev) for t in x)
+        else:
+            z, w = (as_dev_f32(t, e.dev) for t in x)
+        S, L, _ = z.shape
+        if self._cell is None:
+            self._cell = StatefulLSTM(e.view("decoder_h.kernel"), e.view("decoder_h.recurrent_kernel"), e.view("decoder_h.bias"))
+        wr = w.reshape(S, 1, e.C).expand(S, L, e.C)
+        xin = torch.cat(([xp] if self.use_x_prev else []) + [z, wr], dim=-1).contiguous()      # [Xp | Z | W]
+        h = self._cell(xin).reshape(S * L, e.H)
+        p = dense(h, e.view("X_decoded_mean.kernel"), e.view("X_decoded_mean.bias"), act=2)
+        return p.reshape(S, L, e.D).cpu().numpy()
 
 
 def make_w_encoder(model, original_dim, n_classes, seq_length=1, batch_size=1):
@@ -181,7 +286,7 @@ def make_z_encoder(model, original_dim, n_classes, latent_dims, seq_length=1, ba
 
 def make_decoder(model, original_dim, intermediate_dim, latent_dim, n_classes, use_x_prev,
                  seq_length=1, batch_size=1, stateful=True):
-    return Decoder(model)
+    return Decoder(model, use_x_prev)
 
 
 # ---------------------------------------------------------------------- numpy samplers (host)
@@ -234,10 +339,10 @@ def infer_w_device(w_enc_model, seeds_u8, seq_length, w_sample=False):
     M = chunks.shape[0]
     Wargs = w_enc_model.wargs_device(chunks)
     C1 = e.C - 1
-    if w_sample:
-        eps = torch.from_numpy(np.random.randn(M, C1).astype(np.float32)).to(e.dev)
-    else:
-        eps = torch.zeros(M, C1, device=e.dev)
+    # sample_w draws np.random.randn(1, C-1) for EVERY chunk, also with add_noise=False (it multiplies
+    # the draw by 0, cl_vrnn/model.py:71-80): consume the stream exactly like the reference does
+    draws = np.stack([np.random.randn(1, C1)[0] for _ in range(M)]).astype(np.float32)
+    eps = torch.from_numpy(draws if w_sample else 0 * draws).to(e.dev)
     Wc = torch.empty(M, e.C, device=e.dev)
     scratch = torch.zeros(8, device=e.dev)
     labels = torch.zeros(M, dtype=torch.int32, device=e.dev)
@@ -250,7 +355,7 @@ def infer_w_device(w_enc_model, seeds_u8, seq_length, w_sample=False):
 
 def generate_samples(dec_model, w_enc_model, z_enc_model, x_seeds, nsteps, use_x_prev, w_vals=None,
                      seq_length=None, w_sample=False, w_discrete=False, noise=None, seed=0, song0=0,
-                     return_probs=False):
+                     return_probs=False, keep_seed_steps=False):
     """Batched B200 form of generate_sample: S songs in one persistent kernel launch.
     x_seeds [S, T_seed, D] (numpy or device uint8); w_vals [S, C] or None (infer from the seed);
     noise = (eps_z [S,T,Z], u [S,T,D]) tapes or None (in-kernel Philox keyed by seed/song/t).
@@ -280,19 +385,27 @@ def generate_samples(dec_model, w_enc_model, z_enc_model, x_seeds, nsteps, use_x
     check(lib().clv_vrnn_sample(C.byref(cfg), ptr(e.params), ptr(lstm[0]), ptr(lstm[1]), ptr(lstm[2]),
                                 ptr(seeds), T_seed, nsteps, ptr(w), ptr(eps_z), ptr(u), seed, song0, S,
                                 ptr(out), ptr(probs), _stream()), "clv_vrnn_sample")
-    res = out[:, T_seed:].cpu().numpy()
+    res = (out if keep_seed_steps else out[:, T_seed:]).cpu().numpy()
     return (res, probs.cpu().numpy()) if return_probs else res
 
 
 def generate_sample(dec_model, w_enc_model, z_enc_model, x_seed, nsteps, use_x_prev, w_val=None,
                     do_reset=True, seq_length=None, w_sample=False, w_discrete=False):
-    """cl_vrnn/model.py:9-60, one song.  The whole `for t` loop runs inside the persistent kernel;
-    the noise tape is drawn from np.random in the reference's order (per step: randn(z) then
-    rand(88)) so a fixed np.random.seed gives the draw-for-draw stream.  Returns float64 [nsteps, D]."""
+    """cl_vrnn/model.py:9-60, one song.  The whole `for t` loop runs inside the persistent kernel; the
+    np.random stream is consumed draw for draw in the reference's order -- per inferred-key chunk
+    randn(1, C-1) (drawn even when w_sample is off), one np.random.choice with w_discrete, then per step
+    randn(z) and rand(88) -- so a fixed np.random.seed reproduces the reference's sample (pinned by
+    tests/golden/vrnn_sampler.npz, produced by running the reference's own generate_sample).
+    A 1-D x_seed is the reference's `nseedsteps == 0` form (:27-31): the seed frame is x_prev of the first
+    generated step and all nsteps outputs are returned.  Returns float64 [nsteps, D]."""
     e = dec_model.model.engine
     x_seed = np.asarray(x_seed)
-    if x_seed.ndim == 1:
+    one_d = x_seed.ndim == 1
+    if one_d:
+        if w_val is None:
+            raise IndexError("a 1-D x_seed needs w_val: the reference reads x_seed.shape[1] to infer the key")
         x_seed = x_seed[None, :]
+        nsteps -= 1                      # the seed step's own sampled frame is output 0
     T = x_seed.shape[0] + nsteps
     if w_val is None:
         w = infer_w_device(w_enc_model, torch.from_numpy(_binary_u8(x_seed, "x_seed")[None]).to(e.dev),
@@ -307,5 +420,5 @@ def generate_sample(dec_model, w_enc_model, z_enc_model, x_seed, nsteps, use_x_p
         eps_z[0, t] = np.random.randn(e.Z)
         u[0, t] = np.random.rand(e.D)
     xs = generate_samples(dec_model, w_enc_model, z_enc_model, x_seed[None], nsteps, use_x_prev,
-                          w_vals=w, noise=(eps_z, u))
+                          w_vals=w, noise=(eps_z, u), keep_seed_steps=one_d)
     return xs[0].astype(np.float64)

@@ -36,9 +36,6 @@ def train(args):
     wv = to_categorical(P.valid_song_keys, args.n_classes)
     print("Training with {} classes.".format(args.n_classes))
     assert not (args.predict_next and args.use_x_prev), "Can't use --predict_next if using --use_x_prev"
-    if args.predict_next:
-        raise NotImplementedError("--predict_next (autoencode x_{t+1} from x_t) is not built; "
-                                  "the configurations of the paper use --use_x_prev")
     callbacks = get_callbacks(args, patience=args.patience, min_epoch=max(args.kl_anneal, args.w_kl_anneal) + 1,
                               do_log=args.do_log)
     if args.kl_anneal > 0:
@@ -57,7 +54,8 @@ def train(args):
     args.optimizer, was_adam_wn = init_adam_wn(args.optimizer)
     model, _ = get_model(args.batch_size, args.original_dim, args.intermediate_dim, args.latent_dim,
                          args.seq_length, args.n_classes, args.use_x_prev, args.optimizer, args.class_weight,
-                         kl_weight, w_kl_weight=w_kl_weight, w_log_var_prior=args.w_log_var_prior)
+                         kl_weight, w_kl_weight=w_kl_weight, w_log_var_prior=args.w_log_var_prior,
+                         predict_next=args.predict_next)
     args.optimizer = 'adam-wn' if was_adam_wn else args.optimizer
     os.makedirs(args.model_dir, exist_ok=True)
     save_model_in_pieces(model, args)

@@ -182,7 +182,7 @@ __global__ void bias_act_kernel(float* __restrict__ C, int64_t ldc, int M, int N
   const int64_t m = i / N;
   const int n = (int)(i - m * N);
   float v = C[m * ldc + n] + (bias ? __ldg(bias + n) : 0.f);
-  C[m * ldc + n] = relu ? fmaxf(v, 0.f) : v;
+  C[m * ldc + n] = relu == 1 ? fmaxf(v, 0.f) : (relu == 2 ? sigmoid_f(v) : v);
 }
 
 }  // namespace

@@ -242,6 +242,7 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   const int B = c->B, L = c->L, D = c->D, H = c->H, Z = c->Z, C = c->C, C1 = C - 1, G = 4 * H;
   const int BL = B * L, xo = c->use_x_prev ? D : 0;
   const int sx = c->x_shift > 0 ? c->x_shift : (c->use_x_prev ? 1 : 0);
+  const int sy = c->y_shift > 0 ? c->y_shift : sx;   // reconstruction target (--predict_next: next frame)
   const float sb = 1.0f / (float)c->B_global, sbl = 1.0f / ((float)c->B_global * (float)L);
   const Ws w = carve(c);
 #define WSP(name) (ws + w.find(name))
@@ -342,11 +343,11 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   else TRY_PDL(clv_lstm_fwd_fused(gates_d, c->use_x_prev, Ud, bd, W, Kd_w, C, Zs, Kd_z, Z, h_d, c_d, B, L, H, st));
   // ---- X head + Bernoulli loss + dlogits + dgrad to h_d in one pass (model.py:229-234,241-242)
   if (H == 88 && D == 88) {
-    TRY_PDL(clv_xhead_fwd_bwd(h_d, Kx, bx, roll, off, L, sx, loss, logits, dh, BL, H, D, sbl,
+    TRY_PDL(clv_xhead_fwd_bwd(h_d, Kx, bx, roll, off, L, sy, loss, logits, dh, BL, H, D, sbl,
                               c->do_backward, st));
   } else {
     TRY(nn_f32(h_d, H, Kx, D, logits, D, BL, D, H, bx, 0, 0, st));
-    TRY(clv_bernoulli_ce_fwd_bwd(logits, roll, off, L, sx, loss, BL, D, sbl, c->do_backward, st));
+    TRY(clv_bernoulli_ce_fwd_bwd(logits, roll, off, L, sy, loss, BL, D, sbl, c->do_backward, st));
     if (c->do_backward) TRY(nt_f32(logits, D, Kx, D, dh, H, BL, H, D, nullptr, 0, 0, st));
   }
   if (!c->do_backward) return CLV_OK;
@@ -442,6 +443,7 @@ int vae_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uin
   const int B = c->B, D = c->D, H = c->H, Hc = c->Hc, Z = c->Z, C = c->C, C1 = C - 1;
   const int xo = c->use_x_prev ? D : 0;
   const int sx = c->x_shift > 0 ? c->x_shift : (c->use_x_prev ? 1 : 0);
+  const int sy = c->y_shift > 0 ? c->y_shift : sx;
   const float sb = 1.0f / (float)c->B_global;
   const Ws w = carve(c);
 #define WSP(name) (ws + w.find(name))
@@ -476,7 +478,7 @@ int vae_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uin
               0, 1, st));
   TRY(nn_f32(Zs, Z, Kdh + (int64_t)(C + xo) * H, H, h_dec, H, B, H, Z, bdh, 1, 1, st));
   TRY(nn_f32(h_dec, H, Kx, D, logits, D, B, D, H, bx, 0, 0, st));
-  TRY(clv_bernoulli_ce_fwd_bwd(logits, roll, off, 1, sx, loss, B, D, sb, c->do_backward, st));
+  TRY(clv_bernoulli_ce_fwd_bwd(logits, roll, off, 1, sy, loss, B, D, sb, c->do_backward, st));
   if (!c->do_backward) return CLV_OK;
 
   // ---- backward

@@ -43,7 +43,7 @@ class Engine:
                  optimizer="adam-wn", lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-8,
                  seed=0, device=None, world_size=1, rank=0, process_group=None, use_graph=True,
                  overlap_wgrad=True, gemm_algo=1, p2p_allreduce=False, tc_lstm_min=0,
-                 fused_optimizer=True):
+                 fused_optimizer=True, predict_next=False):
         _require_cuda()
         lib()
         if optimizer not in ("adam-wn", "adam"):
@@ -54,8 +54,12 @@ class Engine:
         self.B, self.L, self.D, self.H, self.Z, self.C = B, (L if self.model == 0 else 1), D, H, Z, n_classes
         self.Hc = Hc
         self.use_x_prev = bool(use_x_prev)
-        self.W = self.L + 1 if self.use_x_prev else self.L            # frames per window
+        self.predict_next = bool(predict_next)                         # --predict_next: target = next frame
+        if self.predict_next and self.use_x_prev:
+            raise ValueError("Can't use --predict_next if using --use_x_prev")     # cl_vrnn/train.py:28
+        self.W = self.L + 1 if (self.use_x_prev or self.predict_next) else self.L   # frames per window
         self.x_shift = 0                                               # 0 = default placement
+        self.y_shift = 1 if self.predict_next else 0                   # 0 = the target is `current`
         self.hyper = dict(class_weight=class_weight, kl_weight=kl_weight, w_kl_weight=w_kl_weight,
                           w_log_var_prior=w_log_var_prior)
         self.optimizer, self.lr, self.b1, self.b2, self.eps = optimizer, lr, beta_1, beta_2, epsilon
@@ -130,7 +134,7 @@ class Engine:
     def cfg(self, **over):
         kw = dict(model=self.model, B=self.B, L=self.L, D=self.D, H=self.H, Z=self.Z, C_=self.C,
                   use_x_prev=self.use_x_prev, Hc=self.Hc, B_global=self.B * self.world_size,
-                  seed=self.seed, x_shift=self.x_shift, overlap_wgrad=int(self.overlap_wgrad), gemm_algo=self.gemm_algo,
+                  seed=self.seed, x_shift=self.x_shift, y_shift=self.y_shift, overlap_wgrad=int(self.overlap_wgrad), gemm_algo=self.gemm_algo,
                   tc_lstm_min=self.tc_lstm_min,
                   **self.hyper)
         kw.update(over)
@@ -143,10 +147,13 @@ class Engine:
         if changed:
             self._graphs.clear()
 
-    def set_window(self, frames, x_shift):
+    def set_window(self, frames, x_shift, y_shift=None):
         """Window geometry: `frames` per window, `current` starts at frame x_shift (0 = default:
-        1 with use_x_prev).  Used when current/history are independent arrays ([history | current])."""
+        1 with use_x_prev), the target at y_shift (0 = the target is `current`).  Used when
+        current/history (or input/target) are independent arrays ([history | current], [x | y])."""
         self.W, self.x_shift = frames, x_shift
+        if y_shift is not None:
+            self.y_shift = y_shift
         self._win_off_seq = (torch.arange(self.B, dtype=torch.int32, device=self.dev) * self.W).contiguous()
         self.win_off.copy_(self._win_off_seq)
         self._win_off_is_seq = True

@@ -168,7 +168,7 @@ class BaseModel:
         self.engine.run(train=True, gen_noise=True)
         return self.engine.read_losses()
 
-    def _windows_from_inputs(self, x):
+    def _windows_from_inputs(self, x, y=None):
         raise NotImplementedError
 
     def _labels_from_targets(self, y):
@@ -179,13 +179,13 @@ class BaseModel:
         return lab
 
     def train_on_batch(self, x, y):
-        win = torch.from_numpy(self._windows_from_inputs(x))
+        win = torch.from_numpy(self._windows_from_inputs(x, y))
         lab = torch.from_numpy(self._labels_from_targets(y))
         return self._as_list(self.train_on_batch_windows(win, lab))
 
     def test_on_batch(self, x, y):
         self._sync_weights_of_losses()
-        self.engine.stage_windows(torch.from_numpy(self._windows_from_inputs(x)),
+        self.engine.stage_windows(torch.from_numpy(self._windows_from_inputs(x, y)),
                                   torch.from_numpy(self._labels_from_targets(y)))
         self.engine.run(train=False, gen_noise=True)
         return self._as_list(self.engine.read_losses())
@@ -218,13 +218,19 @@ class BaseModel:
         e = self.engine
         if batch_size is not None and batch_size != e.B:
             raise ValueError("batch_size is baked into the model (%d), got %d" % (e.B, batch_size))
-        wins = torch.from_numpy(self._windows_from_inputs(x)).to(e.dev).reshape(-1)
+        # window geometry (frames per window, where `current` / the target sit) is decided ONCE for both
+        # splits: a validation split stored differently from the training split would change e.W under
+        # the training offsets
+        ov = self._overlaps(x, y)
+        if validation_data is not None:
+            ov = ov and self._overlaps(validation_data[0], validation_data[1])
+        wins = torch.from_numpy(self._windows_from_inputs(x, y, overlap=ov)).to(e.dev).reshape(-1)
         labs = torch.from_numpy(self._labels_from_targets(y)).to(e.dev)
         n = labs.numel()
         val = None
         if validation_data is not None:
             xv, yv = validation_data[0], validation_data[1]
-            val = (torch.from_numpy(self._windows_from_inputs(xv)).to(e.dev).reshape(-1),
+            val = (torch.from_numpy(self._windows_from_inputs(xv, yv, overlap=ov)).to(e.dev).reshape(-1),
                    torch.from_numpy(self._labels_from_targets(yv)).to(e.dev))
         callbacks = list(callbacks or [])
         hist = History()
@@ -259,7 +265,7 @@ class BaseModel:
 
     def evaluate(self, x, y, batch_size=None, verbose=0):
         e = self.engine
-        wins = torch.from_numpy(self._windows_from_inputs(x)).to(e.dev).reshape(-1)
+        wins = torch.from_numpy(self._windows_from_inputs(x, y)).to(e.dev).reshape(-1)
         labs = torch.from_numpy(self._labels_from_targets(y)).to(e.dev)
         self._sync_weights_of_losses()
         return self._as_list(self._run_epoch(wins, labs, torch.arange(labs.numel(), device=e.dev), False))

@@ -63,6 +63,10 @@ typedef struct clv_cfg {
   int32_t gemm_algo_tc_lstm_min; /* batch from which the tcgen05 recurrence is used (0 = default 8192) */
   int32_t overlap_wgrad;/* 1: run the weight-gradient GEMMs on the library's auxiliary stream
                            (needs clv_runtime_init()); forked from / joined into `stream`       */
+  int32_t y_shift;      /* frame of the reconstruction TARGET inside a window; 0 = the target is
+                           `current` (y == x, cl_vrnn/train.py:51-57).  --predict_next: windows of L+1
+                           frames, current = frames 0..L-1 (x_shift 0), target = frames 1..L (y_shift 1) */
+  int32_t reserved0;
   uint64_t seed;        /* Philox key for gen_noise (make it rank-dependent)                  */
 } clv_cfg;
 
@@ -117,7 +121,8 @@ int clv_inproj_tc(const uint8_t* roll, const int32_t* win_off, int32_t grp, int3
 int clv_lstm_wgrad_tc(const float* dA, const uint8_t* roll, const int32_t* win_off, int32_t L,
                       int32_t shift, int32_t D, const float* h, const float* Zs, int32_t Z, float* gKx,
                       float* gU, float* gKz, int64_t R, int32_t H, void* stream);
-/* C[M,N] = act(C + bias[N])  -- epilogue of a split-K forward GEMM */
+/* C[M,N] = act(C + bias[N])  -- epilogue of a split-K forward GEMM; relu: 0 = none, 1 = ReLU,
+ * 2 = sigmoid (the X_decoded_mean head of the sampler sub-models' predict()) */
 int clv_bias_act(float* C, int64_t ldc, int32_t M, int32_t N, const float* bias, int32_t relu,
                  void* stream);
 /* out[N] (+)= sum_m A[m,N]  (bias gradients) */

@@ -74,6 +74,8 @@ def test_generate_sample_matches_oracle_under_the_same_numpy_seed():
     # oracle with the tape np.random would have produced in the reference's draw order
     np.random.seed(123)
     T = 8 + 10
+    for _ in range(2):                 # two full 4-frame chunks of the 8-frame seed: sample_w draws per chunk
+        np.random.randn(1, C - 1)      # (cl_vrnn/model.py:71-80; pinned by tests/golden/vrnn_sampler.npz)
     eps_z, u = np.zeros((T, Z), np.float32), np.zeros((T, 88), np.float32)
     for t in range(T):
         eps_z[t] = np.random.randn(Z); u[t] = np.random.rand(88)
