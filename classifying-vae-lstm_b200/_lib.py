@@ -69,6 +69,8 @@ PROTOTYPES = {
     "clv_lstm_bwd_fused": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _P, _I32, _P, _I32, _P, _I32, _I32, _I32, _P]),
     "clv_lstm_bwd_heads": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _P, _I32, _P, _I32, _P, _P, _P, _F, _P, _P, _P,
                                      _P, _I32, _I32, _I32, _I32, _P]),
+    "clv_lstm_pair_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P,
+                                    _P, _P, _P, _P, _F, _I32, _U64, _P, _I32, _I32, _I32, _I32, _P]),
     "clv_lstm_fwd_tc_scratch_bytes": (_I64, []),
     "clv_lstm_fwd_tc": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _I32, _I32, _I32, _P]),
     "clv_xhead_fwd_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _I64, _I32, _I32, _F, _I32, _P]),

@@ -35,6 +35,11 @@ extern "C" int clv_keyenc_bwd_full(const uint8_t*, const int32_t*, int32_t, int3
 extern "C" int clv_keyenc_bwd(const float*, const float*, const int32_t*, const float*, const float*,
                               const float*, const float*, float*, float*, int32_t, int32_t, int32_t, float,
                               float, float, void*);
+extern "C" int clv_lstm_pair_fwd(float*, const float*, const float*, const float*, float*, float*, float*,
+                                 int32_t, const float*, const float*, const float*, const float*, float*,
+                                 float*, const float*, int32_t, const float*, const float*, const float*,
+                                 const float*, float*, float*, float*, float*, float, int32_t, uint64_t,
+                                 const uint64_t*, int32_t, int32_t, int32_t, int32_t, void*);
 
 namespace {
 
@@ -159,6 +164,11 @@ int tn_u8(const uint8_t* roll, const int32_t* off, int grp, int shift, int64_t l
 // launch whose stream predecessor is one of our kernels: allow programmatic dependent launch
 // (the kernel's parameter-only prologue overlaps the predecessor; see common.cuh)
 #define TRY_PDL(x) do { g_clv_pdl = pdl_enabled(); int rc__ = (x); g_clv_pdl = 0; if (rc__ != CLV_OK) return rc__; } while (0)
+static int pair_disabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CLV_NO_PAIR"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v;
+}
 static int pdl_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("CLV_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -267,8 +277,13 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
               *Kzv = P + po[R_ZV_K], *bzv = P + po[R_ZV_B], *Kd = P + po[R_DEC_K],
               *Ud = P + po[R_DEC_U], *bd = P + po[R_DEC_B], *Kx = P + po[R_X_K], *bx = P + po[R_X_B];
 
+  // encoder/decoder wavefront (lstm_pair.cu): both recurrences in one launch, the decoder a step or two
+  // behind the encoder; needs the 2-latent head exchange and the FFMA recurrence
+  const bool pair = !tcl && Z <= 2 && H == 88 && C <= 16 && !pair_disabled();
   if (c->do_backward && !c->accumulate)
     CLV_CUDA(cudaMemsetAsync(Gr, 0, sizeof(float) * (po[R_X_B] + pc[R_X_B]), st));
+  // wavefront hand-over: the consumer polls the producer's rows themselves; 0xFFFFFFFF = "not written yet"
+  if (pair) CLV_CUDA(cudaMemsetAsync(h_e, 0xFF, sizeof(float) * (size_t)BL * H, st));
   TRY(clv_step_begin(loss, ctr, !c->accumulate, c->gen_noise, st));   // last: the key encoder chains on it
 
   Fork fk(st, c->overlap_wgrad != 0);
@@ -331,8 +346,15 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
     } else {
       TRY(fk.join());   // both roll projections (issued before the key encoder) are done
     }
-    TRY(clv_lstm_fwd_fused(gates_e, 1, Ue, be, W, Ke_w, C, nullptr, nullptr, 0, h_e, c_e, B, L, H, st));
+    if (pair) {
+      TRY(clv_lstm_pair_fwd(gates_e, Ue, be, Ke_w, h_e, c_e, gates_d, c->use_x_prev, Ud, bd, Kd_w, Kd_z, h_d, c_d,
+                            W, C, Kzm, bzm, Kzv, bzv, eps_z, Zargs, Zs, loss, sbl, c->gen_noise, c->seed, ctr,
+                            B, L, H, Z, st));
+    } else {
+      TRY(clv_lstm_fwd_fused(gates_e, 1, Ue, be, W, Ke_w, C, nullptr, nullptr, 0, h_e, c_e, B, L, H, st));
+    }
   }
+  if (!pair) {
   // ---- Z heads + sample + kl (model.py:200-216,236-239)
   TRY_PDL(clv_gauss_heads_fwd(h_e, Kzm, bzm, Kzv, bzv, eps_z, Zargs, Zs, loss, BL, H, Z, sbl,
                               c->gen_noise, c->seed, ctr, st));
@@ -341,6 +363,7 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   if (tcl) TRY(clv_lstm_fwd_tc(gates_d, Ud, Zs, Kd_z, Z, h_d, c_d, uimg_d, B, L, H, st));
   else if (c->use_x_prev && !enc_proj_side) TRY(clv_lstm_fwd_fused(gates_d, c->use_x_prev, Ud, bd, W, Kd_w, C, Zs, Kd_z, Z, h_d, c_d, B, L, H, st));
   else TRY_PDL(clv_lstm_fwd_fused(gates_d, c->use_x_prev, Ud, bd, W, Kd_w, C, Zs, Kd_z, Z, h_d, c_d, B, L, H, st));
+  }
   // ---- X head + Bernoulli loss + dlogits + dgrad to h_d in one pass (model.py:229-234,241-242)
   if (H == 88 && D == 88) {
     TRY_PDL(clv_xhead_fwd_bwd(h_d, Kx, bx, roll, off, L, sy, loss, logits, dh, BL, H, D, sbl,
