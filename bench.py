@@ -11,8 +11,11 @@ CL-VRNN on one batch of B=200 synthetic piano-roll windows of the JSB Chorales s
 C=10 keys, z=2, --use_x_prev): BASELINE.json configs[1].  Weak scaling: every rank steps its own 200.
 `value` is device-timed with the batch already in HBM; `e2e` goes through the public train_on_batch
 call with pinned HOST buffers (H2D of windows+labels and D2H of the loss scalars inside the timed
-region).  The same line carries the sampler metric (timesteps/s of generate_sample), the roofline of
-the dominant kernel, and a CPU baseline (the oracle port timed on the host cores).
+region).  The same line carries the sampler metric (timesteps/s of generate_sample, given and inferred
+key), the CL-VAE train step (BASELINE configs[0]), the roofline of the dominant kernel against the
+MEASURED HBM and fp32-FMA peaks of this box, and CPU baselines (the oracle port on the host cores).
+At N > 1 it first checks data-parallel parity: the all-reduced gradient of a batch sharded over the
+ranks against rank 0 stepping the whole batch in micro-batches (`dp_parity_max_rel_err`).
 """
 import argparse
 import json
@@ -111,6 +114,33 @@ def cpu_train_port(steps, warmup, B=None):
     return dict(value=c["B"] / (ms / 1e3), ms_per_step=ms, cores=cores, B=c["B"])
 
 
+def cpu_vae_train_port(steps, warmup, B=100, C=2, Z=4):
+    """CL-VAE train step (cl_vae/model.py:130-224 + Adam-WN) of the oracle port on the host cores."""
+    import numpy as np
+    import torch
+    from oracle import clv_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(0)
+    p = O.init_vae_params(rng, 88, 88, Z, 88, C, True, dtype=torch.float32)
+    opt = O.AdamWN(p)
+    pool = O.synth_rolls(rng, B * 4, 2, 88)
+    labels = rng.integers(0, C, B * 4)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        i0 = (it % 4) * B
+        win = torch.tensor(pool[i0:i0 + B], dtype=torch.float32)
+        out, g = O.vae_loss_and_grads(p, win[:, 1], win[:, 0], O.one_hot(labels[i0:i0 + B], C, torch.float32),
+                                      torch.randn(B, C - 1), torch.randn(B, Z), C, True)
+        p = opt.step(p, g)
+        float(out["loss"])
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    return dict(value=B / (ms / 1e3), ms_per_step=ms, cores=cores, B=B)
+
+
 def cpu_sampler_port(songs, nsteps, T_seed=16, C=12):
     """Reference-faithful Python sampling loop (batch 1, two model calls per step) on the host."""
     import numpy as np
@@ -169,6 +199,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sampler", action="store_true")
+    ap.add_argument("--no-vae", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-fused-opt", action="store_true", help="step then Adam-WN as two calls (N=1)")
     ap.add_argument("--p2p", type=int, default=-1, help="1/0: force the fused peer-memory all-reduce+Adam path on/off")
@@ -234,6 +265,47 @@ def main():
         e.stage_offsets(offs[i % n_batches], labs[i % n_batches])   # D2D of 1.6 KB: batch already in HBM
         e.run(train=True, gen_noise=True)
 
+    # ---------------- data-parallel parity (N > 1): one gen_noise=0 step on a COMMON seeded batch of N*B
+    # sequences sharded over the ranks; the all-reduced [grads | losses] must equal rank 0 stepping the
+    # whole batch as N accumulated micro-batches (same kernels, same global-mean scaling)
+    dp_parity, dp_failed = None, False
+    if world > 1:
+        gcpu = torch.Generator().manual_seed(20171107)
+        NB = world * B
+        cwin = (torch.rand(NB, L + 1, D, generator=gcpu) < 0.06).to(torch.uint8)
+        clab = torch.randint(0, Cc, (NB,), generator=gcpu, dtype=torch.int32)
+        cew = torch.randn(NB, Cc - 1, generator=gcpu)
+        cez = torch.randn(NB, L, Z, generator=gcpu)
+        stc = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def raw_step(sl, grads, loss_acc, accumulate):
+            e.stage_windows(cwin[sl].to(devn), clab[sl].to(devn))
+            e.eps_w.copy_(cew[sl].reshape(-1)); e.eps_z.copy_(cez[sl].reshape(-1))
+            cfgp = e.cfg(gen_noise=0, do_backward=1, accumulate=int(accumulate))
+            check(lib().clv_train_step(C.byref(cfgp), ptr(e.params), ptr(grads), ptr(loss_acc), ptr(e.roll),
+                                       ptr(e.win_off), ptr(e.labels), ptr(e.eps_w), ptr(e.eps_z), None,
+                                       ptr(e.workspace), e.workspace.numel() * 4, stc), "clv_train_step")
+        buf = torch.zeros(e.P + 8, device=devn)
+        raw_step(slice(rank * B, (rank + 1) * B), buf[:e.P], buf[e.P:], False)
+        dist.all_reduce(buf)
+        if rank == 0:
+            ref = torch.zeros(e.P + 8, device=devn)
+            for r_ in range(world):
+                raw_step(slice(r_ * B, (r_ + 1) * B), ref[:e.P], ref[e.P:], r_ > 0)
+            torch.cuda.synchronize()
+            worst = 0.0
+            for k_ in e.names + ["losses"]:
+                if k_ == "losses":
+                    a_, b_ = buf[e.P:e.P + 5], ref[e.P:e.P + 5]
+                else:
+                    i_ = e.names.index(k_)
+                    n_ = (e.rows[i_] if e.rows[i_] > 0 else 1) * e.cols[i_]
+                    a_, b_ = buf[e.offs[i_]:e.offs[i_] + n_], ref[e.offs[i_]:e.offs[i_] + n_]
+                worst = max(worst, float((a_ - b_).abs().max() / (b_.abs().max() + 1e-30)))
+            dp_parity = worst
+        e.roll = e.win_buf
+        barrier()
+
     for i in range(Wm):
         step_resident(i)
     l0 = lib().clv_launch_count()
@@ -277,32 +349,59 @@ def main():
            "h2d_bytes_per_step": B * (L + 1) * D + 4 * B, "d2h_bytes_per_step": 32,
            "ms_per_step": ms_e2e, "api": "model.train_on_batch_windows(pinned uint8 [B,L+1,88], int32 labels)"}
 
+    # ---------------- measured fp32 peaks of THIS box (MEASURED_PEAKS.json has none): FMA-pipe peak and the
+    # rate reachable with the 5-distinct-register FFMA2 of the register-resident mat-vecs (RF-bank limited)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    scr = torch.zeros(2 * torch.cuda.get_device_properties(local).multi_processor_count * 512, device=devn)
+    fp32 = {}
+    for mode, nm in ((0, "fma_pipe_peak"), (1, "matvec_operand_pattern")):
+        tf = C.c_double(0.0)
+        check(lib().clv_fp32_peak_probe(mode, ptr(scr), scr.numel(), C.byref(tf), st), "clv_fp32_peak_probe")
+        fp32[nm] = tf.value
+    fp32_peak = fp32["fma_pipe_peak"]
+
     # ---------------- per-kernel timing (CUDA events on the launching stream, L2 flushed between
     # launches) of the kernels that dominate the step, on this batch shape
-    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     G = 4 * H
     gates = torch.randn(B, L, G, device=devn) * 0.5
+    gates2 = torch.randn(B, L, G, device=devn) * 0.5
     U = e.view("encoder_h.recurrent_kernel")
     hbuf = torch.zeros(B, L, H, device=devn); cbuf = torch.zeros(B, L, H, device=devn)
+    hbuf2 = torch.zeros(B, L, H, device=devn); cbuf2 = torch.zeros(B, L, H, device=devn)
     dh = torch.randn(B, L, H, device=devn); dAsum = torch.zeros(B, G, device=devn)
     dZb = torch.zeros(B, L, Z, device=devn); dWb = torch.zeros(B, Cc, device=devn)
     Wv = torch.rand(B, Cc, device=devn); Zs = torch.randn(B, L, Z, device=devn)
+    Zargs_b = torch.zeros(B, L, 2 * Z, device=devn); eps_b = torch.randn(B, L, Z, device=devn)
+    lacc = torch.zeros(8, device=devn)
     Kd = e.view("decoder_h.kernel"); Ke = e.view("encoder_h.kernel")
     scratch = torch.zeros(lib().clv_inproj_tc_scratch_bytes() // 4, device=devn)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=devn)
 
-    def time_kernel(fn, reps=20):
+    def time_kernel(fn, reps=20, pre=None):
         tot = 0.0
         for _ in range(3):
+            if pre:
+                pre()
             fn()
         for _ in range(reps):
             flush.zero_()                       # flush L2 between timed launches
+            if pre:
+                pre()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); fn(); b.record()
             torch.cuda.synchronize()
             tot += a.elapsed_time(b)
         return tot / reps
 
+    pair_ok = Z <= 2 and Cc <= 16
+    t_pair = None
+    if pair_ok:
+        t_pair = time_kernel(lambda: check(lib().clv_lstm_pair_fwd(
+            ptr(gates), ptr(U), ptr(e.view("encoder_h.bias")), ptr(Ke[D:]), ptr(hbuf), ptr(cbuf), ptr(gates2), 1,
+            ptr(e.view("decoder_h.recurrent_kernel")), ptr(e.view("decoder_h.bias")), ptr(Kd[D + Z:]), ptr(Kd[D:D + Z]),
+            ptr(hbuf2), ptr(cbuf2), ptr(Wv), Cc, ptr(e.view("Z_mean.kernel")), ptr(e.view("Z_mean.bias")),
+            ptr(e.view("Z_log_var.kernel")), ptr(e.view("Z_log_var.bias")), ptr(eps_b), ptr(Zargs_b), ptr(Zs), ptr(lacc),
+            1.0 / (B * L), 0, 0, None, B, L, H, Z, st)), pre=lambda: hbuf.view(torch.int32).fill_(-1))
     t_fwd = time_kernel(lambda: check(lib().clv_lstm_fwd_fused(
         ptr(gates), 1, ptr(U), ptr(e.view("decoder_h.bias")), ptr(Wv), ptr(Kd[D + Z:]), Cc, ptr(Zs),
         ptr(Kd[D:D + Z]), Z, ptr(hbuf), ptr(cbuf), B, L, H, st)))
@@ -311,40 +410,58 @@ def main():
         ptr(Kd[D:D + Z]), Z, ptr(dZb), B, L, H, st)))
     t_tc = time_kernel(lambda: check(lib().clv_inproj_tc(
         ptr(e.roll), ptr(e.win_off), L, 1, D, ptr(Ke), G, G, ptr(scratch), ptr(gates), G, B * L, None, 0, 0, st)))
-    # algorithmic bytes per launch: streamed operands only, weights excluded
+    # algorithmic bytes / flops per launch: streamed operands only, weights excluded
     bytes_fwd = 4 * L * (2 * G + 2 * H + Z) * B                 # read xproj+Zs, write gates+h+c
     bytes_bwd = 4 * L * (2 * G + 3 * H + Z) * B + 4 * (G + Cc) * B   # read gates,c,dh; write dA,dZ,dAsum,dW
     bytes_tc = (D + 4 * G) * B * L                              # read uint8 roll rows, write fp32 projection
+    bytes_pair = 4 * L * B * (2 * (2 * G + 2 * H) + H + 4 * Z)  # both LSTMs + h_enc re-read + eps/Zargs/Zs
+    flop_rec = 2 * H * G * L * B                                # one recurrent mat-vec pass (h @ U)
+
+    def kentry(ms, nbytes, flop, launches, bound, note=None):
+        d = {"ms": ms, "bytes": nbytes, "GBps": nbytes / ms / 1e6, "frac_hbm": nbytes / ms / 1e6 / hbm_peak,
+             "launches_per_step": launches, "bound": bound}
+        if flop:
+            d.update({"flop": flop, "fp32_tflops": flop / ms / 1e9, "frac_issue": flop / ms / 1e9 / fp32_peak})
+        if note:
+            d["note"] = note
+        return d
+    lat = "latency/issue (serial recurrence: L dependent steps of a register-resident fp32 mat-vec; FFMA2 + LDS bound)"
     kern = {
-        "clv_lstm_bwd_fused": {"ms": t_bwd, "bytes": bytes_bwd, "GBps": bytes_bwd / t_bwd / 1e6,
-                               "launches_per_step": 2, "bound": "hbm (latency bound at B=200, FFMA-issue bound at large B)"},
-        "clv_lstm_fwd_fused": {"ms": t_fwd, "bytes": bytes_fwd, "GBps": bytes_fwd / t_fwd / 1e6,
-                               "launches_per_step": 2, "bound": "hbm (latency bound at B=200, FFMA-issue bound at large B)"},
-        "clv_inproj_tc (tcgen05)": {"ms": t_tc, "bytes": bytes_tc, "GBps": bytes_tc / t_tc / 1e6,
-                                    "launches_per_step": 2, "bound": "hbm"},
+        "clv_lstm_bwd_fused": kentry(t_bwd, bytes_bwd, flop_rec, 2, lat),
+        "clv_lstm_fwd_fused": kentry(t_fwd, bytes_fwd, flop_rec, 0 if pair_ok else 2, lat,
+                                     "replaced in the step by clv_lstm_pair_fwd when Z <= 2" if pair_ok else None),
+        "clv_inproj_tc (tcgen05)": kentry(t_tc, bytes_tc, 0, 2, "hbm"),
     }
-    dom = "clv_lstm_bwd_fused" if t_bwd >= t_fwd else "clv_lstm_fwd_fused"
-    # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
-    # (profiles/ncu_full_step_kernels_r1.md, B=200 L=16; profiles/ncu_full_large_batch_B16384_L32_r1.md)
-    ncu_traffic = {(200, 16): {"clv_lstm_bwd_fused": 7.01e6, "clv_lstm_fwd_fused": 4.74e6},
+    if pair_ok:
+        kern["clv_lstm_pair_fwd"] = kentry(t_pair, bytes_pair, 2 * flop_rec + 2 * H * 2 * Z * L * B, 1, lat,
+                                           "encoder + Z heads + decoder forward as one wavefront launch")
+    in_step = {k: v["ms"] * v["launches_per_step"] for k, v in kern.items()}
+    dom = max(in_step, key=in_step.get)
+    # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full captures
+    # (profiles/ncu_full_step_kernels_r1.md / _r2.md, B=200 L=16; profiles/ncu_full_large_batch_B16384_L32_r1.md)
+    ncu_traffic = {(200, 16): {"clv_lstm_bwd_fused": 7.01e6, "clv_lstm_fwd_fused": 4.74e6, "clv_lstm_pair_fwd": 9.40e6},
                    (16384, 32): {"clv_lstm_bwd_fused": 1.845e9}}
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["GBps"], "peak": hbm_peak,
-                "unit": "GB/s", "frac": kern[dom]["GBps"] / hbm_peak,
+    roofline = {"kernel": dom, "bound": "latency/issue", "achieved": kern[dom]["GBps"], "peak": hbm_peak,
+                "unit": "GB/s", "frac": kern[dom]["GBps"] / hbm_peak, "frac_hbm": kern[dom]["frac_hbm"],
+                "frac_issue": kern[dom].get("frac_issue"), "fp32_tflops": kern[dom].get("fp32_tflops"),
+                "fp32_tflops_measured_peak": fp32_peak, "fp32_tflops_matvec_operand_pattern": fp32["matvec_operand_pattern"],
                 "traffic": ncu_traffic.get((B, L), {}).get(dom),
-                "peak_source": peak_src,
-                "share_of_step": 2 * kern[dom]["ms"] / ms_step,
+                "peak_source": peak_src + "; fp32: clv_fp32_peak_probe run in this process",
+                "share_of_step": in_step[dom] / ms_step,
                 "note": "algorithmic bytes = streamed operands of one launch (DESIGN.md section 3); timed alone with "
                         "L2 flushed, so share_of_step is an upper bound (in the step the operands are L2-resident "
-                        "and the prologue overlaps the predecessor via PDL). At B=200 the recurrence is 100 CTAs x 2 "
-                        "rows x 16 serial steps: latency bound, DRAM traffic below the algorithmic bytes because "
-                        "the whole working set sits in the 126 MB L2; the HBM-bound kernel of the path is the "
-                        "tcgen05 projection (75-80% of measured peak at B>=16384, see `kernels` and profiles/)"}
+                        "and prologues overlap predecessors via PDL). The recurrences are neither HBM- nor "
+                        "tensor-bound at B=200: 4 rows x L serial steps per CTA, DRAM traffic below the algorithmic "
+                        "bytes (working set in L2); frac_issue = fp32 FLOP/s of the recurrent mat-vecs over the "
+                        "measured FMA-pipe peak. The HBM-bound kernel of the path is the tcgen05 projection "
+                        "(75-80% of measured peak at B>=16384, see `kernels` and profiles/)"}
 
     # ---------------- sampler: generate_sample for songs_per_gpu songs, Philox noise in-kernel
     sampler = None
     if not args.no_sampler:
         S, Ts, Ns, Cs = SAMPLER["songs_per_gpu"], SAMPLER["T_seed"], SAMPLER["nsteps"], SAMPLER["C"]
         smodel, _ = get_model(1, D, H, Z, L, Cs, True, "adam-wn", seed=7, use_graph=False)
+        from clvae_b200.cl_vrnn.model import make_w_encoder, infer_w_device
         T = Ts + Ns
         seeds = (torch.rand(S, Ts, D, device=devn) < 0.05).to(torch.uint8)
         seeds[:, :, :15] = 0; seeds[:, :, 76:] = 0
@@ -352,40 +469,110 @@ def main():
         wkey[torch.arange(S), torch.randint(0, Cs, (S,), device=devn)] = 1.0
         out = torch.zeros(S, T, D, dtype=torch.uint8, device=devn)
         cfg = smodel.engine.cfg()
+        w_enc = make_w_encoder(smodel, D, Cs, L)
 
-        def samp():
+        def samp(w):
             check(lib().clv_vrnn_sample(C.byref(cfg), ptr(smodel.engine.params), None, None, None,
-                                        ptr(seeds), Ts, Ns, ptr(wkey), None, None, 99, rank * S, S,
+                                        ptr(seeds), Ts, Ns, ptr(w), None, None, 99, rank * S, S,
                                         ptr(out), None, st))
+
+        def samp_infer():
+            samp(infer_w_device(w_enc, seeds, L, False))      # key inferred from the seed (cl_vrnn/model.py:34-41)
         for _ in range(2):
-            samp()
+            samp(wkey)
         barrier()
         reps = 3
         ev0.record()
         for _ in range(reps):
-            samp()
+            samp(wkey)
         ev1.record()
         barrier()
         ms_s = max_over_ranks(ev0.elapsed_time(ev1) / reps)
+        samp_infer()
+        barrier()
+        ev0.record()
+        samp_infer()
+        ev1.record()
+        barrier()
+        ms_i = max_over_ranks(ev0.elapsed_time(ev1))
         # e2e: host seeds in, host rolls out
         seeds_h = seeds.cpu().pin_memory(); w_h = wkey.cpu().pin_memory()
         out_h = torch.zeros(S, T, D, dtype=torch.uint8).pin_memory()
         barrier()
         ev0.record()
         seeds.copy_(seeds_h, non_blocking=True); wkey.copy_(w_h, non_blocking=True)
-        samp()
+        samp(wkey)
         out_h.copy_(out, non_blocking=True)
         ev1.record()
         barrier()
         ms_se = max_over_ranks(ev0.elapsed_time(ev1))
         flop = 2 * ((D + Cs) * G + H * G + H * 2 * Z + (D + Z + Cs) * G + H * G + H * D)
+        tfl = flop * S * T / (ms_s / 1e3) / 1e12
         sampler = {"metric": "cl_vrnn_sample_timesteps_per_sec", "value": S * T * world / (ms_s / 1e3),
                    "unit": "timesteps/s", "ms": ms_s, "songs": S * world, "steps_per_song": T,
+                   "inferred_key": {"value": S * T * world / (ms_i / 1e3), "unit": "timesteps/s", "ms": ms_i,
+                                    "note": "key inferred from the seed chunks (hW/Wargs GEMMs + softmax + chunk mean) then the same kernel"},
                    "e2e": {"value": S * T * world / (ms_se / 1e3), "unit": "timesteps/s",
                            "h2d_bytes": S * Ts * D + 4 * S * Cs, "d2h_bytes": S * T * D},
-                   "fp32_tflops": flop * S * T / (ms_s / 1e3) / 1e12,
+                   "fp32_tflops": tfl,
+                   "roofline": {"kernel": "vrnn_sample_kernel", "bound": "issue (fp32 FMA; weights stream from L2)",
+                                "achieved": tfl, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tfl / fp32_peak,
+                                "peak_source": "clv_fp32_peak_probe (FFMA2, this process)",
+                                "bytes_out_per_timestep": D, "hbm_GBps": S * T * D / (ms_s / 1e3) / 1e9},
                    "note": "given one-hot key, Philox noise keyed by (seed, global song, t); "
                            "density of generated notes depends on random-init weights"}
+
+    # ---------------- CL-VAE train step (BASELINE configs[0]: B=100, C=2, z=4, --use_x_prev), one GPU
+    vae = None
+    if rank == 0 and world == 1 and not args.no_vae:
+        from clvae_b200.cl_vae.model import get_model as get_vae
+        Bv, Cv, Zv = 100, 2, 4
+        vmodel, _ = get_vae(Bv, D, (88, Zv), (88, Cv), "adam-wn", use_x_prev=True, seed=11)
+        ve = vmodel.engine
+        vpool = torch.zeros(400_000, D, dtype=torch.uint8, device=devn)
+        vpool[:, 15:76] = (torch.rand(400_000, 61, device=devn) < 0.05).to(torch.uint8)
+        ve.set_resident_roll(vpool)
+        voff = torch.randint(0, 400_000 - 4, (64, Bv), dtype=torch.int32, device=devn)
+        vlab = torch.randint(0, Cv, (64, Bv), dtype=torch.int32, device=devn)
+
+        def vstep(i):
+            ve.stage_offsets(voff[i % 64], vlab[i % 64])
+            ve.run(train=True, gen_noise=True)
+        for i in range(Wm):
+            vstep(i)
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(K):
+            vstep(i)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms_v = ev0.elapsed_time(ev1) / K
+        vwin = [torch.from_numpy((rng.random((Bv, 2, D)) < 0.05).astype(np.uint8)).pin_memory() for _ in range(8)]
+        vl = [torch.from_numpy(rng.integers(0, Cv, Bv).astype(np.int32)).pin_memory() for _ in range(8)]
+        for i in range(Wm):
+            vmodel.train_on_batch_windows(vwin[i % 8], vl[i % 8])
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(K):
+            vmodel.train_on_batch_windows(vwin[i % 8], vl[i % 8])
+        ev1.record()
+        torch.cuda.synchronize()
+        ms_ve = ev0.elapsed_time(ev1) / K
+        vflop = 195360 * Bv                                     # fwd+bwd FLOP per frame
+        vae = {"metric": "cl_vae_train_frames_per_sec", "value": Bv / (ms_v / 1e3), "unit": "frames/s", "ms_per_step": ms_v,
+               "config": "CL-VAE B=100, C=2, latent_dim=4, --use_x_prev (BASELINE configs[0])",
+               "launches_per_step": int(ve.launches_per_step),
+               "e2e": {"value": Bv / (ms_ve / 1e3), "unit": "frames/s", "ms_per_step": ms_ve,
+                       "h2d_bytes_per_step": Bv * 2 * D + 4 * Bv, "d2h_bytes_per_step": 32},
+               "roofline": {"bound": "launch latency (%d dependent launches of a 100-row problem)" % int(ve.launches_per_step),
+                            "achieved": vflop / (ms_v / 1e3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                            "frac": vflop / (ms_v / 1e3) / 1e12 / fp32_peak,
+                            "us_per_launch": 1e3 * ms_v / max(1, int(ve.launches_per_step))}}
+        if not args.no_cpu_baseline:
+            rv = cpu_vae_train_port(steps=20, warmup=2, B=Bv, C=Cv, Z=Zv)
+            vae["cpu_baseline"] = {"value": rv["value"], "unit": "frames/s", "cores": rv["cores"], "kind": "port",
+                                   "sample": "20 CL-VAE train steps of B=100 on the oracle port (PyTorch-CPU f32)",
+                                   "ms_per_step": rv["ms_per_step"]}
 
     # ---------------- CPU baseline (rank 0, N=1 only)
     cpu = None
@@ -394,6 +581,10 @@ def main():
         cpu = {"value": r["value"], "unit": "sequences/s", "cores": r["cores"], "kind": "port",
                "sample": "20 train steps of B=200 L=16 on the oracle port (PyTorch-CPU f32, %d threads)" % r["cores"],
                "ms_per_step": r["ms_per_step"]}
+        if sampler is not None:
+            sv = cpu_sampler_port(2, 128)
+            sampler["cpu_baseline"] = {"value": sv, "unit": "timesteps/s", "cores": r["cores"], "kind": "port",
+                                       "sample": "2 songs x (16 seed + 128) steps, batch-1 Python loop (2 model calls per step)"}
 
     if rank == 0:
         line = {
@@ -402,12 +593,17 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world), "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(e.launches_per_step) * K, "launches_per_step": int(e.launches_per_step),
-            "roofline": roofline, "kernels": kern, "cpu_baseline": cpu, "sampler": sampler,
-            "final_losses": losses,
+            "roofline": roofline, "fp32_tflops_measured": fp32, "kernels": kern, "cpu_baseline": cpu,
+            "sampler": sampler, "cl_vae": vae, "final_losses": losses,
         }
+        if dp_parity is not None:
+            line["dp_parity_max_rel_err"] = dp_parity
         if B != CFG["B"] or L != CFG["L"]:
             line["config"]["workload"] = "cl_vrnn train step, synthetic sweep point B=%d/GPU L=%d" % (B, L)
         print(json.dumps(line), flush=True)
+        if dp_parity is not None and not dp_parity <= 1e-4:
+            print("DP PARITY FAILED: %g > 1e-4" % dp_parity, file=sys.stderr, flush=True)
+            dp_failed = True
     # teardown: NCCL kernels captured in CUDA graphs must be released before the communicator goes
     # away; a watchdog guarantees the process exits even if the communicator teardown stalls
     sys.stdout.flush()
@@ -424,6 +620,8 @@ def main():
         dist.destroy_process_group()
         wd.cancel()
     # normal return: interpreter exit hooks (atexit, the harness's loaded-library record) run
+    if dp_failed:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

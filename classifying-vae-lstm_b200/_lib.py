@@ -94,6 +94,7 @@ PROTOTYPES = {
                                   _P, _P, _P]),
     "clv_vae_sample": (C.c_int, [_CFG, _P, _P, _I32, _P, _P, _P, _U64, _I64, _I32, _I32, _P, _P, _P]),
     "clv_chunk_mean": (C.c_int, [_P, _P, _I32, _I32, _I32, _P]),
+    "clv_fp32_peak_probe": (C.c_int, [_I32, _P, _I64, C.POINTER(C.c_double), _P]),
 }
 
 class clv_adam_args(C.Structure):

@@ -199,6 +199,22 @@ int clv_lstm_bwd_heads(float* gates, const float* U, const float* c, const float
                        float klw_scale, float* dZargs_out, const float* dZargs_in, const float* Kzm,
                        const float* Kzv, int32_t Zh, int32_t B, int32_t L, int32_t H, void* stream);
 
+/* Encoder LSTM + Z heads / sampling / z-KL + decoder LSTM of one CL-VRNN forward pass
+ * (cl_vrnn/model.py:193-228,236-239) as ONE wavefront launch: CTA 2p = encoder of row group p (4 sequences),
+ * CTA 2p+1 = its decoder one or two steps behind; the decoder's helper warp computes Z_t from the encoder's
+ * h rows, which it polls through L2 until they differ from the 0xFFFFFFFF pattern the CALLER fills h_e with
+ * before the launch (no flags, no fences).  Arguments as clv_lstm_fwd_fused for both LSTMs (gates_*: hoisted
+ * projection in, activated gates out; K*_w: [C,4H] rows that multiply W; Kd_z: [Z,4H]) and as
+ * clv_gauss_heads_fwd for the heads (kl_scale = 1/(B_global L)).  H = 88, Z <= 2, C <= 16.
+ * The recurrence uses tanh through ex2.approx/rcp.approx (abs. error < 5e-7). */
+int clv_lstm_pair_fwd(float* gates_e, const float* Ue, const float* be, const float* Ke_w, float* h_e,
+                      float* c_e, float* gates_d, int32_t has_xproj_d, const float* Ud, const float* bd,
+                      const float* Kd_w, const float* Kd_z, float* h_d, float* c_d, const float* Wv, int32_t C,
+                      const float* Kzm, const float* bzm, const float* Kzv, const float* bzv, float* eps_z,
+                      float* Zargs, float* Zs, float* loss_acc, float kl_scale, int32_t gen_noise,
+                      uint64_t seed, const uint64_t* ctr, int32_t B, int32_t L, int32_t H, int32_t Z,
+                      void* stream);
+
 /* Tensor-core form of the forward recurrence for large batches: 128 rows per CTA, h_{t-1} @ U on
  * tcgen05 (fp16 hi+lo splits of both operands, 3 products, fp32 accumulate in TMEM), cell state in
  * TMEM, U resident in shared memory.  `gates` must already hold x@kernel + bias + W term (use
@@ -339,6 +355,14 @@ int clv_vae_sample(const clv_cfg* cfg, const float* params, const uint8_t* x_see
  * (key inference over seed chunks, cl_vrnn/model.py:34-41). */
 int clv_chunk_mean(const float* in, float* out, int32_t S, int32_t n_chunks, int32_t C,
                    void* stream);
+
+/* ---------------------------------------------------------------- diagnostics ------------ */
+/* Measured fp32 FMA throughput of this device in TFLOP/s (bench.py's issue-bound roofline denominator;
+ * MEASURED_PEAKS.json carries no fp32 figure).  mode 0: FMA-pipe peak (FFMA2, shared operands); mode 1: FFMA2
+ * in the 5-distinct-register operand pattern of the register-resident LSTM mat-vecs (register-file bank
+ * limited).  scratch: >= 2 * #SMs * 512 floats.  Unlike every other entry point it SYNCHRONISES. */
+int clv_fp32_peak_probe(int32_t mode, float* scratch, int64_t scratch_floats, double* tflops_out,
+                        void* stream);
 
 #ifdef __cplusplus
 }
