@@ -270,6 +270,7 @@ def main():
     # whole batch as N accumulated micro-batches (same kernels, same global-mean scaling)
     dp_parity, dp_failed = None, False
     if world > 1:
+        saved_roll = e.roll
         gcpu = torch.Generator().manual_seed(20171107)
         NB = world * B
         cwin = (torch.rand(NB, L + 1, D, generator=gcpu) < 0.06).to(torch.uint8)
@@ -288,22 +289,42 @@ def main():
         buf = torch.zeros(e.P + 8, device=devn)
         raw_step(slice(rank * B, (rank + 1) * B), buf[:e.P], buf[e.P:], False)
         dist.all_reduce(buf)
+        ref = torch.zeros(e.P + 8, device=devn)
         if rank == 0:
-            ref = torch.zeros(e.P + 8, device=devn)
             for r_ in range(world):
                 raw_step(slice(r_ * B, (r_ + 1) * B), ref[:e.P], ref[e.P:], r_ > 0)
-            torch.cuda.synchronize()
-            worst = 0.0
+
+        def worst_err(got):
+            w_ = 0.0
             for k_ in e.names + ["losses"]:
                 if k_ == "losses":
-                    a_, b_ = buf[e.P:e.P + 5], ref[e.P:e.P + 5]
+                    a_, b_ = got[e.P:e.P + 5], ref[e.P:e.P + 5]
                 else:
                     i_ = e.names.index(k_)
                     n_ = (e.rows[i_] if e.rows[i_] > 0 else 1) * e.cols[i_]
-                    a_, b_ = buf[e.offs[i_]:e.offs[i_] + n_], ref[e.offs[i_]:e.offs[i_] + n_]
-                worst = max(worst, float((a_ - b_).abs().max() / (b_.abs().max() + 1e-30)))
-            dp_parity = worst
-        e.roll = e.win_buf
+                    a_, b_ = got[e.offs[i_]:e.offs[i_] + n_], ref[e.offs[i_]:e.offs[i_] + n_]
+                w_ = max(w_, float((a_ - b_).abs().max() / (b_.abs().max() + 1e-30)))
+            return w_
+        torch.cuda.synchronize()
+        if rank == 0:
+            dp_parity = worst_err(buf)
+        # ... and the PRODUCT path (scheduled step with the exchange fused in): after one step on the same
+        # sharded batch every rank must hold the parameters of a reference Adam-WN update with `ref`
+        p0, s0 = e.params.clone(), e.opt_state.clone()
+        sl = slice(rank * B, (rank + 1) * B)
+        e.stage_windows(cwin[sl].to(devn), clab[sl].to(devn))
+        e.eps_w.copy_(cew[sl].reshape(-1)); e.eps_z.copy_(cez[sl].reshape(-1))
+        e.run(train=True, gen_noise=False)
+        torch.cuda.synchronize()
+        dist.broadcast(ref, src=0)
+        check(lib().clv_adamwn_step(C.byref(e.cfg()), ptr(p0), ptr(ref), ptr(s0), e.lr, e.b1, e.b2, e.eps, 1.0,
+                                    int(e.optimizer == "adam-wn"), stc), "clv_adamwn_step")
+        torch.cuda.synchronize()
+        perr = torch.tensor([float((e.params - p0).abs().max() / p0.abs().max())], device=devn)
+        dist.all_reduce(perr, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            dp_parity = max(dp_parity, float(perr.item()))
+        e.roll = saved_roll                     # back to the resident pool
         barrier()
 
     for i in range(Wm):

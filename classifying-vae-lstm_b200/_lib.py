@@ -94,6 +94,10 @@ PROTOTYPES = {
                                   _P, _P, _P]),
     "clv_vae_sample": (C.c_int, [_CFG, _P, _P, _I32, _P, _P, _P, _U64, _I64, _I32, _I32, _P, _P, _P]),
     "clv_chunk_mean": (C.c_int, [_P, _P, _I32, _I32, _I32, _P]),
+    "clv_p2p_flag_ints": (C.c_int, []),
+    "clv_p2p_signal": (C.c_int, [_P, _P, _CFG, _I32, _P]),
+    "clv_p2p_wait_done": (C.c_int, [_P, _P, _CFG, _P]),
+    "clv_adamwn_step_range_p2p": (C.c_int, [_CFG, _P, _P, _P, _D, _D, _D, _D, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "clv_fp32_peak_probe": (C.c_int, [_I32, _P, _I64, C.POINTER(C.c_double), _P]),
 }
 
@@ -101,7 +105,18 @@ class clv_adam_args(C.Structure):
     """include/clv_b200.h: clv_adam_args (optimizer settings of clv_train_step_opt)."""
     _fields_ = [("state", C.c_void_p), ("lr", C.c_double), ("beta_1", C.c_double), ("beta_2", C.c_double),
                 ("epsilon", C.c_double), ("grad_scale", C.c_double), ("weightnorm", C.c_int32),
-                ("loss_mirror", C.c_void_p)]
+                ("loss_mirror", C.c_void_p), ("exchange", C.c_void_p), ("exchange_user", C.c_void_p),
+                ("p2p", C.c_void_p)]
+
+
+class clv_p2p_args(C.Structure):
+    """include/clv_b200.h: clv_p2p_args (peer-memory data parallelism, hand-shake inside the kernels)."""
+    _fields_ = [("peer_grads", C.c_void_p), ("peer_flags", C.c_void_p), ("n_peers", C.c_int32), ("rank", C.c_int32),
+                ("gsum", C.c_void_p), ("loss_out", C.c_void_p)]
+
+
+# include/clv_b200.h: clv_exchange_fn(user, buf, count, stream) -> int
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
 
 _lib = None

@@ -6,6 +6,7 @@
 // Adam (p -= lr_t * m / (sqrt(v) + eps)) [K2-recall (7)].
 // A block owns 8 (short tensors) or 4 (tall tensors) adjacent columns of one matrix; see below.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -29,7 +30,24 @@ struct PeerSet {
   int n;
   float* gsum;                 // local scratch [P]: reduced gradient for the second pass
   float* loss_out;             // local [8]: reduced loss scalars
+  // in-kernel hand-shake (clv_p2p_args): flag blocks of every rank in peer-mapped memory
+  int32_t* const* flags;       // device array of n pointers, or null (caller-side barriers)
+  int rank, slot, reduce_losses;
 };
+
+// flag block of one rank: ready[slot][src rank] = step number whose gradients of bucket `slot` rank `src` has
+// finished writing; done[src] = step number after which `src` no longer reads anyone's gradients
+constexpr int P2P_MAXR = 16, P2P_SLOTS = 4;
+__device__ __forceinline__ int32_t* flag_ready(int32_t* f, int slot, int src) { return f + slot * P2P_MAXR + src; }
+__device__ __forceinline__ int32_t* flag_done(int32_t* f, int src) { return f + P2P_SLOTS * P2P_MAXR + src; }
+__device__ __forceinline__ int ld_acquire_sys(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int32_t* p, const int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 template <bool P2P>
 __device__ __forceinline__ float load_grad(const float* __restrict__ G, const PeerSet& ps, int64_t e) {
@@ -59,14 +77,20 @@ __device__ __forceinline__ void col_reduce(float (&val)[NV], float (*red)[32][8]
     if (lane < ct) red[i][wid][lane] = val[i];
   }
   __syncthreads();
-  if (tid < ct) {
+  // warp c sums the 32 warp partials of column c with a shuffle tree (a serial loop over the 32 partials by
+  // one thread per column was ~1 us per reduction, three times per launch on the step's tail)
+  if (wid < ct) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      float a = 0.f;
-#pragma unroll
-      for (int w = 0; w < NTH / 32; ++w) a += red[i][w][tid];
-      val[i] = a;
+      float a = red[i][lane][wid];
+      a = warp_sum(a);
+      if (lane == 0) red[i][0][wid] = a;
     }
+  }
+  __syncthreads();
+  if (tid < ct) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) val[i] = red[i][0][tid];
   }
 }
 
@@ -79,16 +103,44 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
                                                      const int weightnorm, const PeerSet ps,
                                                      const int block_base, const int advance,
                                                      float* __restrict__ loss_mirror) {
-  pdl_wait();   // no-op unless launched as a programmatic dependent
-  if (P2P && blockIdx.x == 0 && threadIdx.x < 8) {
-    float v = 0.f;
-    for (int p = 0; p < ps.n; ++p) v += ps.peers[p][pl.P + threadIdx.x];
-    ps.loss_out[threadIdx.x] = v;
+  // (the programmatic-dependent wait comes later: everything up to the first gradient read touches only
+  //  state that no kernel of this step writes -- this range's W, m, v, V_scaler, the iteration counter)
+  int tnow_p2p = 0;
+  if (P2P) {
+    pdl_wait();
+    if (ps.flags) {
+      // This launch is stream-ordered behind the kernels that produced bucket `slot` of this rank, so its first
+      // block publishes the bucket: the step number goes into every peer's flag block over NVLink.  The wait
+      // for the peers' signals comes later (p2p_wait_peers), after the local operands have been fetched, so
+      // the one-way NVLink latency of the hand-shake overlaps useful loads.  A rank's signal never depends on
+      // another rank's progress, so the waits cannot deadlock.
+      tnow_p2p = *reinterpret_cast<const int*>(state + 2 * pl.P + 3 * (int64_t)pl.NC + 2) + 1;
+      if (blockIdx.x == 0 && threadIdx.x < ps.n) {
+        __threadfence_system();
+        st_release_sys(flag_ready(ps.flags[threadIdx.x], ps.slot, ps.rank), tnow_p2p);
+      }
+    }
+  }
+  // every peer has published bucket `slot` of THIS step: poll LOCAL memory (the peers store into my block)
+  auto p2p_wait_peers = [&]() {
+    if (P2P && ps.flags) {
+      if (threadIdx.x < ps.n) {
+        // relaxed polls (an acquire per poll is a system-scope fence each time), one fence after the last
+        const volatile int32_t* f = flag_ready(ps.flags[ps.rank], ps.slot, threadIdx.x);
+        while (*f < tnow_p2p) { }
+        __threadfence_system();
+      }
+      __syncthreads();
+    }
+  };
+  const bool red_losses = P2P && ps.reduce_losses && blockIdx.x == 0;
+  if (red_losses && threadIdx.x < 8) {     // (after the wait above: every block passes exactly one p2p_wait_peers)
+    float lv = 0.f;
+    for (int p = 0; p < ps.n; ++p) lv += ps.peers[p][pl.P + threadIdx.x];
+    ps.loss_out[threadIdx.x] = lv;
   }
   // the advancing (last) launch of a step also mirrors the 8 loss scalars that follow the gradients
   // to `loss_mirror` (host-mapped pinned memory: the caller then needs a stream sync, not a D2H copy)
-  if (!P2P && loss_mirror && advance && blockIdx.x == 0 && threadIdx.x < 8)
-    loss_mirror[threadIdx.x] = G[pl.P + threadIdx.x];
   __shared__ float red[2][32][8];
   __shared__ float col[4][8];
   __shared__ float lr_s;
@@ -129,13 +181,17 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
   if (rows == 0 || !weightnorm) {  // plain Adam on a flat chunk
     const int64_t n = (rows == 0) ? cols : (int64_t)rows * cols;
     const int64_t i = (int64_t)lb * NTH + tid;
+    float w0 = 0.f, m0 = 0.f, v0 = 0.f;
+    if (i < n) { w0 = W[off + i]; m0 = m[off + i]; v0 = v[off + i]; }
+    if (!P2P) pdl_wait();
+    p2p_wait_peers();
     if (i < n) {
       const float g = load_grad<P2P>(G, ps, off + i) * gscale;
-      const float mt = b1 * m[off + i] + (1.0f - b1) * g;
-      const float vt = b2 * v[off + i] + (1.0f - b2) * g * g;
+      const float mt = b1 * m0 + (1.0f - b1) * g;
+      const float vt = b2 * v0 + (1.0f - b2) * g * g;
       m[off + i] = mt;
       v[off + i] = vt;
-      W[off + i] -= lr_t * mt / (sqrtf(vt) + eps);
+      W[off + i] = w0 - lr_t * mt / (sqrtf(vt) + eps);
     }
   } else {
     const int ct = adam_ct(rows), rl = NTH / ct;
@@ -155,14 +211,28 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
         Wr[u] = Gr[u] = Mr[u] = Vr[u] = 0.f;
         if (cv && r < rows) {
           const int64_t e = off + (int64_t)r * cols + c;
+          Wr[u] = W[e] / vs; Mr[u] = m[e]; Vr[u] = v[e];
+        }
+      }
+      if (!P2P) pdl_wait();      // the gradients are the only operands the predecessor writes
+      p2p_wait_peers();
+#pragma unroll
+      for (int u = 0; u < NRF; ++u) {
+        const int r = ry + u * rl;
+        if (cv && r < rows) {
+          const int64_t e = off + (int64_t)r * cols + c;
           const float graw = load_grad<P2P>(G, ps, e);
           if (P2P) ps.gsum[e] = graw;
-          Wr[u] = W[e] / vs; Gr[u] = graw * gscale; Mr[u] = m[e]; Vr[u] = v[e];
+          Gr[u] = graw * gscale;
         }
       }
 #pragma unroll
       for (int u = 0; u < NRF; ++u) { s2[0] = fmaf(Wr[u], Wr[u], s2[0]); s2[1] = fmaf(Gr[u], Wr[u], s2[1]); }
-    } else if (cv) {
+    } else {
+      if (!P2P) pdl_wait();
+      p2p_wait_peers();
+    }
+    if (!in_regs && cv) {
 #pragma unroll 4
       for (int r = ry; r < rows; r += rl) {
         const int64_t e = off + (int64_t)r * cols + c;
@@ -272,6 +342,15 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
       }
     }
   }
+  if (red_losses && threadIdx.x < 8) {     // (after the wait above: every block passes exactly one p2p_wait_peers)
+    float lv = 0.f;
+    for (int p = 0; p < ps.n; ++p) lv += ps.peers[p][pl.P + threadIdx.x];
+    ps.loss_out[threadIdx.x] = lv;
+  }
+  // the advancing (last) launch of a step also mirrors the 8 loss scalars that follow the gradients
+  // to `loss_mirror` (host-mapped pinned memory: the caller then needs a stream sync, not a D2H copy)
+  if (loss_mirror && advance && blockIdx.x == 0 && threadIdx.x < 8)
+    loss_mirror[threadIdx.x] = P2P ? ps.loss_out[threadIdx.x] : G[pl.P + threadIdx.x];
   // last block to finish advances `iterations` (only the final launch of a step is told to) and
   // caches the bias-correction factor of the next step
   if (!advance) return;
@@ -286,7 +365,30 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
       __threadfence();
       *iter = t;
       *done = 0u;
+      if (P2P && ps.flags) {
+        // this rank has finished reading every peer's gradients of step t (the other buckets' kernels were
+        // joined before this launch): tell the peers their buffers may be overwritten
+        __threadfence_system();
+        for (int p = 0; p < ps.n; ++p) st_release_sys(flag_done(ps.flags[p], ps.rank), t);
+      }
     }
+  }
+}
+
+// bucket `slot` of this rank's gradient buffer is final: publish the step number to every peer's flag block
+__global__ void p2p_signal_kernel(int32_t* const* flags, const int n, const int rank, const int slot,
+                                  const int* iter) {
+  pdl_wait();
+  const int t = *iter + 1;
+  __threadfence_system();
+  if ((int)threadIdx.x < n) st_release_sys(flag_ready(flags[threadIdx.x], slot, rank), t);
+}
+// start of a step: no peer is still reading this rank's gradient buffer of the previous step
+__global__ void p2p_wait_done_kernel(int32_t* const* flags, const int n, const int rank, const int* iter) {
+  const int tprev = *iter;
+  if ((int)threadIdx.x < n) {
+    const int32_t* f = flag_done(flags[rank], threadIdx.x);
+    while (ld_acquire_sys(f) < tprev) __nanosleep(64);
   }
 }
 
@@ -345,7 +447,7 @@ extern "C" int clv_adamwn_step_range(const clv_cfg* cfg, float* params, const fl
   AdamPlan pl;
   int rc = make_plan(cfg, &pl, weightnorm);
   if (rc != CLV_OK) return rc;
-  PeerSet ps = {nullptr, 0, nullptr, nullptr};
+  PeerSet ps = {nullptr, 0, nullptr, nullptr, nullptr, 0, 0, 0};
   const int nb = pl.first_block[t_last] - pl.first_block[t_first];
   if (nb <= 0) return CLV_OK;
   CLV_CUDA(clv_launch(adamwn_kernel<false>, nb, NTH, 0, (cudaStream_t)stream, pl, params, grads, state, lr,
@@ -371,9 +473,61 @@ extern "C" int clv_adamwn_step_p2p(const clv_cfg* cfg, float* params, const floa
   AdamPlan pl;
   int rc = make_plan(cfg, &pl, weightnorm);
   if (rc != CLV_OK) return rc;
-  PeerSet ps = {peer_grads, n_peers, gsum, loss_out};
+  PeerSet ps = {peer_grads, n_peers, gsum, loss_out, nullptr, 0, 0, 1};
   adamwn_kernel<true><<<pl.first_block[CLV_N_TENSORS], NTH, 0, (cudaStream_t)stream>>>(
       pl, params, nullptr, state, lr, beta_1, beta_2, (float)epsilon, 1.0f, weightnorm, ps, 0, 1, nullptr);
+  CLV_CHECK_LAUNCH();
+  return CLV_OK;
+}
+
+// ---- peer-memory data parallelism with the hand-shake inside the kernels (clv_p2p_args) ------------------
+extern "C" int clv_p2p_flag_ints(void) { return (P2P_SLOTS + 1) * P2P_MAXR; }
+
+extern "C" int clv_p2p_signal(const clv_p2p_args* pp, const float* state, const clv_cfg* cfg, int32_t slot,
+                              void* stream) {
+  if (!pp || !state || !cfg || slot < 0 || slot >= P2P_SLOTS || pp->n_peers < 1 || pp->n_peers > P2P_MAXR)
+    return CLV_E_INVALID;
+  AdamPlan pl;
+  int rc = make_plan(cfg, &pl, 1);
+  if (rc != CLV_OK) return rc;
+  const int* iter = reinterpret_cast<const int*>(state + 2 * pl.P + 3 * (int64_t)pl.NC + 2);
+  CLV_CUDA(clv_launch(p2p_signal_kernel, 1, 32, 0, (cudaStream_t)stream, pp->peer_flags, (int)pp->n_peers,
+                      (int)pp->rank, (int)slot, iter));
+  CLV_CHECK_LAUNCH();
+  return CLV_OK;
+}
+
+extern "C" int clv_p2p_wait_done(const clv_p2p_args* pp, const float* state, const clv_cfg* cfg, void* stream) {
+  if (!pp || !state || !cfg || pp->n_peers < 1 || pp->n_peers > P2P_MAXR) return CLV_E_INVALID;
+  AdamPlan pl;
+  int rc = make_plan(cfg, &pl, 1);
+  if (rc != CLV_OK) return rc;
+  const int* iter = reinterpret_cast<const int*>(state + 2 * pl.P + 3 * (int64_t)pl.NC + 2);
+  p2p_wait_done_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pp->peer_flags, (int)pp->n_peers, (int)pp->rank, iter);
+  CLV_CHECK_LAUNCH();
+  return CLV_OK;
+}
+
+extern "C" int clv_adamwn_step_range_p2p(const clv_cfg* cfg, float* params, const clv_p2p_args* pp, float* state,
+                                         double lr, double beta_1, double beta_2, double epsilon,
+                                         int32_t weightnorm, int32_t t_first, int32_t t_last, int32_t slot,
+                                         int32_t advance, float* loss_mirror, void* stream) {
+  if (!cfg || !params || !pp || !state || !pp->peer_grads || !pp->peer_flags || !pp->gsum || !pp->loss_out)
+    return CLV_E_INVALID;
+  if (t_first < 0 || t_last > CLV_N_TENSORS || t_first >= t_last || slot < 0 || slot >= P2P_SLOTS)
+    return CLV_E_INVALID;
+  if (pp->n_peers < 1 || pp->n_peers > P2P_MAXR || pp->rank < 0 || pp->rank >= pp->n_peers) return CLV_E_INVALID;
+  AdamPlan pl;
+  int rc = make_plan(cfg, &pl, weightnorm);
+  if (rc != CLV_OK) return rc;
+  PeerSet ps = {pp->peer_grads, pp->n_peers, pp->gsum, pp->loss_out, pp->peer_flags, pp->rank, slot,
+                t_last == CLV_N_TENSORS ? 1 : 0};
+
+  const int nb = pl.first_block[t_last] - pl.first_block[t_first];
+  if (nb <= 0) return CLV_OK;
+  CLV_CUDA(clv_launch(adamwn_kernel<true>, nb, NTH, 0, (cudaStream_t)stream, pl, params, (const float*)nullptr,
+                      state, lr, beta_1, beta_2, (float)epsilon, 1.0f, (int)weightnorm, ps,
+                      pl.first_block[t_first], (int)advance, loss_mirror));
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }

@@ -188,6 +188,11 @@ struct SideStream {
 };
 SideStream g_side[16];
 
+static bool side_ready() {
+  int dev = 0;
+  return cudaGetDevice(&dev) == cudaSuccess && dev < 16 && g_side[dev].ready;
+}
+
 // Independent side work (weight gradients, the decoder's roll projection) is spread round-robin
 // over NAUX auxiliary streams so those launch-latency-bound kernels overlap each other as well as
 // the critical path.
@@ -242,7 +247,15 @@ struct Fork {
 int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uint8_t* roll,
               const int32_t* off, const int32_t* labels, float* eps_w, float* eps_z,
               uint64_t* ctr, float* ws, cudaStream_t st, const clv_adam_args* opt) {
-  auto adam = [&](int t0, int t1, int advance, cudaStream_t s_) {
+  // Adam-WN of the tensor range [t0, t1).  Peer-memory data parallelism (opt->p2p): the range is a gradient
+  // bucket -- the update kernel publishes it to the peers, waits for the peers' signals and sums their buffers
+  // over NVLink (all-reduce fused into the optimizer, slot = bucket id)
+  auto adam = [&](int t0, int t1, int advance, cudaStream_t s_, int slot) -> int {
+    if (opt->p2p) {
+      return clv_adamwn_step_range_p2p(c, const_cast<float*>(P), opt->p2p, opt->state, opt->lr, opt->beta_1,
+                                       opt->beta_2, opt->epsilon, opt->weightnorm, t0, t1, slot, advance,
+                                       advance ? opt->loss_mirror : nullptr, s_);
+    }
     return clv_adamwn_step_range(c, const_cast<float*>(P), Gr, opt->state, opt->lr, opt->beta_1, opt->beta_2,
                                  opt->epsilon, opt->grad_scale, opt->weightnorm, t0, t1, advance,
                                  advance ? opt->loss_mirror : nullptr, s_);
@@ -280,13 +293,24 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   // encoder/decoder wavefront (lstm_pair.cu): both recurrences in one launch, the decoder a step or two
   // behind the encoder; needs the 2-latent head exchange and the FFMA recurrence
   const bool pair = !tcl && Z <= 2 && H == 88 && C <= 16 && !pair_disabled();
-  if (c->do_backward && !c->accumulate)
-    CLV_CUDA(cudaMemsetAsync(Gr, 0, sizeof(float) * (po[R_X_B] + pc[R_X_B]), st));
+  // zero the gradients; data parallel over peer memory: only once no peer still reads last step's (both off
+  // the critical path when side streams exist: nothing writes a gradient before the first join)
+  const bool side_zero = opt && opt->p2p && c->overlap_wgrad != 0 && side_ready() && c->do_backward && !c->accumulate;
+  if (!side_zero) {
+    if (opt && opt->p2p) TRY(clv_p2p_wait_done(opt->p2p, opt->state, c, st));
+    if (c->do_backward && !c->accumulate)
+      CLV_CUDA(cudaMemsetAsync(Gr, 0, sizeof(float) * (po[R_X_B] + pc[R_X_B]), st));
+  }
   // wavefront hand-over: the consumer polls the producer's rows themselves; 0xFFFFFFFF = "not written yet"
   if (pair) CLV_CUDA(cudaMemsetAsync(h_e, 0xFF, sizeof(float) * (size_t)BL * H, st));
   TRY(clv_step_begin(loss, ctr, !c->accumulate, c->gen_noise, st));   // last: the key encoder chains on it
 
   Fork fk(st, c->overlap_wgrad != 0);
+  if (side_zero) {
+    TRY(fk.fork());
+    TRY(clv_p2p_wait_done(opt->p2p, opt->state, c, fk.opt_stream()));
+    CLV_CUDA(cudaMemsetAsync(Gr, 0, sizeof(float) * (po[R_X_B] + pc[R_X_B]), fk.opt_stream()));
+  }
   const bool fused_ke = (int64_t)L * D <= 65535 && (D % 4) == 0;
   const float* Ke_w = Ke + (int64_t)D * G;            // rows of the kernels that multiply W
   const float* Kd_z = Kd + (int64_t)xo * G;           //                               ... Z
@@ -418,11 +442,15 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
     // K2b bwd overwrites dh: its only reader (decoder BPTT) is ordered before it on st
     TRY_PDL(clv_gauss_heads_bwd(h_e, Kzm, Kzv, eps_z, Zargs, dZ, dh, gKzm, gbzm, gKzv, gbzv, BL, H, Z, klw, 0, st));
   }
+  // data parallel through the host callback (NCCL): ONE all-reduce of the whole buffer after the last weight
+  // gradient, then one update (measured: a second all-reduce overlapped with the encoder BPTT costs more than
+  // it hides -- 0.178 vs 0.163 ms/step at N=2); the peer-memory form keeps the three-bucket schedule of N=1
+  const bool dp = opt && opt->exchange && !opt->p2p;
   if (opt) {   // decoder and X-head gradients are complete once the side branches drain; the Z heads
                // stay out of this range: the encoder BPTT below still reads their kernels
     TRY(fk.fork());
     TRY(fk.gather());
-    TRY(adam(R_DEC_K, CLV_N_TENSORS, 0, fk.opt_stream()));
+    if (!dp) TRY(adam(R_DEC_K, CLV_N_TENSORS, 0, fk.opt_stream(), 0));
   }
   if (fuse_heads)
     TRY_PDL(clv_lstm_bwd_heads(gates_e, Ue, c_e, nullptr, dAsum_e, Ke_w, C, dW_ext, 1, nullptr, 0, nullptr,
@@ -443,7 +471,9 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
     TRY_PDL(clv_keyenc_bwd_full(roll, off, sx, L, D, Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, gKhw,
                                 gbhw, gKwa, gbwa, B, C, c->w_log_var_prior, c->class_weight * sb,
                                 c->w_kl_weight * sb, st));
-    if (opt) TRY_PDL(adam(R_HW_K, R_ENC_K, 0, st));   // key-encoder tensors: overlaps the encoder wgrads
+    // key-encoder tensors: overlaps the encoder wgrads (one GPU).  Over peer memory every bucket on the tail
+    // costs a hand-shake + a remote read (~10 us): there the key encoder joins the last bucket instead
+    if (opt && !dp && !opt->p2p) TRY_PDL(adam(R_HW_K, R_ENC_K, 0, st, 1));
   } else {
     TRY(clv_keyenc_bwd(Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, B, C, D,
                        c->w_log_var_prior, c->class_weight * sb, c->w_kl_weight * sb, st));
@@ -454,7 +484,12 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
     TRY(clv_colsum(dhW, D, B, D, gbhw, 1, fk.next()));
   }
   TRY(fk.join());
-  if (opt) TRY(adam(fused_ke ? R_ENC_K : R_HW_K, R_DEC_K, 1, st));
+  if (dp) {
+    if (opt->exchange(opt->exchange_user, Gr, po[R_X_B] + pc[R_X_B] + 8, (void*)st) != 0) return CLV_E_CUDA;
+    TRY(adam(R_HW_K, CLV_N_TENSORS, 1, st, 0));
+  } else if (opt) {
+    TRY(adam((fused_ke && !opt->p2p) ? R_ENC_K : R_HW_K, R_DEC_K, 1, st, 2));
+  }
   return CLV_OK;
 }
 
@@ -481,6 +516,7 @@ int vae_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uin
               *Kzv = P + po[V_ZV_K], *bzv = P + po[V_ZV_B], *Kdh = P + po[V_DH_K],
               *bdh = P + po[V_DH_B], *Kx = P + po[V_X_K], *bx = P + po[V_X_B];
 
+  if (opt && opt->p2p) TRY(clv_p2p_wait_done(opt->p2p, opt->state, c, st));
   TRY(clv_step_begin(loss, ctr, !c->accumulate, c->gen_noise, st));
   if (c->do_backward && !c->accumulate)
     CLV_CUDA(cudaMemsetAsync(Gr, 0, sizeof(float) * (po[V_X_B] + pc[V_X_B]), st));
@@ -536,10 +572,16 @@ int vae_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uin
   TRY(nt_f32(dWargs + C1, 2 * C1, Kwv, C1, dh_w, Hc, B, Hc, C1, h_w, Hc, 1, st));
   TRY(tn_u8(roll, off, 1, sx, D, dh_w, Hc, gKhw, Hc, D, Hc, B, st));
   TRY(clv_colsum(dh_w, Hc, B, Hc, gbhw, 1, st));
-  if (opt)
+  if (opt && opt->p2p) {
+    TRY(clv_adamwn_step_range_p2p(c, const_cast<float*>(P), opt->p2p, opt->state, opt->lr, opt->beta_1, opt->beta_2,
+                                  opt->epsilon, opt->weightnorm, 0, CLV_N_TENSORS, 0, 1, opt->loss_mirror, st));
+  } else if (opt) {
+    if (opt->exchange && opt->exchange(opt->exchange_user, Gr, po[V_X_B] + pc[V_X_B] + 8, (void*)st) != 0)
+      return CLV_E_CUDA;
     TRY(clv_adamwn_step_range(c, const_cast<float*>(P), Gr, opt->state, opt->lr, opt->beta_1, opt->beta_2,
                               opt->epsilon, opt->grad_scale, opt->weightnorm, 0, CLV_N_TENSORS, 1,
                               opt->loss_mirror, st));
+  }
   return CLV_OK;
 }
 
@@ -623,6 +665,12 @@ static int train_step_impl(const clv_cfg* cfg, const float* params, float* grads
   if (cfg->do_backward && !grads) return CLV_E_INVALID;
   if (cfg->gen_noise && !rng_ctr) return CLV_E_INVALID;
   if (opt && (!opt->state || !cfg->do_backward || cfg->accumulate)) return CLV_E_INVALID;
+  if (opt && (opt->loss_mirror || opt->exchange || opt->p2p)) {
+    // both read the 8 loss scalars at grads[P..P+8): the caller must pass the [grads | losses] buffer
+    int64_t po_[CLV_N_TENSORS]; int32_t pr_[CLV_N_TENSORS], pc_[CLV_N_TENSORS];
+    const int64_t P_ = clv_param_layout(cfg, po_, pr_, pc_);
+    if (P_ < 0 || loss_acc != grads + P_) return CLV_E_INVALID;
+  }
   if (workspace_bytes < carve(cfg).total * (int64_t)sizeof(float)) return CLV_E_WORKSPACE;
   if (cfg->B == 0) return CLV_OK;
   cudaStream_t st = (cudaStream_t)stream;

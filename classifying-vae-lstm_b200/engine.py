@@ -10,11 +10,12 @@ graph cl_vrnn/model.py:169-264; optimizer utils/weightnorm.py:75-143).
 """
 import ctypes as C
 import math
+import os
 import numpy as np
 import torch
 
 from . import _lib
-from ._lib import lib, check, ptr, clv_adam_args
+from ._lib import lib, check, ptr, clv_adam_args, clv_p2p_args
 
 VRNN_TENSORS = ["hW.kernel", "hW.bias", "Wargs.kernel", "Wargs.bias",
                 "encoder_h.kernel", "encoder_h.recurrent_kernel", "encoder_h.bias",
@@ -78,13 +79,20 @@ class Engine:
         self.P, self.offs, self.rows, self.cols = _lib.param_layout(cfg)
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.params = torch.zeros(self.P, **f32)
-        # [grads | 8 loss scalars].  Data parallel default: one NCCL all-reduce of this buffer inside the
-        # step's CUDA graph.  Opt-in (p2p_allreduce=True): the buffer lives in symmetric (peer-mapped)
-        # memory and the all-reduce is fused into the Adam-WN kernel (clv_adamwn_step_p2p).  Measured on
-        # this pool the fused form is still slower (N=2: 0.339 vs 0.307 ms/step, N=8: 0.360 vs 0.325):
-        # two stream barriers + latency-bound peer reads cost more than NCCL's 1 MB all-reduce.
+        # [grads | 8 loss scalars].  Data parallel (world_size > 1), two forms:
+        #  * default: ONE NCCL all-reduce of the whole buffer, enqueued by the library through the exchange
+        #    callback after the last weight gradient, then one Adam-WN launch -- all inside clv_train_step_opt
+        #    and the step's CUDA graph (N=2: 0.164 ms/step against 0.139 for two uncoupled ranks);
+        #  * p2p_allreduce=True (opt-in): the buffer and a small flag block live in peer-mapped (symmetric)
+        #    memory; the Adam-WN kernel of each gradient bucket publishes the bucket to the peers, waits for their
+        #    flags, reads their gradients over NVLink and applies the update -- all-reduce fused into the
+        #    optimizer, no collective launch, no host barrier (clv_p2p_args).  Parity-tested
+        #    (tests/dist_p2p_check.py) but measured slower on this pool: every hand-shake + remote read costs
+        #    15-20 us per bucket kernel (profiles/p2p_probe.py: 59 vs 21 us for the two bucket updates at N=2),
+        #    0.177-0.182 ms/step.
         self.symm = None
-        if world_size > 1 and p2p_allreduce:
+        self.p2p = None
+        if world_size > 1 and p2p_allreduce is not False:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 group = process_group if process_group is not None else torch.distributed.group.WORLD
@@ -93,11 +101,25 @@ class Engine:
                 self.symm = symm_mem.rendezvous(self.gradbuf, group)
                 self.peer_ptrs = torch.tensor([int(x) for x in self.symm.buffer_ptrs], dtype=torch.int64,
                                               device=self.dev)
+                nfl = int(lib().clv_p2p_flag_ints())
+                self.flagbuf = symm_mem.empty(nfl, dtype=torch.int32, device=self.dev)
+                self.flagbuf.zero_()
+                self.symm_flags = symm_mem.rendezvous(self.flagbuf, group)
+                self.peer_flag_ptrs = torch.tensor([int(x) for x in self.symm_flags.buffer_ptrs], dtype=torch.int64,
+                                                   device=self.dev)
                 self.gsum = torch.zeros(self.P, **f32)
                 self.loss_red = torch.zeros(8, **f32)
+                self.p2p = clv_p2p_args(peer_grads=self.peer_ptrs.data_ptr(), peer_flags=self.peer_flag_ptrs.data_ptr(),
+                                        n_peers=world_size, rank=rank, gsum=self.gsum.data_ptr(),
+                                        loss_out=self.loss_red.data_ptr())
+                torch.cuda.synchronize(self.dev)
+                torch.distributed.barrier(group=process_group)        # every rank's flags are zero before any signal
             except Exception as ex:  # noqa: BLE001
-                print("[clvae_b200] symmetric memory unavailable (%s): using NCCL all-reduce" % (ex,))
+                if p2p_allreduce is True:
+                    raise
+                print("[clvae_b200] symmetric memory unavailable (%s): using the NCCL all-reduce path" % (ex,))
                 self.symm = None
+                self.p2p = None
         if self.symm is None:
             self.gradbuf = torch.zeros(self.P + 8, **f32)
         self.grads, self.loss_acc = self.gradbuf[:self.P], self.gradbuf[self.P:]
@@ -119,6 +141,8 @@ class Engine:
         self.loss_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self._loss_mirrored = False      # loss_host already holds the last step's scalars
         self.launches_per_step = 0
+        self._exchange_cb = _lib.EXCHANGE_FN(self._exchange)     # kept alive: the library holds a raw pointer
+        self._exchange_error = None
 
     def _alloc_window_staging(self):
         """One device allocation [windows uint8 | pad | labels int32]: a host batch whose labels sit
@@ -240,17 +264,26 @@ class Engine:
     # ------------------------------------------------------------------ one step
     def _launch_step(self, train, gen_noise):
         cfg = self.cfg(gen_noise=int(gen_noise), do_backward=int(train))
-        if train and self.world_size == 1 and self.fused_optimizer:
-            # single GPU: nothing sits between backward and update, so the optimizer is part of the
-            # step's schedule (Adam-WN per tensor range, overlapped with the encoder BPTT / wgrads)
+        if train and self.fused_optimizer:
+            # the optimizer is part of the step's schedule (Adam-WN per tensor range, overlapped with the
+            # encoder BPTT / wgrads).  Data parallel: either the peer-memory form (self.p2p: signal kernels +
+            # Adam-WN kernels that sum the peers' gradients over NVLink) or the NCCL callback (one all-reduce)
             opt = clv_adam_args(state=self.opt_state.data_ptr(), lr=self.lr, beta_1=self.b1, beta_2=self.b2,
                                 epsilon=self.eps, grad_scale=1.0, weightnorm=int(self.optimizer == "adam-wn"),
-                                loss_mirror=self.loss_host.data_ptr())   # pinned => device-visible (UVA)
-            check(lib().clv_train_step_opt(C.byref(cfg), ptr(self.params), ptr(self.grads), ptr(self.loss_acc),
-                                           ptr(self.roll), ptr(self.win_off), ptr(self.labels),
-                                           ptr(self.eps_w), ptr(self.eps_z), ptr(self.rng_ctr),
-                                           ptr(self.workspace), self.workspace.numel() * 4, C.byref(opt),
-                                           _stream()), "clv_train_step_opt")
+                                loss_mirror=self.loss_host.data_ptr(),   # pinned => device-visible (UVA)
+                                exchange=(C.cast(self._exchange_cb, C.c_void_p)
+                                          if (self.world_size > 1 and self.p2p is None) else None),
+                                exchange_user=None,
+                                p2p=(C.addressof(self.p2p) if self.p2p is not None else None))
+            self._exchange_error = None
+            rc = lib().clv_train_step_opt(C.byref(cfg), ptr(self.params), ptr(self.grads), ptr(self.loss_acc),
+                                          ptr(self.roll), ptr(self.win_off), ptr(self.labels),
+                                          ptr(self.eps_w), ptr(self.eps_z), ptr(self.rng_ctr),
+                                          ptr(self.workspace), self.workspace.numel() * 4, C.byref(opt),
+                                          _stream())
+            if self._exchange_error is not None:
+                raise _lib.ClvError("gradient exchange callback failed") from self._exchange_error
+            check(rc, "clv_train_step_opt")
             return
         check(lib().clv_train_step(C.byref(cfg), ptr(self.params), ptr(self.grads), ptr(self.loss_acc),
                                    ptr(self.roll), ptr(self.win_off), ptr(self.labels),
@@ -275,6 +308,20 @@ class Engine:
                                         ptr(self.opt_state), self.lr, self.b1, self.b2, self.eps, 1.0,
                                         int(self.optimizer == "adam-wn"), _stream()), "clv_adamwn_step")
 
+    def _exchange(self, user, buf, count, stream):
+        """clv_exchange_fn: sum-all-reduce gradbuf[buf .. buf+count) over the ranks on `stream`."""
+        try:
+            off = (int(buf) - self.gradbuf.data_ptr()) // 4
+            view = self.gradbuf[off:off + int(count)]
+            sp = int(stream or 0)              # a NULL cudaStream_t (the legacy default stream) arrives as None
+            ctx = torch.cuda.stream(torch.cuda.ExternalStream(sp, device=self.dev)) if sp else torch.cuda.stream(torch.cuda.default_stream(self.dev))
+            with ctx:
+                torch.distributed.all_reduce(view, group=self.pg)
+            return 0
+        except Exception as ex:  # noqa: BLE001  (an exception must not cross the C frame)
+            self._exchange_error = ex
+            return -1
+
     def run(self, train=True, gen_noise=True):
         """Launch one step on the current stream using the staged batch.  With use_graph the launch
         sequence (fwd+bwd kernels, NCCL all-reduce, Adam-WN) is captured once per
@@ -282,7 +329,7 @@ class Engine:
         # where the (globally reduced) loss scalars of this step end up
         self._loss_src = self.loss_red if (train and self.symm is not None) else self.loss_acc
         # the scheduled-optimizer step mirrors its loss scalars into loss_host from its last kernel
-        self._loss_mirrored = bool(train and self.world_size == 1 and self.fused_optimizer)
+        self._loss_mirrored = bool(train and self.fused_optimizer)
         if not self.use_graph:
             n0 = lib().clv_launch_count()
             self._launch_step(train, gen_noise)

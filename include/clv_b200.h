@@ -321,11 +321,49 @@ int clv_train_step(const clv_cfg* cfg, const float* params, float* grads, float*
  * later kernel of the step reads those parameters, so most of the update overlaps the encoder BPTT
  * and the weight-gradient kernels.  Result identical to clv_train_step + clv_adamwn_step.
  * Requires do_backward=1, accumulate=0. */
+/* Peer-memory data parallelism with the hand-shake INSIDE the kernels (no collective launch, no host-side
+ * barrier): every rank's [grads | losses] buffer and a small flag block live in peer-mapped (symmetric)
+ * memory.  When a gradient bucket is final a one-warp kernel stores the step number into every peer's flag
+ * block over NVLink (clv_p2p_signal); the Adam-WN kernel of that bucket polls its OWN flag block until all
+ * peers have published, then reads the peers' gradients directly over NVLink, sums them in rank order
+ * (bitwise identical on every rank) and applies the update -- all-reduce and optimizer are one kernel.  The
+ * last kernel of a step tells the peers it has stopped reading (done flags); clv_p2p_wait_done at the start of
+ * the next step keeps a rank from overwriting gradients a slower peer still reads.  Step numbers come from
+ * the Adam state's `iterations`, so CUDA-graph replays need no host-side counters. */
+typedef struct clv_p2p_args {
+  const float* const* peer_grads;  /* device array [n_peers]: every rank's [grads(P) | losses(8)] buffer, rank order */
+  int32_t* const* peer_flags;      /* device array [n_peers]: every rank's flag block, clv_p2p_flag_ints() int32,
+                                      zero-initialised before the first step */
+  int32_t n_peers, rank;
+  float* gsum;                     /* local scratch [P] */
+  float* loss_out;                 /* local [8]: reduced loss scalars */
+} clv_p2p_args;
+int clv_p2p_flag_ints(void);
+int clv_p2p_signal(const clv_p2p_args* pp, const float* adam_state, const clv_cfg* cfg, int32_t slot, void* stream);
+int clv_p2p_wait_done(const clv_p2p_args* pp, const float* adam_state, const clv_cfg* cfg, void* stream);
+/* clv_adamwn_step_range on the sum of all peers' gradients; slot = the bucket's flag slot (0..3). */
+int clv_adamwn_step_range_p2p(const clv_cfg* cfg, float* params, const clv_p2p_args* pp, float* state,
+                              double lr, double beta_1, double beta_2, double epsilon, int32_t weightnorm,
+                              int32_t t_first, int32_t t_last, int32_t slot, int32_t advance,
+                              float* loss_mirror, void* stream);
+
+/* Data-parallel hook: called by clv_train_step_opt on the HOST, while it enqueues the step, once per
+ * gradient bucket at the point of the schedule where that bucket's gradients are final: sum-all-reduce
+ * buf[0..count) over the ranks ON `stream` (stream-ordered; e.g. ncclAllReduce / torch.distributed.all_reduce
+ * with `stream` current).  Buckets, in the order they become final: [decoder | X head | 8 loss scalars]
+ * (during the encoder BPTT, on an auxiliary stream) and [key encoder | encoder LSTM | Z heads] (after the last
+ * weight gradient); each is followed by the Adam-WN update of its range.  Return 0 on success. */
+typedef int (*clv_exchange_fn)(void* user, float* buf, int64_t count, void* stream);
 typedef struct clv_adam_args {
   float* state;                 /* clv_adamwn_state_floats() floats, initialised by clv_adamwn_init */
   double lr, beta_1, beta_2, epsilon, grad_scale;
   int32_t weightnorm;
-  float* loss_mirror;           /* nullable: host-mapped copy of the step's 8 loss scalars (see above) */
+  float* loss_mirror;           /* nullable: host-mapped copy of the step's 8 loss scalars (see above);
+                                   requires loss_acc == grads + P (the [grads | losses] buffer) */
+  clv_exchange_fn exchange;     /* nullable: gradient exchange between ranks (requires loss_acc == grads + P) */
+  void* exchange_user;
+  const clv_p2p_args* p2p;      /* nullable: peer-memory exchange fused into the Adam-WN kernels (takes
+                                   precedence over `exchange`; grads must be this rank's peer-mapped buffer) */
 } clv_adam_args;
 int clv_train_step_opt(const clv_cfg* cfg, float* params, float* grads, float* loss_acc,
                        const uint8_t* roll, const int32_t* win_off, const int32_t* labels,

@@ -20,10 +20,17 @@ def main():
     case = util.make_vrnn_case(5, B * world, 6, C=4, Z=2)
     sl = slice(rank * B, (rank + 1) * B)
     results = {}
-    for mode, use_graph in (("nccl", False), ("p2p", False), ("p2p", True)):
+    engines = []
+    # nccl: step -> one all-reduce -> Adam-WN (three calls);  dp: clv_train_step_opt with the NCCL exchange
+    # callback;  p2p: the product default -- peer-memory exchange fused into the scheduled Adam-WN kernels
+    # (in-kernel flags);  p2p-barrier: the round-1 form (host-side symmetric-memory barriers around one kernel)
+    for mode, use_graph in (("nccl", False), ("dp", False), ("dp", True), ("p2p", False), ("p2p", True),
+                            ("p2p-barrier", False)):
         e = Engine("vrnn", B, L=6, D=88, H=88, Z=2, n_classes=4, use_x_prev=True, world_size=world, rank=rank,
-                   use_graph=use_graph, p2p_allreduce=(mode == "p2p"))
-        assert (e.symm is not None) == (mode == "p2p"), "symmetric memory set-up failed"
+                   use_graph=use_graph, p2p_allreduce=mode.startswith("p2p"),
+                   fused_optimizer=(mode in ("dp", "p2p")))
+        engines.append(e)
+        assert (e.symm is not None) == mode.startswith("p2p"), "symmetric memory set-up failed"
         e.set_params({k: v.numpy() for k, v in case["p"].items()})
         e.stage_windows(torch.tensor(case["win"][sl]).cuda(), torch.tensor(case["labels"][sl]).cuda())
         e.eps_w.copy_(torch.tensor(case["eps_w"][sl], dtype=torch.float32).reshape(-1))
@@ -39,7 +46,7 @@ def main():
         dist.broadcast(ref, src=0)
         assert torch.equal(ref, e.params), "ranks diverged in mode %s" % mode
     base_l, base_p = results[("nccl", False)]
-    for key in (("p2p", False), ("p2p", True)):
+    for key in (("dp", False), ("dp", True), ("p2p", False), ("p2p", True), ("p2p-barrier", False)):
         l, p = results[key]
         assert np.allclose(l, base_l, rtol=2e-5), (key, l, base_l)
         err = float((p - base_p).abs().max() / base_p.abs().max())
@@ -49,9 +56,19 @@ def main():
         out, _ = util.oracle_vrnn(case)
         assert abs(base_l[0] - float(out["loss"])) < 1e-4 * float(out["loss"])
         print("P2P_CHECK_OK world=%d losses=%s" % (world, ["%.5f" % x for x in base_l]), flush=True)
+    # CUDA graphs that captured NCCL kernels must be released before the communicator goes away
+    torch.cuda.synchronize()
     dist.barrier()
+    for e_ in engines:
+        e_._graphs.clear()
+    del engines, e
+    torch.cuda.synchronize()
+    import threading
+    wd = threading.Timer(30.0, lambda: os._exit(0))      # fallback only: a stalled communicator teardown
+    wd.daemon = True
+    wd.start()
     dist.destroy_process_group()
-    os._exit(0)
+    wd.cancel()
 
 
 if __name__ == "__main__":
