@@ -15,9 +15,15 @@ from ..utils.weightnorm import data_based_init
 from ..keras_like import Variable
 from ..cl_vrnn.train import to_categorical
 from .model import get_model
+from ..parallel import init_from_env
 
 
 def train(args):
+    # one process per GPU under torchrun (RANK / LOCAL_RANK / WORLD_SIZE): --batch_size stays the GLOBAL batch,
+    # every rank steps batch_size / WORLD_SIZE sequences of it and the gradients are all-reduced inside the step
+    world, rank, _ = init_from_env()
+    if args.batch_size % world:
+        raise SystemExit("--batch_size %d must be a multiple of the %d ranks" % (args.batch_size, world))
     P = PianoData(args.train_file, batch_size=args.batch_size, seq_length=args.seq_length, step_length=1,
                   return_y_next=args.predict_next or args.use_x_prev, squeeze_x=True, squeeze_y=True)
     if args.seq_length > 1:
@@ -51,13 +57,14 @@ def train(args):
         w_kl_weight = 1.0
 
     args.optimizer, was_adam_wn = init_adam_wn(args.optimizer)
-    model, enc_model = get_model(args.batch_size, args.original_dim, (args.intermediate_dim, args.latent_dim),
+    model, enc_model = get_model(args.batch_size // world, args.original_dim, (args.intermediate_dim, args.latent_dim),
                                  (args.intermediate_class_dim, args.n_classes), args.optimizer, args.class_weight,
                                  kl_weight, use_x_prev=args.use_x_prev, w_kl_weight=w_kl_weight,
-                                 w_log_var_prior=args.w_log_var_prior, predict_next=args.predict_next)
+                                 w_log_var_prior=args.w_log_var_prior, predict_next=args.predict_next, world_size=world, rank=rank)
     args.optimizer = 'adam-wn' if was_adam_wn else args.optimizer
     os.makedirs(args.model_dir, exist_ok=True)
-    save_model_in_pieces(model, args)
+    if rank == 0:
+        save_model_in_pieces(model, args)      # RUN.json keeps the GLOBAL batch_size
 
     if args.use_x_prev:
         xtr, xva = [P.y_train, P.x_train], [P.y_valid, P.x_valid]

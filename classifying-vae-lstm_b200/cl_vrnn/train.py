@@ -18,6 +18,7 @@ from ..utils.model_utils import get_callbacks, save_model_in_pieces, AnnealLossW
 from ..utils.weightnorm import data_based_init
 from ..keras_like import Variable
 from .model import get_model
+from ..parallel import init_from_env
 
 
 def to_categorical(y, num_classes):
@@ -28,6 +29,11 @@ def to_categorical(y, num_classes):
 
 
 def train(args):
+    # one process per GPU under torchrun (RANK / LOCAL_RANK / WORLD_SIZE): --batch_size stays the GLOBAL batch,
+    # every rank steps batch_size / WORLD_SIZE sequences of it and the gradients are all-reduced inside the step
+    world, rank, _ = init_from_env()
+    if args.batch_size % world:
+        raise SystemExit("--batch_size %d must be a multiple of the %d ranks" % (args.batch_size, world))
     P = PianoData(args.train_file, batch_size=args.batch_size, seq_length=args.seq_length, step_length=1,
                   return_y_next=args.predict_next or args.use_x_prev, return_y_hist=True,
                   squeeze_x=False, squeeze_y=False)
@@ -52,13 +58,14 @@ def train(args):
         w_kl_weight = 1.0
 
     args.optimizer, was_adam_wn = init_adam_wn(args.optimizer)
-    model, _ = get_model(args.batch_size, args.original_dim, args.intermediate_dim, args.latent_dim,
+    model, _ = get_model(args.batch_size // world, args.original_dim, args.intermediate_dim, args.latent_dim,
                          args.seq_length, args.n_classes, args.use_x_prev, args.optimizer, args.class_weight,
                          kl_weight, w_kl_weight=w_kl_weight, w_log_var_prior=args.w_log_var_prior,
-                         predict_next=args.predict_next)
+                         predict_next=args.predict_next, world_size=world, rank=rank)
     args.optimizer = 'adam-wn' if was_adam_wn else args.optimizer
     os.makedirs(args.model_dir, exist_ok=True)
-    save_model_in_pieces(model, args)
+    if rank == 0:
+        save_model_in_pieces(model, args)      # RUN.json keeps the GLOBAL batch_size
 
     print(P.x_train.shape, P.y_train.shape)
     if args.use_x_prev:
@@ -70,8 +77,18 @@ def train(args):
     ytr = [y, w, w, y]
     yva = [yv, wv, wv, yv]
     data_based_init(model, x[:100])
-    history = model.fit(x, ytr, shuffle=True, epochs=args.num_epochs, batch_size=args.batch_size,
-                        callbacks=callbacks, validation_data=(xv, yva))
+    if getattr(args, 'materialize_windows', False):
+        history = model.fit(x, ytr, shuffle=True, epochs=args.num_epochs, batch_size=args.batch_size,
+                            callbacks=callbacks, validation_data=(xv, yva))
+    else:
+        # same batches, same labels, same results -- but each split lives in HBM as ONE uint8 roll plus window
+        # offsets instead of the 17x-materialised [n, L(+1), 88] windows (utils/pianoroll.py:52-62)
+        from ..utils.pianoroll import DeviceRolls
+        window = args.seq_length + int(args.predict_next or args.use_x_prev)
+        tr, _ = DeviceRolls.from_pickle(args.train_file, 'train', window, args.batch_size)
+        va, _ = DeviceRolls.from_pickle(args.train_file, 'valid', window, args.batch_size)
+        assert len(tr.labels) == len(P.train_song_keys) and np.array_equal(tr.labels, P.train_song_keys)
+        history = model.fit_rolls(tr, va, shuffle=True, epochs=args.num_epochs, callbacks=callbacks)
     best_ind = np.argmin([v if i >= min(args.kl_anneal, args.w_kl_anneal) else np.inf
                           for i, v in enumerate(history.history['val_loss'])])
     best_loss = {k: history.history[k][best_ind] for k in history.history}
@@ -90,6 +107,9 @@ def build_parser():
     parser.add_argument('--seq_length', type=int, default=16, help='sequence length (to use as history)')
     parser.add_argument('--class_weight', type=float, default=1.0, help='relative weight on classifying key')
     parser.add_argument("--predict_next", action="store_true", help="use x_t to 'autoencode' x_{t+1}")
+    parser.add_argument("--materialize_windows", action="store_true",
+                        help="(B200 build) feed model.fit the materialised PianoData windows like the reference; "
+                             "default: one device-resident roll per split + window offsets (same batches)")
     parser.add_argument("--do_log", action="store_true", help="save log files")
     parser.add_argument("--w_log_var_prior", type=float, default=0.0, help="log variance prior on w")
     parser.add_argument("--kl_anneal", type=int, default=0, help="number of epochs before kl loss term is 1.0")
@@ -104,4 +124,10 @@ def build_parser():
 
 
 if __name__ == '__main__':
-    train(build_parser().parse_args())
+    _parser = build_parser()
+    _args = _parser.parse_args()
+    if _args.intermediate_dim != 88 or _args.original_dim != 88:
+        _parser.error("the B200 recurrence kernels keep the 88x352 recurrent kernel of one LSTM in the registers of "
+                      "one CTA (352 threads x 88): --intermediate_dim and --original_dim are fixed at 88, the value "
+                      "every configuration of the reference uses")
+    train(_args)

@@ -44,7 +44,7 @@ class Engine:
                  optimizer="adam-wn", lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-8,
                  seed=0, device=None, world_size=1, rank=0, process_group=None, use_graph=True,
                  overlap_wgrad=True, gemm_algo=1, p2p_allreduce=False, tc_lstm_min=0,
-                 fused_optimizer=True, predict_next=False):
+                 fused_optimizer=True, predict_next=False, micro_batch=None, workspace_budget_bytes=None):
         _require_cuda()
         lib()
         if optimizer not in ("adam-wn", "adam"):
@@ -75,6 +75,27 @@ class Engine:
             with torch.cuda.device(self.dev):
                 check(lib().clv_runtime_init(), "clv_runtime_init")
         self.names = VRNN_TENSORS if self.model == 0 else VAE_TENSORS
+        # host micro-batching: a logical batch of B sequences is stepped as B / Bm calls of Bm sequences that
+        # ACCUMULATE into the same gradient / loss buffers (clv_cfg.accumulate), then one exchange + Adam-WN.
+        # The workspace (activations of one call) is sized for Bm, so the top of the sweep (B = 65 536, L = 512:
+        # 177 GB of activations) fits.  micro_batch=None: the largest divisor of B whose workspace fits the budget
+        # (default 60 % of the free HBM).
+        self.Bm = B
+        if micro_batch is not None:
+            if B % int(micro_batch):
+                raise ValueError("micro_batch %d must divide the batch %d" % (micro_batch, B))
+            self.Bm = int(micro_batch)
+        else:
+            budget = workspace_budget_bytes
+            if budget is None:
+                free, _ = torch.cuda.mem_get_info(self.dev)
+                budget = int(0.6 * free)
+            while self.Bm > 1 and lib().clv_workspace_bytes(C.byref(self.cfg(B=self.Bm))) > budget:
+                nb = self.Bm - 1
+                while nb > 1 and B % nb:
+                    nb -= 1
+                self.Bm = nb
+        self.n_micro = B // self.Bm
         cfg = self.cfg()
         self.P, self.offs, self.rows, self.cols = _lib.param_layout(cfg)
         f32 = dict(dtype=torch.float32, device=self.dev)
@@ -127,7 +148,7 @@ class Engine:
         n_state = check(lib().clv_adamwn_state_floats(C.byref(cfg)), "clv_adamwn_state_floats")
         self.opt_state = torch.zeros(n_state, **f32)
         check(lib().clv_adamwn_init(C.byref(cfg), ptr(self.opt_state), _stream()), "clv_adamwn_init")
-        ws_bytes = check(lib().clv_workspace_bytes(C.byref(cfg)), "clv_workspace_bytes")
+        ws_bytes = check(lib().clv_workspace_bytes(C.byref(self.cfg(B=self.Bm))), "clv_workspace_bytes")
         self.workspace = torch.zeros(ws_bytes // 4 + 64, **f32)
         self.eps_w = torch.zeros(B * (self.C - 1), **f32)
         self.eps_z = torch.zeros(B * self.L * Z, **f32)
@@ -264,6 +285,8 @@ class Engine:
     # ------------------------------------------------------------------ one step
     def _launch_step(self, train, gen_noise):
         cfg = self.cfg(gen_noise=int(gen_noise), do_backward=int(train))
+        if self.n_micro > 1:
+            return self._launch_micro(train, gen_noise)
         if train and self.fused_optimizer:
             # the optimizer is part of the step's schedule (Adam-WN per tensor range, overlapped with the
             # encoder BPTT / wgrads).  Data parallel: either the peer-memory form (self.p2p: signal kernels +
@@ -308,6 +331,26 @@ class Engine:
                                         ptr(self.opt_state), self.lr, self.b1, self.b2, self.eps, 1.0,
                                         int(self.optimizer == "adam-wn"), _stream()), "clv_adamwn_step")
 
+    def _launch_micro(self, train, gen_noise):
+        """B / Bm accumulated calls of Bm sequences, then the exchange and ONE Adam-WN update (SURVEY 7 "BPTT
+        memory at the top of the sweep"; test_microbatch_accumulation_equals_full_batch)."""
+        if self.symm is not None:
+            raise NotImplementedError("micro-batching with the peer-memory exchange")
+        Bm, C1 = self.Bm, self.C - 1
+        for k in range(self.n_micro):
+            cfg = self.cfg(B=Bm, gen_noise=int(gen_noise), do_backward=int(train), accumulate=int(k > 0))
+            check(lib().clv_train_step(C.byref(cfg), ptr(self.params), ptr(self.grads), ptr(self.loss_acc),
+                                       ptr(self.roll), ptr(self.win_off[k * Bm:]), ptr(self.labels[k * Bm:]),
+                                       ptr(self.eps_w[k * Bm * C1:]), ptr(self.eps_z[k * Bm * self.L * self.Z:]),
+                                       ptr(self.rng_ctr), ptr(self.workspace), self.workspace.numel() * 4, _stream()),
+                  "clv_train_step")
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self.gradbuf if train else self.loss_acc, group=self.pg)
+        if train:
+            check(lib().clv_adamwn_step(C.byref(self.cfg()), ptr(self.params), ptr(self.grads),
+                                        ptr(self.opt_state), self.lr, self.b1, self.b2, self.eps, 1.0,
+                                        int(self.optimizer == "adam-wn"), _stream()), "clv_adamwn_step")
+
     def _exchange(self, user, buf, count, stream):
         """clv_exchange_fn: sum-all-reduce gradbuf[buf .. buf+count) over the ranks on `stream`."""
         try:
@@ -329,7 +372,7 @@ class Engine:
         # where the (globally reduced) loss scalars of this step end up
         self._loss_src = self.loss_red if (train and self.symm is not None) else self.loss_acc
         # the scheduled-optimizer step mirrors its loss scalars into loss_host from its last kernel
-        self._loss_mirrored = bool(train and self.fused_optimizer)
+        self._loss_mirrored = bool(train and self.fused_optimizer and self.n_micro == 1)
         if not self.use_graph:
             n0 = lib().clv_launch_count()
             self._launch_step(train, gen_noise)

@@ -116,7 +116,10 @@ class BaseModel:
             i += k
 
     def save_weights(self, filepath, overwrite=True):
-        """Keras-2.0.0 save_weights HDF5 layout (utils/model_utils.py:138)."""
+        """Keras-2.0.0 save_weights HDF5 layout (utils/model_utils.py:138).  Data parallel: the
+        replicas are bit-identical, rank 0 writes."""
+        if self.engine.rank != 0:
+            return
         from .utils import hdf5
         layers = []
         for lname in self.all_layer_names:
@@ -191,47 +194,48 @@ class BaseModel:
         return self._as_list(self.engine.read_losses())
 
     # ------------------------------------------------------------------ epochs
-    def _run_epoch(self, wins_dev, labs_dev, order, train):
-        """One pass over a device-resident split; losses accumulate on the device, one D2H at the end."""
+    def _run_epoch(self, roll_dev, off_dev, labs_dev, order, train):
+        """One pass over a device-resident split given as (roll, first frame of every window, key label);
+        losses accumulate on the device, one D2H at the end."""
         e = self.engine
-        B = e.B
+        B, Bg = e.B, e.B * e.world_size        # data parallel: every rank steps its slice of each global batch
         n = len(order)
-        assert n % B == 0, "sample count must be a multiple of batch_size (PianoData guarantees it)"
-        e.roll = wins_dev
-        off_all = (order.to(torch.int32) * e.W).contiguous()
+        assert n % Bg == 0, "sample count must be a multiple of the global batch_size (PianoData guarantees it)"
+        e.roll = roll_dev
+        off_all = off_dev[order].contiguous()
         lab_all = labs_dev[order].contiguous()
         acc = torch.zeros(8, device=e.dev)
-        for i in range(n // B):
-            e.stage_offsets(off_all[i * B:(i + 1) * B], lab_all[i * B:(i + 1) * B])
+        for i in range(n // Bg):
+            lo = i * Bg + e.rank * B            # == parallel.local_batch(order, i, B, world_size, rank)
+            e.stage_offsets(off_all[lo:lo + B], lab_all[lo:lo + B])
             e.run(train=train, gen_noise=True)
-            acc += e._loss_src
-        v = (acc / (n // B)).tolist()
+            acc += e._loss_src                  # already the GLOBAL means (summed over ranks inside the step)
+        v = (acc / (n // Bg)).tolist()
         d = dict(zip(LOSS_NAMES, v[:5]))
         h = e.hyper
         d["loss"] = d["vae"] + h["w_kl_weight"] * d["w_kl"] + h["class_weight"] * d["w_rec"] + h["kl_weight"] * d["z_kl"]
         return d
 
-    def fit(self, x, y, shuffle=True, epochs=1, batch_size=None, callbacks=None, validation_data=None,
-            verbose=1):
-        """model.fit as the reference calls it (cl_vrnn/train.py:66-71): per-epoch shuffle,
-        validation pass every epoch with noise still sampled, callbacks, History."""
+    def _split_from_windows(self, x, y, overlap):
+        """materialised windows -> (roll, window offsets, labels) on the device"""
         e = self.engine
-        if batch_size is not None and batch_size != e.B:
-            raise ValueError("batch_size is baked into the model (%d), got %d" % (e.B, batch_size))
-        # window geometry (frames per window, where `current` / the target sit) is decided ONCE for both
-        # splits: a validation split stored differently from the training split would change e.W under
-        # the training offsets
-        ov = self._overlaps(x, y)
-        if validation_data is not None:
-            ov = ov and self._overlaps(validation_data[0], validation_data[1])
-        wins = torch.from_numpy(self._windows_from_inputs(x, y, overlap=ov)).to(e.dev).reshape(-1)
+        wins = torch.from_numpy(self._windows_from_inputs(x, y, overlap=overlap)).to(e.dev).reshape(-1)
         labs = torch.from_numpy(self._labels_from_targets(y)).to(e.dev)
-        n = labs.numel()
-        val = None
-        if validation_data is not None:
-            xv, yv = validation_data[0], validation_data[1]
-            val = (torch.from_numpy(self._windows_from_inputs(xv, yv, overlap=ov)).to(e.dev).reshape(-1),
-                   torch.from_numpy(self._labels_from_targets(yv)).to(e.dev))
+        off = (torch.arange(labs.numel(), dtype=torch.int32, device=e.dev) * e.W).contiguous()
+        return wins, off, labs
+
+    def _split_from_rolls(self, dr):
+        """utils.pianoroll.DeviceRolls -> the same triple WITHOUT materialising the sliding windows: the roll of
+        the whole split is uploaded once, a window is only its first-frame offset"""
+        e = self.engine
+        if dr.window != e.W or e.x_shift != 0 or e.y_shift not in (0, 1):
+            raise ValueError("DeviceRolls window %d does not match the model's %d-frame windows" % (dr.window, e.W))
+        return (torch.from_numpy(dr.roll).to(e.dev).reshape(-1), torch.from_numpy(dr.win_off).to(e.dev),
+                torch.from_numpy(np.asarray(dr.labels, dtype=np.int32)).to(e.dev))
+
+    def _fit_core(self, train, val, shuffle, epochs, callbacks, verbose):
+        e = self.engine
+        n = train[2].numel()
         callbacks = list(callbacks or [])
         hist = History()
         for cb in callbacks:
@@ -243,15 +247,16 @@ class BaseModel:
                 cb.on_epoch_begin(epoch, {})
             self._sync_weights_of_losses()
             t0 = time.time()
-            order = torch.from_numpy(np.random.permutation(n) if shuffle else np.arange(n)).to(e.dev)
-            logs = self._logs(self._run_epoch(wins, labs, order, True))
+            from .parallel import shared_permutation
+            order = shared_permutation(n, shuffle, device=e.dev, group=e.pg).to(e.dev)   # one order for all ranks
+            logs = self._logs(self._run_epoch(train[0], train[1], train[2], order, True))
             if val is not None:
-                vorder = torch.arange(val[1].numel(), device=e.dev)
-                logs.update(self._logs(self._run_epoch(val[0], val[1], vorder, False), "val_"))
+                vorder = torch.arange(val[2].numel(), device=e.dev)
+                logs.update(self._logs(self._run_epoch(val[0], val[1], val[2], vorder, False), "val_"))
             hist.epoch.append(epoch)
             for k, v in logs.items():
                 hist.history.setdefault(k, []).append(v)
-            if verbose:
+            if verbose and e.rank == 0:
                 print("Epoch %d/%d - %.1fs - %s" % (epoch + 1, epochs, time.time() - t0,
                       " - ".join("%s: %.4f" % (k, logs[k]) for k in sorted(logs))))
             for cb in callbacks:
@@ -263,9 +268,36 @@ class BaseModel:
         self.history = hist
         return hist
 
+    def fit(self, x, y, shuffle=True, epochs=1, batch_size=None, callbacks=None, validation_data=None,
+            verbose=1):
+        """model.fit as the reference calls it (cl_vrnn/train.py:66-71): per-epoch shuffle,
+        validation pass every epoch with noise still sampled, callbacks, History."""
+        e = self.engine
+        if batch_size is not None and batch_size != e.B * e.world_size:
+            raise ValueError("batch_size is baked into the model (%d x %d rank(s)), got %d" % (e.B, e.world_size, batch_size))
+        # window geometry (frames per window, where `current` / the target sit) is decided ONCE for both
+        # splits: a validation split stored differently from the training split would change e.W under
+        # the training offsets
+        ov = self._overlaps(x, y)
+        if validation_data is not None:
+            ov = ov and self._overlaps(validation_data[0], validation_data[1])
+        train = self._split_from_windows(x, y, ov)
+        val = None
+        if validation_data is not None:
+            val = self._split_from_windows(validation_data[0], validation_data[1], ov)
+        return self._fit_core(train, val, shuffle, epochs, callbacks, verbose)
+
+    def fit_rolls(self, train_rolls, valid_rolls=None, shuffle=True, epochs=1, callbacks=None, verbose=1):
+        """fit on utils.pianoroll.DeviceRolls splits: identical batches and results to fit() on the PianoData
+        windows of the same pickle (same enumeration, trim and labels), but the 17x-materialised
+        [n, L+1, 88] windows never exist -- each split is one uint8 roll in HBM plus int32 window offsets
+        that the kernels gather from."""
+        train = self._split_from_rolls(train_rolls)
+        val = self._split_from_rolls(valid_rolls) if valid_rolls is not None else None
+        return self._fit_core(train, val, shuffle, epochs, callbacks, verbose)
+
     def evaluate(self, x, y, batch_size=None, verbose=0):
         e = self.engine
-        wins = torch.from_numpy(self._windows_from_inputs(x, y)).to(e.dev).reshape(-1)
-        labs = torch.from_numpy(self._labels_from_targets(y)).to(e.dev)
+        wins, off, labs = self._split_from_windows(x, y, None)
         self._sync_weights_of_losses()
-        return self._as_list(self._run_epoch(wins, labs, torch.arange(labs.numel(), device=e.dev), False))
+        return self._as_list(self._run_epoch(wins, off, labs, torch.arange(labs.numel(), device=e.dev), False))

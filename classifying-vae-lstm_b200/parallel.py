@@ -40,3 +40,23 @@ def allreduce_sum_(flat, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return flat
+
+
+def local_batch(order, step, B_local, world_size, rank):
+    """Indices of the sequences rank `rank` steps at optimisation step `step` of an epoch whose GLOBAL sample
+    order is `order` (identical on every rank): global batch `step` = order[step*Bg : (step+1)*Bg] with
+    Bg = B_local * world_size, of which each rank takes its contiguous B_local slice -- so N ranks with
+    --batch_size Bg visit exactly the batches one process with --batch_size Bg would."""
+    Bg = B_local * world_size
+    lo = step * Bg + rank * B_local
+    return order[lo:lo + B_local]
+
+
+def shared_permutation(n, shuffle, device=None, group=None):
+    """The epoch's sample order, drawn on rank 0 (np.random, like Keras' fit) and broadcast to every rank."""
+    import numpy as np
+    perm = torch.from_numpy(np.random.permutation(n) if shuffle else np.arange(n))
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        perm = perm.to(device) if device is not None else perm
+        dist.broadcast(perm, src=0, group=group)
+    return perm

@@ -165,3 +165,52 @@ def test_vae_cli_train_then_sample_readme_example(tmp_path):
     mids = sorted(os.listdir(sdir))
     assert mids == ["outfile_0.mid", "outfile_1.mid"]
     assert open(os.path.join(sdir, mids[0]), "rb").read(4) == b"MThd"
+
+
+def test_fit_rolls_equals_fit_on_materialised_windows():
+    """DeviceRolls (one roll per split + window offsets, no 17x window blow-up) feeds the same batches as the
+    reference's materialised PianoData windows: same History under the same seeds."""
+    from clvae_b200.cl_vrnn import model as M
+    from clvae_b200.cl_vrnn.train import to_categorical
+    from clvae_b200.utils.pianoroll import PianoData, DeviceRolls
+    f = os.path.join(DATA, "JSB Chorales_all.pickle")
+    P = PianoData(f, batch_size=200, seq_length=16, step_length=1, return_y_next=True, return_y_hist=True,
+                  squeeze_x=False, squeeze_y=False)
+    C = len(np.unique(P.train_song_keys))
+    tr, _ = DeviceRolls.from_pickle(f, "train", 17, 200)
+    va, _ = DeviceRolls.from_pickle(f, "valid", 17, 200)
+    assert np.array_equal(tr.labels, P.train_song_keys) and np.array_equal(va.labels, P.valid_song_keys)
+    w, wv = to_categorical(P.train_song_keys, C), to_categorical(P.valid_song_keys, C)
+    hists = []
+    for mode in ("windows", "rolls"):
+        np.random.seed(5)
+        model, _ = M.get_model(200, 88, 88, 2, 16, C, True, "adam-wn", seed=9)
+        if mode == "windows":
+            h = model.fit([P.y_train, P.x_train], [P.y_train, w, w, P.y_train], shuffle=True, epochs=1, batch_size=200,
+                          validation_data=([P.y_valid, P.x_valid], [P.y_valid, wv, wv, P.y_valid]), verbose=0)
+        else:
+            h = model.fit_rolls(tr, va, shuffle=True, epochs=1, verbose=0)
+        hists.append(h.history)
+    for k in hists[0]:
+        assert np.allclose(hists[0][k], hists[1][k], rtol=1e-6, atol=1e-7), (k, hists[0][k], hists[1][k])
+
+
+def test_host_micro_batching_equals_the_full_batch_step():
+    """Engine(micro_batch=Bm): B / Bm accumulated calls + one update == the one-call step (how B = 65 536 x
+    L = 512, 177 GB of activations, is stepped in 180 GB of HBM)."""
+    from clvae_b200.engine import Engine
+    case = util.make_vrnn_case(11, B=24, L=6, C=5, Z=2)
+    full = util.engine_for(case, "vrnn", use_graph=False)
+    micro = util.engine_for(case, "vrnn", use_graph=False, micro_batch=8)
+    assert micro.n_micro == 3 and micro.workspace.numel() < full.workspace.numel()
+    for e in (full, micro):
+        e.run(train=True, gen_noise=False)
+    lf, lm = full.read_losses(), micro.read_losses()
+    for k in lf:
+        assert abs(lf[k] - lm[k]) <= 2e-5 * max(1.0, abs(lf[k])), (k, lf[k], lm[k])
+    assert util.rel_err(micro.grads.cpu().numpy(), full.grads.cpu().numpy()) < 1e-4
+    assert util.rel_err(micro.params.cpu().numpy(), full.params.cpu().numpy()) < 1e-5
+    # automatic choice: a budget smaller than the full workspace forces a split
+    auto = Engine("vrnn", 24, L=6, D=88, H=88, Z=2, n_classes=5, use_x_prev=True, use_graph=False,
+                  workspace_budget_bytes=full.workspace.numel() * 4 // 2)
+    assert auto.n_micro > 1 and 24 % auto.Bm == 0
