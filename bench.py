@@ -488,14 +488,15 @@ def main():
         seeds[:, :, :15] = 0; seeds[:, :, 76:] = 0
         wkey = torch.zeros(S, Cs, device=devn)
         wkey[torch.arange(S), torch.randint(0, Cs, (S,), device=devn)] = 1.0
-        out = torch.zeros(S, T, D, dtype=torch.uint8, device=devn)
+        NBY = (D + 7) // 8                      # rolls leave the GPU bit-packed: 11 bytes per 88-key frame
+        out = torch.zeros(S, T, NBY, dtype=torch.uint8, device=devn)
         cfg = smodel.engine.cfg()
         w_enc = make_w_encoder(smodel, D, Cs, L)
 
         def samp(w):
-            check(lib().clv_vrnn_sample(C.byref(cfg), ptr(smodel.engine.params), None, None, None,
-                                        ptr(seeds), Ts, Ns, ptr(w), None, None, 99, rank * S, S,
-                                        ptr(out), None, st))
+            check(lib().clv_vrnn_sample_bits(C.byref(cfg), ptr(smodel.engine.params), None, None, None,
+                                             ptr(seeds), Ts, Ns, ptr(w), None, None, 99, rank * S, S,
+                                             ptr(out), None, st))
 
         def samp_infer():
             samp(infer_w_device(w_enc, seeds, L, False))      # key inferred from the seed (cl_vrnn/model.py:34-41)
@@ -518,7 +519,7 @@ def main():
         ms_i = max_over_ranks(ev0.elapsed_time(ev1))
         # e2e: host seeds in, host rolls out
         seeds_h = seeds.cpu().pin_memory(); w_h = wkey.cpu().pin_memory()
-        out_h = torch.zeros(S, T, D, dtype=torch.uint8).pin_memory()
+        out_h = torch.zeros(S, T, NBY, dtype=torch.uint8).pin_memory()
         barrier()
         ev0.record()
         seeds.copy_(seeds_h, non_blocking=True); wkey.copy_(w_h, non_blocking=True)
@@ -534,12 +535,13 @@ def main():
                    "inferred_key": {"value": S * T * world / (ms_i / 1e3), "unit": "timesteps/s", "ms": ms_i,
                                     "note": "key inferred from the seed chunks (hW/Wargs GEMMs + softmax + chunk mean) then the same kernel"},
                    "e2e": {"value": S * T * world / (ms_se / 1e3), "unit": "timesteps/s",
-                           "h2d_bytes": S * Ts * D + 4 * S * Cs, "d2h_bytes": S * T * D},
+                           "h2d_bytes": S * Ts * D + 4 * S * Cs, "d2h_bytes": S * T * NBY,
+                           "note": "bit-packed rolls (clv_vrnn_sample_bits): 11 B per frame over PCIe, unpacked on the host"},
                    "fp32_tflops": tfl,
                    "roofline": {"kernel": "vrnn_sample_kernel", "bound": "issue (fp32 FMA; weights stream from L2)",
                                 "achieved": tfl, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tfl / fp32_peak,
                                 "peak_source": "clv_fp32_peak_probe (FFMA2, this process)",
-                                "bytes_out_per_timestep": D, "hbm_GBps": S * T * D / (ms_s / 1e3) / 1e9},
+                                "bytes_out_per_timestep": NBY, "hbm_GBps": S * T * NBY / (ms_s / 1e3) / 1e9},
                    "note": "given one-hot key, Philox noise keyed by (seed, global song, t); "
                            "density of generated notes depends on random-init weights"}
 

@@ -92,6 +92,8 @@ PROTOTYPES = {
     "clv_train_step_opt": (C.c_int, [_CFG, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
     "clv_vrnn_sample": (C.c_int, [_CFG, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _U64, _I64, _I32,
                                   _P, _P, _P]),
+    "clv_vrnn_sample_bits": (C.c_int, [_CFG, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _U64, _I64, _I32,
+                                       _P, _P, _P]),
     "clv_vae_sample": (C.c_int, [_CFG, _P, _P, _I32, _P, _P, _P, _U64, _I64, _I32, _I32, _P, _P, _P]),
     "clv_chunk_mean": (C.c_int, [_P, _P, _I32, _I32, _I32, _P]),
     "clv_p2p_flag_ints": (C.c_int, []),

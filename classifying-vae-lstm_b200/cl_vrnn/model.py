@@ -378,14 +378,17 @@ def generate_samples(dec_model, w_enc_model, z_enc_model, x_seeds, nsteps, use_x
         eps_z = torch.as_tensor(noise[0], dtype=torch.float32).to(e.dev).contiguous()
         u = torch.as_tensor(noise[1], dtype=torch.float32).to(e.dev).contiguous()
         assert eps_z.shape == (S, T, e.Z) and u.shape == (S, T, D)
-    out = torch.empty(S, T, D, dtype=torch.uint8, device=e.dev)
+    # the rolls leave the GPU bit-packed (11 bytes per 88-key frame, 8x less D2H) and are unpacked on the host
+    nb = (D + 7) // 8
+    out = torch.empty(S, T, nb, dtype=torch.uint8, device=e.dev)
     probs = torch.empty(S, T, D, device=e.dev) if return_probs else None
     lstm = z_enc_model.lstm or [None, None, None]
     cfg = e.cfg(use_x_prev=use_x_prev)
-    check(lib().clv_vrnn_sample(C.byref(cfg), ptr(e.params), ptr(lstm[0]), ptr(lstm[1]), ptr(lstm[2]),
-                                ptr(seeds), T_seed, nsteps, ptr(w), ptr(eps_z), ptr(u), seed, song0, S,
-                                ptr(out), ptr(probs), _stream()), "clv_vrnn_sample")
-    res = (out if keep_seed_steps else out[:, T_seed:]).cpu().numpy()
+    check(lib().clv_vrnn_sample_bits(C.byref(cfg), ptr(e.params), ptr(lstm[0]), ptr(lstm[1]), ptr(lstm[2]),
+                                     ptr(seeds), T_seed, nsteps, ptr(w), ptr(eps_z), ptr(u), seed, song0, S,
+                                     ptr(out), ptr(probs), _stream()), "clv_vrnn_sample_bits")
+    packed = (out if keep_seed_steps else out[:, T_seed:]).cpu().numpy()
+    res = np.unpackbits(packed, axis=-1, bitorder="little")[..., :D]
     return (res, probs.cpu().numpy()) if return_probs else res
 
 

@@ -19,7 +19,8 @@ struct VrnnSampArgs {
   const float* w;            // [S, C]
   const float* eps_z;        // [S, T, Z] or null
   const float* u;            // [S, T, D] or null
-  uint8_t* out;              // [S, T, D]
+  uint8_t* out;              // [S, T, D] or null
+  uint8_t* out_bits;         // [S, T, ceil(D/8)] bit-packed (key d = bit d%8 of byte d/8) or null
   float* probs;              // [S, T, D] or null
   uint64_t seed; int64_t song0;
   int S, T_seed, T, D, Z, C, use_x_prev;
@@ -190,17 +191,26 @@ __global__ void __launch_bounds__(SAMP_T, 4) vrnn_sample_kernel(const VrnnSampAr
           lo[4 * q] = l0.x; lo[4 * q + 1] = l0.y; lo[4 * q + 2] = l1.x; lo[4 * q + 3] = l1.y;
         }
       }
+      // lanes of this warp that own a key (the last warp is partial): the ballot below packs their notes
+      const unsigned kmask = __ballot_sync(__activemask(), true);
+      const int lane = tid & 31, nbytes = (D + 7) >> 3;
 #pragma unroll
       for (int s = 0; s < BT; ++s) {
         const int64_t song = s0 + s;
-        if (song >= a.S) continue;
+        if (song >= a.S) continue;           // warp-uniform
         const float p = sigmoid_f(lo[s]);
         const size_t o = ((size_t)song * T + t) * D + d;
         float uu;
         if (a.u) uu = __ldg(a.u + o);
         else uu = u32_to_unit(philox_u32x4(a.seed, 0, 4u, ((uint64_t)(a.song0 + song) * T + t) * D + d).x);
         const float x = (uu <= p) ? 1.f : 0.f;
-        a.out[o] = (uint8_t)x;
+        if (a.out) a.out[o] = (uint8_t)x;
+        if (a.out_bits) {                    // 11 bytes per frame instead of 88 (11 B/timestep)
+          const unsigned bits = __ballot_sync(kmask, x != 0.f);
+          const int byte = (tid >> 5) * 4 + lane;          // lanes 0..3 of a warp store its 4 bytes
+          if (lane < 4 && byte < nbytes)
+            a.out_bits[((size_t)song * T + t) * nbytes + byte] = (uint8_t)(bits >> (8 * lane));
+        }
         if (a.probs) a.probs[o] = p;
         // next x_prev: teacher-forced from the seed while t+1 < T_seed (model.py:48-49)
         xT[d][s] = (t + 1 < a.T_seed)
@@ -335,12 +345,12 @@ __global__ void __launch_bounds__(VT, 1) vae_sample_kernel(const VaeSampArgs a) 
 
 }  // namespace
 
-extern "C" int clv_vrnn_sample(const clv_cfg* cfg, const float* params, const float* enc_kernel,
-                               const float* enc_rkernel, const float* enc_bias,
-                               const uint8_t* seed_roll, int32_t T_seed, int32_t nsteps,
-                               const float* w, const float* eps_z, const float* u, uint64_t seed,
-                               int64_t song0, int32_t S, uint8_t* out, float* probs, void* stream) {
-  if (!cfg || !params || !seed_roll || !w || !out) return CLV_E_INVALID;
+static int vrnn_sample_impl(const clv_cfg* cfg, const float* params, const float* enc_kernel,
+                            const float* enc_rkernel, const float* enc_bias,
+                            const uint8_t* seed_roll, int32_t T_seed, int32_t nsteps,
+                            const float* w, const float* eps_z, const float* u, uint64_t seed,
+                            int64_t song0, int32_t S, uint8_t* out, uint8_t* out_bits, float* probs, void* stream) {
+  if (!cfg || !params || !seed_roll || !w || (!out && !out_bits)) return CLV_E_INVALID;
   if (cfg->model != 0 || cfg->H != SH || cfg->D > 128 || cfg->Z > 16 || cfg->C > 16 || cfg->C < 2)
     return CLV_E_UNSUPPORTED;
   if (T_seed < 1 || nsteps < 0) return CLV_E_INVALID;
@@ -354,7 +364,7 @@ extern "C" int clv_vrnn_sample(const clv_cfg* cfg, const float* params, const fl
   a.Kzm = params + po[7]; a.bzm = params + po[8]; a.Kzv = params + po[9]; a.bzv = params + po[10];
   a.Kd = params + po[11]; a.Ud = params + po[12]; a.bd = params + po[13];
   a.Kx = params + po[14]; a.bx = params + po[15];
-  a.seed_roll = seed_roll; a.w = w; a.eps_z = eps_z; a.u = u; a.out = out; a.probs = probs;
+  a.seed_roll = seed_roll; a.w = w; a.eps_z = eps_z; a.u = u; a.out = out; a.out_bits = out_bits; a.probs = probs;
   a.seed = seed; a.song0 = song0; a.S = S; a.T_seed = T_seed; a.T = T_seed + nsteps;
   a.D = cfg->D; a.Z = cfg->Z; a.C = cfg->C; a.use_x_prev = cfg->use_x_prev;
   // songs per CTA: 16 or 24, whichever leaves the smaller tail in the last wave (4 CTAs per SM)
@@ -379,6 +389,26 @@ extern "C" int clv_vrnn_sample(const clv_cfg* cfg, const float* params, const fl
     vrnn_sample_kernel<16><<<(S + 15) / 16, SAMP_T, smem_for(16), (cudaStream_t)stream>>>(a);
   CLV_CHECK_LAUNCH();
   return CLV_OK;
+}
+
+extern "C" int clv_vrnn_sample(const clv_cfg* cfg, const float* params, const float* enc_kernel,
+                               const float* enc_rkernel, const float* enc_bias,
+                               const uint8_t* seed_roll, int32_t T_seed, int32_t nsteps,
+                               const float* w, const float* eps_z, const float* u, uint64_t seed,
+                               int64_t song0, int32_t S, uint8_t* out, float* probs, void* stream) {
+  if (!out) return CLV_E_INVALID;
+  return vrnn_sample_impl(cfg, params, enc_kernel, enc_rkernel, enc_bias, seed_roll, T_seed, nsteps, w, eps_z, u,
+                          seed, song0, S, out, nullptr, probs, stream);
+}
+
+extern "C" int clv_vrnn_sample_bits(const clv_cfg* cfg, const float* params, const float* enc_kernel,
+                                    const float* enc_rkernel, const float* enc_bias,
+                                    const uint8_t* seed_roll, int32_t T_seed, int32_t nsteps,
+                                    const float* w, const float* eps_z, const float* u, uint64_t seed,
+                                    int64_t song0, int32_t S, uint8_t* out_bits, float* probs, void* stream) {
+  if (!out_bits) return CLV_E_INVALID;
+  return vrnn_sample_impl(cfg, params, enc_kernel, enc_rkernel, enc_bias, seed_roll, T_seed, nsteps, w, eps_z, u,
+                          seed, song0, S, nullptr, out_bits, probs, stream);
 }
 
 extern "C" int clv_vae_sample(const clv_cfg* cfg, const float* params, const uint8_t* x_seed,

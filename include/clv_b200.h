@@ -385,6 +385,14 @@ int clv_vrnn_sample(const clv_cfg* cfg, const float* params, const float* enc_ke
                     int32_t T_seed, int32_t nsteps, const float* w, const float* eps_z,
                     const float* u, uint64_t seed, int64_t song0, int32_t S, uint8_t* out,
                     float* probs, void* stream);
+/* The same sampler with BIT-PACKED output: out_bits[S, T, ceil(D/8)] uint8, key d = bit (d % 8) of byte d / 8
+ * (numpy.unpackbits(..., bitorder="little")) -- 11 bytes per 88-key frame instead of 88, the form in which
+ * samples leave the GPU. */
+int clv_vrnn_sample_bits(const clv_cfg* cfg, const float* params, const float* enc_kernel,
+                         const float* enc_rkernel, const float* enc_bias, const uint8_t* seed_roll,
+                         int32_t T_seed, int32_t nsteps, const float* w, const float* eps_z,
+                         const float* u, uint64_t seed, int64_t song0, int32_t S, uint8_t* out_bits,
+                         float* probs, void* stream);
 /* generate_sample (cl_vae/model.py:9-42): x_seed[S,D]; optional use_z_prior. */
 int clv_vae_sample(const clv_cfg* cfg, const float* params, const uint8_t* x_seed, int32_t nsteps,
                    const float* w, const float* eps_z, const float* u, uint64_t seed, int64_t song0,

@@ -134,3 +134,29 @@ def test_sampler_philox_mode_is_deterministic_and_song_indexed():
     torch.cuda.synchronize()
     assert torch.equal(full[24:], part)
     assert 0.0 < full.float().mean().item() < 1.0
+
+
+def test_bit_packed_sampler_output_equals_the_uint8_rolls():
+    """clv_vrnn_sample_bits: 11 bytes per 88-key frame (numpy.unpackbits little-endian) == clv_vrnn_sample."""
+    from clvae_b200._lib import lib, check, ptr
+    from clvae_b200.engine import Engine
+    rng = np.random.default_rng(77)
+    S, T_seed, nsteps, C, Z, L, D, H = 37, 3, 14, 10, 2, 4, 88, 88
+    p = O.init_vrnn_params(rng, L, D, H, Z, C, True)
+    e = Engine("vrnn", 1, L=L, D=D, H=H, Z=Z, n_classes=C, use_x_prev=True, use_graph=False)
+    e.set_params({k: v.numpy() for k, v in p.items()})
+    T = T_seed + nsteps
+    seeds = dev(O.synth_rolls(rng, S, T_seed, D, 0.1), torch.uint8)
+    w = dev(rng.dirichlet(np.ones(C), S))
+    out = torch.zeros(S, T, D, dtype=torch.uint8, device="cuda")
+    bits = torch.zeros(S, T, 11, dtype=torch.uint8, device="cuda")
+    cfg = e.cfg()
+    st = CT.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib().clv_vrnn_sample(CT.byref(cfg), ptr(e.params), None, None, None, ptr(seeds), T_seed, nsteps, ptr(w),
+                                None, None, 5, 100, S, ptr(out), None, st))
+    check(lib().clv_vrnn_sample_bits(CT.byref(cfg), ptr(e.params), None, None, None, ptr(seeds), T_seed, nsteps, ptr(w),
+                                     None, None, 5, 100, S, ptr(bits), None, st))
+    torch.cuda.synchronize()
+    un = np.unpackbits(bits.cpu().numpy(), axis=-1, bitorder="little")[..., :D]
+    assert np.array_equal(un, out.cpu().numpy())
+    assert out.sum() > 0
