@@ -24,7 +24,7 @@ class clv_cfg(C.Structure):
                 ("w_log_var_prior", C.c_float),
                 ("gen_noise", C.c_int32), ("do_backward", C.c_int32), ("accumulate", C.c_int32),
                 ("gemm_algo", C.c_int32), ("x_shift", C.c_int32), ("gemm_algo_tc_lstm_min", C.c_int32), ("overlap_wgrad", C.c_int32),
-                ("y_shift", C.c_int32), ("reserved0", C.c_int32),
+                ("y_shift", C.c_int32), ("pair_bwd", C.c_int32),
                 ("seed", C.c_uint64)]
 
 
@@ -71,6 +71,8 @@ PROTOTYPES = {
                                      _P, _I32, _I32, _I32, _I32, _P]),
     "clv_lstm_pair_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P,
                                     _P, _P, _P, _P, _F, _I32, _U64, _P, _I32, _I32, _I32, _I32, _P]),
+    "clv_lstm_pair_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                    _I32, _I32, _I32, _I32, _I32, _P]),
     "clv_lstm_fwd_tc_scratch_bytes": (_I64, []),
     "clv_lstm_fwd_tc": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _I32, _I32, _I32, _P]),
     "clv_xhead_fwd_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _I64, _I32, _I32, _F, _I32, _P]),
@@ -152,13 +154,13 @@ def ptr(t):
 
 def make_cfg(model, B, L, D, H, Z, C_, use_x_prev, Hc=0, B_global=None, class_weight=1.0,
              kl_weight=1.0, w_kl_weight=1.0, w_log_var_prior=0.0, gen_noise=0, do_backward=1,
-             accumulate=0, gemm_algo=0, seed=0, x_shift=0, overlap_wgrad=0, tc_lstm_min=0, y_shift=0):
+             accumulate=0, gemm_algo=0, seed=0, x_shift=0, overlap_wgrad=0, tc_lstm_min=0, y_shift=0, pair_bwd=0):
     return clv_cfg(model=model, B=B, B_global=B if B_global is None else B_global, L=L, D=D, H=H,
                    Hc=Hc, Z=Z, C=C_, use_x_prev=int(bool(use_x_prev)), class_weight=class_weight,
                    kl_weight=kl_weight, w_kl_weight=w_kl_weight, w_log_var_prior=w_log_var_prior,
                    gen_noise=gen_noise, do_backward=do_backward, accumulate=accumulate,
                    gemm_algo=gemm_algo, x_shift=x_shift, gemm_algo_tc_lstm_min=tc_lstm_min,
-                   overlap_wgrad=overlap_wgrad, y_shift=y_shift, seed=seed)
+                   overlap_wgrad=overlap_wgrad, y_shift=y_shift, pair_bwd=pair_bwd, seed=seed)
 
 
 def param_layout(cfg):

@@ -401,3 +401,276 @@ extern "C" int clv_lstm_pair_fwd(float* gates_e, const float* Ue, const float* b
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }
+
+// ==================================================================================== backward
+// Mirror image of the forward wavefront: CTA 2p = DECODER BPTT of row group p, CTA 2p+1 = ENCODER BPTT one or
+// two steps behind.  The decoder emits dLoss/d(Z_mean | Z_log_var) of step t from the extra output quad of its
+// mat-vec (dZ = dA @ Kz^T, then the reparametrisation / z-KL backward); the encoder's helper warp polls those
+// rows (caller fills dZa with 0xFF) and hands them to the cell updates, which turn them into dLoss/dh per
+// cell (dh_t += dZa_t @ [Kzm | Kzv]^T).  Thread tiles as lstm_bwd_kernel<88,2>: thread (kq, ns) owns outputs
+// 4kq..4kq+3 x 22 gate columns of U^T; two row groups software-pipelined against each other.
+namespace {
+
+struct PairBwd {
+  float* gates[2];          // [B,L,4H] activated gates in, dLoss/d(pre-activation) out (0 = dec, 1 = enc)
+  const float* U[2];
+  const float* c[2];
+  const float* dh_out;      // decoder only: dLoss/dh from the X head
+  float* dAsum[2];          // [B,4H]
+  const float* Kw[2];       // [C,4H]
+  float* dW_ext;            // [B,C], zeroed by the caller: both BPTTs atomically add dAsum @ Kw^T
+  const float* Kdz;         // [Z,4H]
+  float* dZ;                // [B,L,Z]
+  const float *Zargs, *eps_z;
+  float* dZa;               // [B,L,2Z]: written by the decoder, polled by the encoder (0xFF-filled by the caller)
+  const float *Kzm, *Kzv;   // [H,Z]
+  float klw;
+  int B, L, C, Z;
+};
+
+constexpr int NT_B = 384, NMAIN_B = 352, DZRING = 8;
+
+template <bool ENC>
+__device__ __forceinline__ void pair_bwd_main(const PairBwd& a, float (*da_s)[PG][2], float (*dza_s)[2][4],
+                                              int* zprog_s, int* pub_s, const int tid, const int b0,
+                                              const int nrows) {
+  constexpr int H = PH, G = PG, NS = 16, NSZ = G / NS, NKU = H / 4;
+  constexpr int role = ENC ? 1 : 0;
+  const int kq = tid >> 4, ns = tid & 15, L = a.L, Z = a.Z;
+  const bool is_u = kq < NKU;
+  const int kk_c = (ns & 7) >> 1, q_c = ns & 1;
+  const bool lane_on = ns < 8;
+  const int j = is_u ? 4 * kq + kk_c : 0;
+  const int nbar = ENC ? NMAIN_B : NT_B;
+
+  float Ureg[4][NSZ];
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const int zz = 4 * (kq - NKU) + kk;
+    const float* rowp = is_u ? a.U[role] + (size_t)(4 * kq + kk) * G
+                             : ((!ENC && kq == NKU && zz < Z) ? a.Kdz + (size_t)zz * G : nullptr);
+#pragma unroll
+    for (int i2 = 0; i2 < NSZ / 2; ++i2) {
+      float2 u = make_float2(0.f, 0.f);
+      if (rowp) u = __ldg(reinterpret_cast<const float2*>(rowp + (i2 * NS + ns) * 2));
+      Ureg[kk][2 * i2] = u.x;
+      Ureg[kk][2 * i2 + 1] = u.y;
+    }
+  }
+  float kzm[2] = {0.f, 0.f}, kzv[2] = {0.f, 0.f};
+  if (ENC && is_u) {
+#pragma unroll
+    for (int z = 0; z < 2; ++z)
+      if (z < Z) { kzm[z] = __ldg(a.Kzm + (size_t)j * Z + z); kzv[z] = __ldg(a.Kzv + (size_t)j * Z + z); }
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+  for (int i = tid; i < 2 * G * 2; i += nbar) (&da_s[0][0][0])[i] = 0.f;
+
+  // this lane's two cells (group gi, row q_c): running pointer to the gate row, element offset of (row, t, j)
+  bool con[2];
+  float* gp[2];
+  ptrdiff_t ho[2];
+  float dc[2] = {0.f, 0.f}, dhrec[2] = {0.f, 0.f}, asum[2][4];
+  float pg[2][4], pct[2], pc2[2], pdh[2];
+  const float* const cbase = a.c[role];
+  const float* const dhbase = ENC ? nullptr : a.dh_out;
+#pragma unroll
+  for (int gi = 0; gi < 2; ++gi) {
+    con[gi] = is_u && lane_on && (2 * gi + q_c) < nrows;
+    const size_t bt = (size_t)(b0 + (con[gi] ? 2 * gi + q_c : 0)) * L + (L - 1);
+    gp[gi] = a.gates[role] + bt * G + j;
+    ho[gi] = (ptrdiff_t)(bt * H + j);
+    pct[gi] = pc2[gi] = pdh[gi] = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { asum[gi][g] = 0.f; pg[gi][g] = 0.f; ld_if(pg[gi][g], gp[gi] + g * H, con[gi]); }
+    ld_if(pct[gi], cbase + ho[gi], con[gi]);
+    ld_if(pc2[gi], cbase + ho[gi] - H, con[gi] && L > 1);
+    if (!ENC) ld_if(pdh[gi], dhbase + ho[gi], con[gi]);
+  }
+  __syncthreads();
+
+  // cell index m = (group m&1, step L-1-(m>>1));  block k: cell update of cell k | mat-vec of cell k-1 | barrier.
+  // tleft = steps still to come for the cell's group AFTER this one (prefetch guard)
+#define PAIR_BWD_BLOCK(GM, do_mv, mmv, GC, do_cell, mcell)                                               \
+  {                                                                                                       \
+    const bool cell_on = (do_cell) && con[GC];                                                            \
+    const int tc = L - 1 - ((mcell) >> 1);                                                                \
+    float pza[4] = {0.f, 0.f, 0.f, 0.f};                                                                  \
+    if (ENC && (do_cell)) {                                                                               \
+      while (ld_acquire_cta_shared(zprog_s) < (mcell) + 1) { }                                            \
+      const float4 zz = *reinterpret_cast<const float4*>(&dza_s[(mcell) & (DZRING - 1)][q_c][0]);         \
+      pza[0] = zz.x; pza[1] = zz.y; pza[2] = zz.z; pza[3] = zz.w;                                         \
+    }                                                                                                     \
+    /* ---- cell update (serial chain, branch-free, written first) */                                     \
+    const float ig = pg[GC][0], fg = pg[GC][1], gg = pg[GC][2], og = pg[GC][3];                           \
+    const float ct = pct[GC], cprev = pc2[GC];                                                            \
+    float dh = pdh[GC] + dhrec[GC];                                                                       \
+    if (ENC) {                                                                                            \
+      if (Z == 1) dh = fmaf(pza[0], kzm[0], fmaf(pza[1], kzv[0], dh));                                    \
+      else dh = fmaf(pza[0], kzm[0], fmaf(pza[1], kzm[1], fmaf(pza[2], kzv[0], fmaf(pza[3], kzv[1], dh)))); \
+    }                                                                                                     \
+    {   /* operands of this group's NEXT cell (one step earlier in time) */                               \
+      const int more = cell_on && tc > 0;                                                                 \
+      _Pragma("unroll") for (int g = 0; g < 4; ++g) ld_if(pg[GC][g], gp[GC] - G + g * H, more);           \
+      pct[GC] = cprev;                                                                                    \
+      pc2[GC] = 0.f;                                                                                      \
+      ld_if(pc2[GC], cbase + ho[GC] - 2 * H, cell_on && tc > 1);                                          \
+      if (!ENC) ld_if(pdh[GC], dhbase + ho[GC] - H, more);                                                \
+    }                                                                                                     \
+    const float tch = tanh_fast(ct);                                                                      \
+    const float d_o = dh * tch;                                                                           \
+    const float dcc = fmaf(dh * og, 1.0f - tch * tch, dc[GC]);                                            \
+    const float dai = (ig > 0.f && ig < 1.f) ? 0.2f * dcc * gg : 0.f;                                     \
+    const float daf = (fg > 0.f && fg < 1.f) ? 0.2f * dcc * cprev : 0.f;                                  \
+    const float dag = dcc * ig * (1.0f - gg * gg);                                                        \
+    const float dao = (og > 0.f && og < 1.f) ? 0.2f * d_o : 0.f;                                          \
+    /* ---- mat-vec [dh_rec | dZ] = dA @ [U | Kz]^T of the other group */                                 \
+    float2 acc2[4];                                                                                       \
+    _Pragma("unroll") for (int kk = 0; kk < 4; ++kk) acc2[kk] = make_float2(0.f, 0.f);                    \
+    _Pragma("unroll") for (int i2 = 0; i2 < NSZ / 2; ++i2) {                                              \
+      const float4 dv = *reinterpret_cast<const float4*>(&da_s[GM][(i2 * NS + ns) * 2][0]);               \
+      _Pragma("unroll") for (int kk = 0; kk < 4; ++kk) {                                                  \
+        ffma2(acc2[kk], Ureg[kk][2 * i2], make_float2(dv.x, dv.y));                                       \
+        ffma2(acc2[kk], Ureg[kk][2 * i2 + 1], make_float2(dv.z, dv.w));                                   \
+      }                                                                                                   \
+    }                                                                                                     \
+    if (cell_on) {                                                                                        \
+      dc[GC] = dcc * fg;                                                                                  \
+      float* ds = &da_s[GC][j][q_c];                                                                      \
+      ds[0] = dai; ds[H * 2] = daf; ds[2 * H * 2] = dag; ds[3 * H * 2] = dao;                             \
+      float* gpc = gp[GC];                                                                                \
+      gpc[0] = dai; gpc[H] = daf; gpc[2 * H] = dag; gpc[3 * H] = dao;                                     \
+      asum[GC][0] += dai; asum[GC][1] += daf; asum[GC][2] += dag; asum[GC][3] += dao;                     \
+      gp[GC] -= G;                                                                                        \
+      ho[GC] -= H;                                                                                        \
+    }                                                                                                     \
+    if (do_mv) {                                                                                          \
+      float acc[8];                                                                                       \
+      _Pragma("unroll") for (int kk = 0; kk < 4; ++kk) { acc[2 * kk] = acc2[kk].x; acc[2 * kk + 1] = acc2[kk].y; } \
+      _Pragma("unroll") for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);    \
+      const float val = reduce_scatter_p(acc, ns);   /* element kk_c * 2 + q_c */                          \
+      if (is_u) {                                                                                         \
+        dhrec[GM] = val;                                                                                  \
+      } else if (!ENC && kq == NKU && lane_on && kk_c < Z && (2 * (GM) + q_c) < nrows) {                  \
+        const int tm = L - 1 - ((mmv) >> 1);                                                              \
+        const size_t bt = (size_t)(b0 + 2 * (GM) + q_c) * L + tm;                                         \
+        const int z = kk_c;                                                                               \
+        const float mu = __ldg(a.Zargs + bt * 2 * Z + z), lv = __ldg(a.Zargs + bt * 2 * Z + Z + z);       \
+        const float e = __ldg(a.eps_z + bt * Z + z);                                                      \
+        a.dZ[bt * Z + z] = val;                                                                           \
+        a.dZa[bt * 2 * Z + z] = val + a.klw * mu;                                                         \
+        a.dZa[bt * 2 * Z + Z + z] = val * e * 0.5f * expf(lv * 0.5f) + a.klw * 0.5f * (expf(lv) - 1.0f);  \
+      }                                                                                                   \
+    }                                                                                                     \
+  }
+
+  const int ncell = 2 * L;
+  for (int k = 0; k <= ncell; k += 2) {
+    // block k (even): cell (A, .) | mat-vec of cell k-1 (B)
+    PAIR_BWD_BLOCK(1, k >= 1, k - 1, 0, k < ncell, k);
+    bar_named(1, nbar);
+    if (ENC && tid == 0) st_volatile_shared(pub_s, k + 1);
+    if (k + 1 > ncell) break;
+    // block k+1 (odd): cell (B, .) | mat-vec of cell k (A)
+    PAIR_BWD_BLOCK(0, true, k, 1, k + 1 < ncell, k + 1);
+    bar_named(1, nbar);
+    if (ENC && tid == 0) st_volatile_shared(pub_s, k + 2);
+  }
+#undef PAIR_BWD_BLOCK
+
+  // ---- per-row sums over time, and the gradient to the simplex W: dW[b,:] += dAsum[b,:] @ Kw^T
+#pragma unroll
+  for (int gi = 0; gi < 2; ++gi) {
+    if (con[gi]) {
+      float* ap = a.dAsum[role] + (size_t)(b0 + 2 * gi + q_c) * G + j;
+      ap[0] = asum[gi][0]; ap[H] = asum[gi][1]; ap[2 * H] = asum[gi][2]; ap[3 * H] = asum[gi][3];
+      float* ds = &da_s[gi][j][q_c];
+      ds[0] = asum[gi][0]; ds[H * 2] = asum[gi][1]; ds[2 * H * 2] = asum[gi][2]; ds[3 * H * 2] = asum[gi][3];
+    }
+  }
+  bar_named(1, nbar);
+  {
+    const int lane = tid & 31, wid = tid >> 5, nwarps = nbar >> 5;
+    const float* Ww = a.Kw[role];
+    for (int pc = wid; pc < nrows * a.C; pc += nwarps) {
+      const int r = pc / a.C, cc = pc - r * a.C;
+      float p = 0.f;
+#pragma unroll
+      for (int i0 = 0; i0 < G; i0 += 32) p = fmaf(da_s[r >> 1][i0 + lane][r & 1], __ldg(Ww + (size_t)cc * G + i0 + lane), p);
+      p = warp_sum(p);
+      if (lane == 0) atomicAdd(a.dW_ext + (size_t)(b0 + r) * a.C + cc, p);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT_B, 1) lstm_pair_bwd_kernel(const PairBwd a) {
+  __shared__ __align__(16) float da_s[2][PG][2];       // [group][gate column][row]
+  __shared__ __align__(16) float dza_s[DZRING][2][4];  // encoder: ring [cell & 7][row][mu.. | lv..]
+  __shared__ int zprog_s, pub_s;
+  const int tid = threadIdx.x;
+  const int pair = blockIdx.x >> 1, role = blockIdx.x & 1;     // 0 = decoder BPTT, 1 = encoder BPTT
+  const int b0 = pair * 4, L = a.L, Z = a.Z;
+  const int nrows = min(4, a.B - b0);
+  if (tid == 0) { zprog_s = 0; pub_s = 0; }
+  if (role == 1 && tid >= NMAIN_B) {
+    // ---- encoder helper warp: fetch dLoss/d(Z_mean | Z_log_var) of each cell from the decoder's rows
+    const int lane = tid - NMAIN_B;
+    pdl_wait();
+    pdl_launch_dependents();
+    __syncthreads();
+    const int q = lane >> 2, comp = lane & 3;
+    for (int m = 0; m < 2 * L; ++m) {
+      const int g = m & 1, t = L - 1 - (m >> 1);
+      if (lane == 0) {
+        while (ld_volatile_shared(&pub_s) < m - (DZRING - 2)) __nanosleep(20);   // ring slot free again
+      }
+      __syncwarp();
+      const int r = 2 * g + q;
+      const bool need = lane < 8 && r < nrows && comp < 2 * Z;
+      uint32_t u = 0u;
+      bool ready;
+      do {
+        ready = true;
+        if (need) {
+          asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(u) : "l"(a.dZa + ((size_t)(b0 + r) * L + t) * 2 * Z + comp) : "memory");
+          ready = u != 0xFFFFFFFFu;
+        }
+      } while (!__all_sync(0xffffffffu, ready));
+      if (lane < 8) dza_s[m & (DZRING - 1)][q][comp] = need ? __uint_as_float(u) : 0.f;
+      __syncwarp();
+      if (lane == 0) st_release_cta_shared(&zprog_s, m + 1);
+    }
+    return;
+  }
+  if (role == 0) pair_bwd_main<false>(a, da_s, dza_s, &zprog_s, &pub_s, tid, b0, nrows);
+  else pair_bwd_main<true>(a, da_s, dza_s, &zprog_s, &pub_s, tid, b0, nrows);
+}
+
+}  // namespace
+
+// Decoder BPTT + Z-head exchange + encoder BPTT of one CL-VRNN backward pass as one wavefront launch (the
+// mirror of clv_lstm_pair_fwd; replaces the two clv_lstm_bwd_heads calls).  The caller fills dZargs with
+// 0xFF bytes and zeroes dW_ext before the launch.  H = 88, Z <= 2, C <= 16.
+extern "C" int clv_lstm_pair_bwd(float* gates_d, const float* Ud, const float* c_d, const float* dh_d,
+                                 float* dAsum_d, const float* Kd_w, const float* Kd_z, float* dZ,
+                                 const float* Zargs, const float* eps_z, float klw_scale, float* dZargs,
+                                 float* gates_e, const float* Ue, const float* c_e, float* dAsum_e,
+                                 const float* Ke_w, const float* Kzm, const float* Kzv, float* dW_ext, int32_t C,
+                                 int32_t B, int32_t L, int32_t H, int32_t Z, void* stream) {
+  if (!gates_d || !Ud || !c_d || !dh_d || !dAsum_d || !Kd_w || !Kd_z || !dZ || !Zargs || !eps_z || !dZargs ||
+      !gates_e || !Ue || !c_e || !dAsum_e || !Ke_w || !Kzm || !Kzv || !dW_ext)
+    return CLV_E_INVALID;
+  if (H != PH || Z < 1 || Z > 2 || C < 1 || C > 16) return CLV_E_UNSUPPORTED;
+  if ((((uintptr_t)Ud | (uintptr_t)Ue | (uintptr_t)Kd_z) & 7) != 0) return CLV_E_UNSUPPORTED;   // float2 loads
+  if (B <= 0 || L <= 0) return CLV_OK;
+  PairBwd a;
+  a.gates[0] = gates_d; a.gates[1] = gates_e; a.U[0] = Ud; a.U[1] = Ue; a.c[0] = c_d; a.c[1] = c_e;
+  a.dh_out = dh_d; a.dAsum[0] = dAsum_d; a.dAsum[1] = dAsum_e; a.Kw[0] = Kd_w; a.Kw[1] = Ke_w;
+  a.dW_ext = dW_ext; a.Kdz = Kd_z; a.dZ = dZ; a.Zargs = Zargs; a.eps_z = eps_z; a.dZa = dZargs;
+  a.Kzm = Kzm; a.Kzv = Kzv; a.klw = klw_scale; a.B = B; a.L = L; a.C = C; a.Z = Z;
+  const int npairs = (B + 3) / 4;
+  CLV_CUDA(clv_launch(lstm_pair_bwd_kernel, 2 * npairs, NT_B, 0, (cudaStream_t)stream, a));
+  CLV_CHECK_LAUNCH();
+  return CLV_OK;
+}

@@ -35,6 +35,10 @@ extern "C" int clv_keyenc_bwd_full(const uint8_t*, const int32_t*, int32_t, int3
 extern "C" int clv_keyenc_bwd(const float*, const float*, const int32_t*, const float*, const float*,
                               const float*, const float*, float*, float*, int32_t, int32_t, int32_t, float,
                               float, float, void*);
+extern "C" int clv_lstm_pair_bwd(float*, const float*, const float*, const float*, float*, const float*, const float*,
+                                 float*, const float*, const float*, float, float*, float*, const float*, const float*,
+                                 float*, const float*, const float*, const float*, float*, int32_t, int32_t, int32_t,
+                                 int32_t, int32_t, void*);
 extern "C" int clv_lstm_pair_fwd(float*, const float*, const float*, const float*, float*, float*, float*,
                                  int32_t, const float*, const float*, const float*, const float*, float*,
                                  float*, const float*, int32_t, const float*, const float*, const float*,
@@ -303,6 +307,11 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   }
   // wavefront hand-over: the consumer polls the producer's rows themselves; 0xFFFFFFFF = "not written yet"
   if (pair) CLV_CUDA(cudaMemsetAsync(h_e, 0xFF, sizeof(float) * (size_t)BL * H, st));
+  const bool pairb = pair && c->do_backward && c->pair_bwd != 0;
+  if (pairb) {
+    CLV_CUDA(cudaMemsetAsync(dZa, 0xFF, sizeof(float) * (size_t)BL * 2 * Z, st));
+    CLV_CUDA(cudaMemsetAsync(dW_ext, 0, sizeof(float) * (size_t)B * C, st));
+  }
   TRY(clv_step_begin(loss, ctr, !c->accumulate, c->gen_noise, st));   // last: the key encoder chains on it
 
   Fork fk(st, c->overlap_wgrad != 0);
@@ -416,9 +425,13 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   const float klw = c->kl_weight * sbl;
   g_clv_pdl = (H == 88 && D == 88) ? pdl_enabled() : 0;
   {
-    const int rc__ = clv_lstm_bwd_heads(gates_d, Ud, c_d, dh, dAsum_d, Kd_w, C, dW_ext, 0, Kd_z, Z, dZ,
-                                        fuse_heads ? Zargs : nullptr, fuse_heads ? eps_z : nullptr, klw,
-                                        fuse_heads ? dZa : nullptr, nullptr, nullptr, nullptr, 0, B, L, H, st);
+    // both BPTTs as one wavefront launch (lstm_pair.cu), or the decoder BPTT alone
+    const int rc__ = pairb
+        ? clv_lstm_pair_bwd(gates_d, Ud, c_d, dh, dAsum_d, Kd_w, Kd_z, dZ, Zargs, eps_z, klw, dZa, gates_e, Ue, c_e,
+                            dAsum_e, Ke_w, Kzm, Kzv, dW_ext, C, B, L, H, Z, st)
+        : clv_lstm_bwd_heads(gates_d, Ud, c_d, dh, dAsum_d, Kd_w, C, dW_ext, 0, Kd_z, Z, dZ,
+                             fuse_heads ? Zargs : nullptr, fuse_heads ? eps_z : nullptr, klw,
+                             fuse_heads ? dZa : nullptr, nullptr, nullptr, nullptr, 0, B, L, H, st);
     g_clv_pdl = 0;
     if (rc__ != CLV_OK) return rc__;
   }
@@ -452,7 +465,9 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
     TRY(fk.gather());
     if (!dp) TRY(adam(R_DEC_K, CLV_N_TENSORS, 0, fk.opt_stream(), 0));
   }
-  if (fuse_heads)
+  if (pairb) {
+    // (the encoder BPTT ran inside the wavefront launch above)
+  } else if (fuse_heads)
     TRY_PDL(clv_lstm_bwd_heads(gates_e, Ue, c_e, nullptr, dAsum_e, Ke_w, C, dW_ext, 1, nullptr, 0, nullptr,
                                nullptr, nullptr, 0.f, nullptr, dZa, Kzm, Kzv, Z, B, L, H, st));
   else

@@ -44,7 +44,8 @@ class Engine:
                  optimizer="adam-wn", lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-8,
                  seed=0, device=None, world_size=1, rank=0, process_group=None, use_graph=True,
                  overlap_wgrad=True, gemm_algo=1, p2p_allreduce=False, tc_lstm_min=0,
-                 fused_optimizer=True, predict_next=False, micro_batch=None, workspace_budget_bytes=None):
+                 fused_optimizer=True, predict_next=False, micro_batch=None, workspace_budget_bytes=None,
+                 pair_bwd=False):
         _require_cuda()
         lib()
         if optimizer not in ("adam-wn", "adam"):
@@ -55,6 +56,7 @@ class Engine:
         self.B, self.L, self.D, self.H, self.Z, self.C = B, (L if self.model == 0 else 1), D, H, Z, n_classes
         self.Hc = Hc
         self.use_x_prev = bool(use_x_prev)
+        self.pair_bwd = bool(pair_bwd)                                 # both BPTTs as one wavefront launch (opt-in)
         self.predict_next = bool(predict_next)                         # --predict_next: target = next frame
         if self.predict_next and self.use_x_prev:
             raise ValueError("Can't use --predict_next if using --use_x_prev")     # cl_vrnn/train.py:28
@@ -180,7 +182,7 @@ class Engine:
         kw = dict(model=self.model, B=self.B, L=self.L, D=self.D, H=self.H, Z=self.Z, C_=self.C,
                   use_x_prev=self.use_x_prev, Hc=self.Hc, B_global=self.B * self.world_size,
                   seed=self.seed, x_shift=self.x_shift, y_shift=self.y_shift, overlap_wgrad=int(self.overlap_wgrad), gemm_algo=self.gemm_algo,
-                  tc_lstm_min=self.tc_lstm_min,
+                  tc_lstm_min=self.tc_lstm_min, pair_bwd=int(self.pair_bwd),
                   **self.hyper)
         kw.update(over)
         return _lib.make_cfg(**kw)

@@ -66,7 +66,9 @@ typedef struct clv_cfg {
   int32_t y_shift;      /* frame of the reconstruction TARGET inside a window; 0 = the target is
                            `current` (y == x, cl_vrnn/train.py:51-57).  --predict_next: windows of L+1
                            frames, current = frames 0..L-1 (x_shift 0), target = frames 1..L (y_shift 1) */
-  int32_t reserved0;
+  int32_t pair_bwd;     /* 1: both BPTTs as ONE wavefront launch (clv_lstm_pair_bwd).  Off by default: at B = 200
+                           it is 35.5 us against 18.7 + 19.3 us for the two launches, but the decoder-side weight
+                           gradients and Adam-WN range then no longer overlap the encoder BPTT (0.147 vs 0.137 ms/step) */
   uint64_t seed;        /* Philox key for gen_noise (make it rank-dependent)                  */
 } clv_cfg;
 
@@ -214,6 +216,18 @@ int clv_lstm_pair_fwd(float* gates_e, const float* Ue, const float* be, const fl
                       float* Zargs, float* Zs, float* loss_acc, float kl_scale, int32_t gen_noise,
                       uint64_t seed, const uint64_t* ctr, int32_t B, int32_t L, int32_t H, int32_t Z,
                       void* stream);
+
+/* Decoder BPTT + Z-head exchange + encoder BPTT of one CL-VRNN backward pass as one wavefront launch (the
+ * mirror of clv_lstm_pair_fwd; replaces the two clv_lstm_bwd_heads calls): CTA 2p = decoder BPTT of row group
+ * p, CTA 2p+1 = encoder BPTT one or two steps behind, fed with dLoss/d(Z_mean | Z_log_var) through dZargs,
+ * which its helper warp polls until the rows differ from the 0xFFFFFFFF pattern the CALLER fills dZargs with.
+ * dW_ext[B,C] must be ZEROED by the caller: both BPTTs add dAsum @ K_w^T to it atomically.  Arguments as
+ * clv_lstm_bwd_heads (gates_*: activated gates in, dLoss/d(pre-activation) out).  H = 88, Z <= 2, C <= 16. */
+int clv_lstm_pair_bwd(float* gates_d, const float* Ud, const float* c_d, const float* dh_d, float* dAsum_d,
+                      const float* Kd_w, const float* Kd_z, float* dZ, const float* Zargs, const float* eps_z,
+                      float klw_scale, float* dZargs, float* gates_e, const float* Ue, const float* c_e,
+                      float* dAsum_e, const float* Ke_w, const float* Kzm, const float* Kzv, float* dW_ext,
+                      int32_t C, int32_t B, int32_t L, int32_t H, int32_t Z, void* stream);
 
 /* Tensor-core form of the forward recurrence for large batches: 128 rows per CTA, h_{t-1} @ U on
  * tcgen05 (fp16 hi+lo splits of both operands, 3 products, fp32 accumulate in TMEM), cell state in

@@ -36,6 +36,21 @@ def test_vrnn_step_matches_oracle(B, L, C, Z, xp):
     assert util.rel_err(e.ws_view("h_d", (B, L, 88)).cpu().numpy(), out["h_d"].numpy()) < TOL
 
 
+@pytest.mark.parametrize("B,L,C,Z,xp", [(200, 16, 10, 2, True), (37, 5, 4, 1, False), (3, 9, 12, 2, True)])
+def test_vrnn_step_with_the_backward_wavefront_matches_oracle(B, L, C, Z, xp):
+    """clv_cfg.pair_bwd: decoder BPTT + Z-head exchange + encoder BPTT as one wavefront launch
+    (clv_lstm_pair_bwd), partial last row group and Z = 1 included."""
+    case = util.make_vrnn_case(B * 5 + L, B, L, C=C, Z=Z, use_x_prev=xp)
+    out, g = util.oracle_vrnn(case, **KW)
+    e = util.engine_for(case, "vrnn", use_graph=False, pair_bwd=True, **KW)
+    check_step(e, out, g)
+    # and twice in a row through a CUDA graph (the sentinel fills are part of the captured step)
+    e2 = util.engine_for(case, "vrnn", use_graph=True, pair_bwd=True, **KW)
+    e2.run(train=True, gen_noise=False)
+    torch.cuda.synchronize()
+    assert util.rel_err(e2.params.cpu().numpy(), e.params.cpu().numpy()) < 1e-6
+
+
 @pytest.mark.parametrize("B,C,Z,xp", [(100, 2, 4, True), (100, 10, 2, False), (5, 3, 16, True)])
 def test_vae_step_matches_oracle(B, C, Z, xp):
     case = util.make_vae_case(B + C, B, C=C, Z=Z, use_x_prev=xp)
