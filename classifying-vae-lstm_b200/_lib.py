@@ -71,6 +71,7 @@ PROTOTYPES = {
                                      _P, _I32, _I32, _I32, _I32, _P]),
     "clv_lstm_pair_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P,
                                     _P, _P, _P, _P, _F, _I32, _U64, _P, _I32, _I32, _I32, _I32, _P]),
+    "clv_vae_fused_step": (C.c_int, [_CFG, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "clv_lstm_pair_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                     _I32, _I32, _I32, _I32, _I32, _P]),
     "clv_lstm_fwd_tc_scratch_bytes": (_I64, []),

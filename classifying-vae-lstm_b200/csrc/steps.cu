@@ -35,6 +35,8 @@ extern "C" int clv_keyenc_bwd_full(const uint8_t*, const int32_t*, int32_t, int3
 extern "C" int clv_keyenc_bwd(const float*, const float*, const int32_t*, const float*, const float*,
                               const float*, const float*, float*, float*, int32_t, int32_t, int32_t, float,
                               float, float, void*);
+extern "C" int clv_vae_fused_step(const clv_cfg*, const float*, float*, float*, const uint8_t*, const int32_t*,
+                                  const int32_t*, float*, float*, const uint64_t*, float*, float*, float*, void*);
 extern "C" int clv_lstm_pair_bwd(float*, const float*, const float*, const float*, float*, const float*, const float*,
                                  float*, const float*, const float*, float, float*, float*, const float*, const float*,
                                  float*, const float*, const float*, const float*, float*, int32_t, int32_t, int32_t,
@@ -168,6 +170,11 @@ int tn_u8(const uint8_t* roll, const int32_t* off, int grp, int shift, int64_t l
 // launch whose stream predecessor is one of our kernels: allow programmatic dependent launch
 // (the kernel's parameter-only prologue overlaps the predecessor; see common.cuh)
 #define TRY_PDL(x) do { g_clv_pdl = pdl_enabled(); int rc__ = (x); g_clv_pdl = 0; if (rc__ != CLV_OK) return rc__; } while (0)
+static int vae_fused_max_rows() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CLV_VAE_FUSED_MAX_ROWS"); v = e ? atoi(e) : 4096; }
+  return v;
+}
 static int pair_disabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("CLV_NO_PAIR"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -536,6 +543,28 @@ int vae_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uin
   if (c->do_backward && !c->accumulate)
     CLV_CUDA(cudaMemsetAsync(Gr, 0, sizeof(float) * (po[V_X_B] + pc[V_X_B]), st));
 
+  // ---- small / medium batches: the whole forward + backward as ONE kernel with the model resident in shared
+  //      memory (vae_fused.cu); 3 launches per step instead of 37.  Large batches (where 8-frame tiles would
+  //      pay 41 k red.adds per tile) and shapes outside the fused kernel use the per-layer schedule below.
+  if (B <= vae_fused_max_rows()) {
+    const int rc_ = clv_vae_fused_step(c, P, Gr, loss, roll, off, labels, eps_w, eps_z, ctr, Wargs, W, Zargs, st);
+    if (rc_ == CLV_OK) {
+      if (opt && c->do_backward) {
+        if (opt->p2p) {
+          TRY(clv_adamwn_step_range_p2p(c, const_cast<float*>(P), opt->p2p, opt->state, opt->lr, opt->beta_1, opt->beta_2,
+                                        opt->epsilon, opt->weightnorm, 0, CLV_N_TENSORS, 0, 1, opt->loss_mirror, st));
+        } else {
+          if (opt->exchange && opt->exchange(opt->exchange_user, Gr, po[V_X_B] + pc[V_X_B] + 8, (void*)st) != 0)
+            return CLV_E_CUDA;
+          TRY_PDL(clv_adamwn_step_range(c, const_cast<float*>(P), Gr, opt->state, opt->lr, opt->beta_1, opt->beta_2,
+                                        opt->epsilon, opt->grad_scale, opt->weightnorm, 0, CLV_N_TENSORS, 1,
+                                        opt->loss_mirror, st));
+        }
+      }
+      return CLV_OK;
+    }
+    if (rc_ != CLV_E_UNSUPPORTED) return rc_;
+  }
   // ---- forward (cl_vae/model.py:141-188)
   TRY(nn_u8(roll, off, 1, sx, D, Khw, Hc, h_w, Hc, B, Hc, D, bhw, nullptr, 0, 0, 1, 0, st));
   TRY(nn_f32(h_w, Hc, Kwm, C1, Wargs, 2 * C1, B, C1, Hc, bwm, 0, 0, st));

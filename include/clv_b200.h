@@ -383,6 +383,15 @@ int clv_train_step_opt(const clv_cfg* cfg, float* params, float* grads, float* l
                        const uint8_t* roll, const int32_t* win_off, const int32_t* labels,
                        float* eps_w, float* eps_z, uint64_t* rng_ctr, void* workspace,
                        int64_t workspace_bytes, const clv_adam_args* opt, void* stream);
+/* CL-VAE forward + the four losses (+ backward into grads) for one batch as ONE kernel: a CTA carries a tile
+ * of 8 frames through all 8 Dense layers and back with every weight matrix resident in shared memory
+ * (cl_vae/model.py:136-218 and its TF-autodiff backward); weight gradients are added to `grads` with red.add
+ * (zero it first).  Wargs / W / Zargs are also written to the given workspace views.  Used by clv_train_step
+ * for B <= 4096; returns CLV_E_UNSUPPORTED outside D, H, Hc <= 96, Z, C <= 16 (per-layer schedule then). */
+int clv_vae_fused_step(const clv_cfg* cfg, const float* params, float* grads, float* loss_acc,
+                       const uint8_t* roll, const int32_t* win_off, const int32_t* labels, float* eps_w,
+                       float* eps_z, const uint64_t* rng_ctr, float* ws_Wargs, float* ws_W, float* ws_Zargs,
+                       void* stream);
 /* Named views into the workspace after a step (for parity tests): returns the float offset of
  * e.g. "W", "Zargs", "h_e", "h_d", "logits" or -1. */
 int64_t clv_workspace_offset(const clv_cfg* cfg, const char* name);
