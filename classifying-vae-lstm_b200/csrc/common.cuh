@@ -14,7 +14,7 @@ extern unsigned long long g_clv_launches;
   do {                                                      \
     cudaError_t e__ = cudaGetLastError();                   \
     if (e__ != cudaSuccess) return CLV_E_CUDA;              \
-    ++g_clv_launches;                                       \
+    __atomic_fetch_add(&g_clv_launches, 1ull, __ATOMIC_RELAXED); \
   } while (0)
 
 #define CLV_CUDA(call)                                      \
@@ -57,6 +57,14 @@ __device__ __forceinline__ void ffma2(float2& acc, const float s, const float2 v
   asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc.x), "f"(acc.y));
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(r));
+}
+
+// slot of the current device in the small per-device tables (function attributes, auxiliary streams)
+constexpr int CLV_MAX_DEVICES = 16;
+static inline int clv_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev % CLV_MAX_DEVICES;
 }
 
 static inline int clv_num_sms() {

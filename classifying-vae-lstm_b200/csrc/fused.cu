@@ -531,26 +531,28 @@ extern "C" int clv_xhead_fwd_bwd(const float* h, const float* Kx, const float* b
   if (H != XD || D != XD || R >= (1LL << 32)) return CLV_E_UNSUPPORTED;
   if (R <= 0) return CLV_OK;
   const size_t smem = sizeof(float) * (2 * XD * XD + XD * XRP);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[CLV_MAX_DEVICES] = {};   // per device: function attributes belong to a context
+  const int attr_set_dev = clv_device_slot();
+  if (!attr_set[attr_set_dev]) {
     CLV_CUDA(cudaFuncSetAttribute(xhead_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CLV_CUDA(cudaFuncSetAttribute(xhead_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // without this the driver sizes the carve-out for ONE block and the grid's co-residency is lost
     CLV_CUDA(cudaFuncSetAttribute(xhead_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   (int)cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
+    attr_set[attr_set_dev] = true;
   }
   int64_t xgrid = (R + XR - 1) / XR;
   const bool al8 = (((uintptr_t)dlogits | (uintptr_t)dh) & 7) == 0 && (((uintptr_t)roll) & 1) == 0;
   if ((R + XR2 - 1) / XR2 > clv_num_sms() && al8) {
     // large R: 64-row tiles, 8x2 register tile, 2 CTAs (86 KB smem each) per SM
     const size_t smem2 = sizeof(float) * (2 * XD * XD + XD * XRP2);
-    static bool attr2 = false;
-    if (!attr2) {
+    static bool attr2[CLV_MAX_DEVICES] = {};   // per device: function attributes belong to a context
+  const int attr2_dev = clv_device_slot();
+    if (!attr2[attr2_dev]) {
       CLV_CUDA(cudaFuncSetAttribute(xhead2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
       CLV_CUDA(cudaFuncSetAttribute(xhead2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     (int)cudaSharedmemCarveoutMaxShared));
-      attr2 = true;
+      attr2[attr2_dev] = true;
     }
     int64_t g2 = (R + XR2 - 1) / XR2;
     if (g2 > 2LL * clv_num_sms()) g2 = 2LL * clv_num_sms();

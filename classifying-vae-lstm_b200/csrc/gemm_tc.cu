@@ -340,12 +340,13 @@ extern "C" int clv_inproj_tc(const uint8_t* roll, const int32_t* win_off, int32_
   __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(scratch);
   wsplit_kernel<<<(2 * TN * KP + 255) / 256, 256, 0, st>>>(W, ldw, D, img);
   CLV_CHECK_LAUNCH();
-  static bool attr_set = false;
+  static bool attr_set[CLV_MAX_DEVICES] = {};   // per device: function attributes belong to a context
+  const int attr_set_dev = clv_device_slot();
   const int smem = 2 * A_BYTES + B_BYTES + STAGE_BYTES + 1024;
-  if (!attr_set) {
+  if (!attr_set[attr_set_dev]) {
     CLV_CUDA(cudaFuncSetAttribute(inproj_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CLV_CUDA(cudaFuncSetAttribute(inproj_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_set[attr_set_dev] = true;
   }
   TcArgs a;
   a.roll = roll; a.off = win_off; a.grp = grp; a.shift = shift; a.D = D; a.img = img; a.C = C;

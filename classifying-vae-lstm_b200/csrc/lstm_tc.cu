@@ -289,11 +289,12 @@ extern "C" int clv_lstm_fwd_tc(float* gates, const float* U, const float* Zs, co
   __half* img = reinterpret_cast<__half*>(scratch);
   usplit_kernel<<<(G * KP + 255) / 256, 256, 0, st>>>(U, img);
   CLV_CHECK_LAUNCH();
-  static bool attr_set = false;
+  static bool attr_set[CLV_MAX_DEVICES] = {};   // per device: function attributes belong to a context
+  const int attr_set_dev = clv_device_slot();
   const int smem = 2 * U_IMG + 2 * A_IMG + 1024;
-  if (!attr_set) {
+  if (!attr_set[attr_set_dev]) {
     CLV_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_set[attr_set_dev] = true;
   }
   LtArgs a;
   a.gates = gates; a.uimg = img; a.hout = h; a.cout = c; a.Zs = Zs; a.Kz = Kz; a.Z = Zs ? Z : 0;

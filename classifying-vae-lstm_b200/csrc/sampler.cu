@@ -372,8 +372,9 @@ static int vrnn_sample_impl(const clv_cfg* cfg, const float* params, const float
   const int64_t cost16 = ((((int64_t)S + 15) / 16 + slots - 1) / slots) * 16;
   const int64_t cost24 = ((((int64_t)S + 23) / 24 + slots - 1) / slots) * 24;
   const auto smem_for = [](int bt) { return sizeof(float) * bt * (128 + 4 * SH + 16 + 32 + 16); };
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[CLV_MAX_DEVICES] = {};   // per device: function attributes belong to a context
+  const int attr_set_dev = clv_device_slot();
+  if (!attr_set[attr_set_dev]) {
     CLV_CUDA(cudaFuncSetAttribute(vrnn_sample_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_for(24)));
     // 4 CTAs per SM need 140-210 KB of shared memory: ask for the maximum carve-out explicitly
@@ -381,7 +382,7 @@ static int vrnn_sample_impl(const clv_cfg* cfg, const float* params, const float
                                   (int)cudaSharedmemCarveoutMaxShared));
     CLV_CUDA(cudaFuncSetAttribute(vrnn_sample_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   (int)cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
+    attr_set[attr_set_dev] = true;
   }
   if (cost24 < cost16)
     vrnn_sample_kernel<24><<<(S + 23) / 24, SAMP_T, smem_for(24), (cudaStream_t)stream>>>(a);

@@ -303,7 +303,9 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
 
   // encoder/decoder wavefront (lstm_pair.cu): both recurrences in one launch, the decoder a step or two
   // behind the encoder; needs the 2-latent head exchange and the FFMA recurrence
-  const bool pair = !tcl && Z <= 2 && H == 88 && C <= 16 && !pair_disabled();
+  // (one wave only: with more CTA pairs than SMs the 4-row CTAs lose to the 2..4-row kernels they replace --
+  //  B = 1 024, L = 32: 203 us against 2 x 92 us, profiles/sweep_r2.jsonl)
+  const bool pair = !tcl && Z <= 2 && H == 88 && C <= 16 && 2 * ((B + 3) / 4) <= clv_num_sms() && !pair_disabled();
   // zero the gradients; data parallel over peer memory: only once no peer still reads last step's (both off
   // the critical path when side streams exist: nothing writes a gradient before the first join)
   const bool side_zero = opt && opt->p2p && c->overlap_wgrad != 0 && side_ready() && c->do_backward && !c->accumulate;

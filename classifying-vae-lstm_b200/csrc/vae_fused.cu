@@ -440,10 +440,11 @@ extern "C" int clv_vae_fused_step(const clv_cfg* c, const float* P, float* Gr, f
   a.sx = c->x_shift > 0 ? c->x_shift : (c->use_x_prev ? 1 : 0);
   a.sy = c->y_shift > 0 ? c->y_shift : a.sx;
   a.gen_noise = c->gen_noise; a.do_backward = c->do_backward;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[CLV_MAX_DEVICES] = {};   // per device: function attributes belong to a context
+  const int attr_set_dev = clv_device_slot();
+  if (!attr_set[attr_set_dev]) {
     CLV_CUDA(cudaFuncSetAttribute(vae_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_set = true;
+    attr_set[attr_set_dev] = true;
   }
   int grid = (c->B + VR - 1) / VR;
   if (grid > clv_num_sms()) grid = clv_num_sms();

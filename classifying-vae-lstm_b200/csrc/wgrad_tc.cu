@@ -408,11 +408,12 @@ extern "C" int clv_lstm_wgrad_tc(const float* dA, const uint8_t* roll, const int
       (gKx && ((uintptr_t)roll & 7)))
     return CLV_E_UNSUPPORTED;
   if (R <= 0) return CLV_OK;
-  static bool attr_set = false;
+  static bool attr_set[CLV_MAX_DEVICES] = {};   // per device: function attributes belong to a context
+  const int attr_set_dev = clv_device_slot();
   const int smem = NSTAGE * STAGE + NRAW * RAW_STAGE + 1024;
-  if (!attr_set) {
+  if (!attr_set[attr_set_dev]) {
     CLV_CUDA(cudaFuncSetAttribute(lstm_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_set[attr_set_dev] = true;
   }
   WgArgs a;
   a.dA = dA; a.roll = roll; a.off = win_off; a.h = h; a.Zs = Zs; a.gKx = gKx; a.gU = gU; a.gKz = gKz;

@@ -11,7 +11,11 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
- *     the library never allocates or frees device memory, has no globals and never synchronises;
+ *     the library never allocates or frees device memory and never synchronises (clv_fp32_peak_probe, a
+ *     diagnostic, excepted).  Process-wide state is limited to: the auxiliary streams / events that
+ *     clv_runtime_init creates per device, a per-device "kernel attributes set" flag per kernel, the
+ *     diagnostic launch counter (atomic) and a thread-local launch-attribute switch -- nothing that depends
+ *     on a model or a call;
  *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered (graph-capturable);
  *   - return value: 0 = CLV_OK, negative = CLV_E_*; clv_error_string() names it;
  *   - matrices are row-major fp32 in Keras [in,out] layout; piano-rolls are uint8 {0,1}

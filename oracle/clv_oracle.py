@@ -5,10 +5,23 @@ CPU restatement (PyTorch-CPU, float64 or float32) of the CL-VRNN / CL-VAE hot pa
 mobeets/classifying-vae-lstm.  Only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs may import this module.
 
-PARITY UNPINNED for the model maths: the reference is Python 2 + Keras 2.0.0 + TensorFlow 1.0.1
-(requirements.txt:1-2), none of which exist in this environment, and the reference ships no tests,
-golden vectors or saved weights.  Every Keras/TF-internal semantic below is restated from the
-published Keras 2.0.0 / TF 1.0.1 sources ("[K2-recall]") and is an ASSUMPTION of this oracle:
+PARITY STATUS.  The reference is Python 2 + Keras 2.0.0 + TensorFlow 1.0.1 (requirements.txt:1-2), none of
+which exist in this environment, and it ships no tests, golden vectors or saved weights.  What pins this
+oracle (tests/golden/, produced by tests/golden/make_golden.py IN the build container, where /root/reference
+exists; checked by tests/test_golden_models.py, tests/test_oracle.py, tests/test_pianoroll.py):
+
+  * PINNED to the reference's own source, executed: the whole of code/cl_vrnn/model.py and code/cl_vae/model.py
+    -- get_model (graph wiring, concat orders, Lambdas, the four loss closures, loss_weights, metrics),
+    make_w_encoder / make_z_encoder / make_decoder, generate_sample, sample_x/_w/_z/_w_discrete -- run (after a
+    mechanical tuple-parameter rewrite, nothing else) against tests/golden/keras_shim.py, a recorder shim of
+    the Keras functional API on PyTorch-CPU float64.  Losses agree with this oracle to 1e-12, every gradient
+    tensor to float32 storage precision, sampled rolls bit for bit under the same np.random.seed (including the
+    draw order: randn(1, C-1) per inferred-key chunk even without noise, one np.random.choice for w_discrete,
+    then randn(z), rand(88) per step), for use_x_prev on/off, --predict_next, inferred / discrete / given keys,
+    1-D seeds, CL-VAE use_z_prior.  Also executed unmodified: utils/pianoroll.py (PianoData on both bundled
+    pickles) and utils/weightnorm.py (AdamWithWeightnorm.get_updates on a numpy shim).
+  * STILL "[K2-recall]" (restated from the published Keras 2.0.0 / TF 1.0.1 sources inside the shim and here,
+    because those packages cannot be installed): the PRIMITIVES the reference calls --
 
   (1) LSTM: gate order i,f,c,o; recurrent_activation hard_sigmoid = clip(0.2x+0.5,0,1);
       activation tanh; weights [kernel, recurrent_kernel, bias]; h0=c0=0.
@@ -20,11 +33,6 @@ published Keras 2.0.0 / TF 1.0.1 sources ("[K2-recall]") and is an ASSUMPTION of
   (6) metric 'accuracy' on W with a custom loss = categorical accuracy.
   (7) Keras Adam: p -= lr_t*m/(sqrt(v)+eps), lr_t = lr*sqrt(1-b2^t)/(1-b1^t).
   (8) clip_by_value passes its gradient on the closed interval (torch.clamp does the same).
-
-What IS pinned against reference code run in this container (tests/golden/, made by
-tests/golden/make_golden.py): utils/pianoroll.py (PianoData) and utils/weightnorm.py
-(get_weightnorm_params_and_grads / add_weightnorm_param_updates / AdamWithWeightnorm.get_updates
-executed against a numpy shim of the keras/tensorflow API).
 
 All noise is an explicit input (eps_w, eps_z, u) so the CUDA path can be compared on identical draws.
 Parameter containers are plain dicts name -> tensor in Keras [in,out] layout.
