@@ -48,7 +48,8 @@ def test_vrnn_step_with_the_backward_wavefront_matches_oracle(B, L, C, Z, xp):
     e2 = util.engine_for(case, "vrnn", use_graph=True, pair_bwd=True, **KW)
     e2.run(train=True, gen_noise=False)
     torch.cuda.synchronize()
-    assert util.rel_err(e2.params.cpu().numpy(), e.params.cpu().numpy()) < 1e-6
+    # the weight gradients are float atomics (order varies run to run) and the first Adam step is lr * g / |g|
+    assert util.rel_err(e2.params.cpu().numpy(), e.params.cpu().numpy()) < 1e-5
 
 
 @pytest.mark.parametrize("B,C,Z,xp", [(100, 2, 4, True), (100, 10, 2, False), (5, 3, 16, True)])
