@@ -202,7 +202,7 @@ def main():
     ap.add_argument("--no-vae", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-fused-opt", action="store_true", help="step then Adam-WN as two calls (N=1)")
-    ap.add_argument("--p2p", type=int, default=-1, help="1/0: force the fused peer-memory all-reduce+Adam path on/off")
+    ap.add_argument("--p2p", type=int, default=-1, help="data-parallel exchange: 0 NCCL (default), 1 one-shot all-reduce kernels over peer memory, 2 exchange fused into the Adam-WN kernels")
     ap.add_argument("--batch", type=int, default=CFG["B"], help="per-GPU batch (sweep points)")
     ap.add_argument("--seq-len", type=int, default=CFG["L"])
     args = ap.parse_args()
@@ -245,7 +245,7 @@ def main():
         return float(t.item())
 
     # ---------------- model through the public API (mirrors cl_vrnn/train.py:45-46)
-    extra = {} if args.p2p < 0 else {"p2p_allreduce": bool(args.p2p)}
+    extra = {} if args.p2p < 0 else {"p2p_allreduce": ("fused" if args.p2p == 2 else bool(args.p2p))}
     if args.no_fused_opt:
         extra["fused_optimizer"] = False
     model, _ = get_model(B, D, H, Z, L, Cc, True, "adam-wn", world_size=world, rank=rank,
@@ -336,11 +336,15 @@ def main():
     clk = ClockSampler(local) if rank == 0 else None   # one poller per job: nvidia-smi takes driver locks
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    e.p2p_stats()                              # (reset the exchange diagnostics)
     ev0.record()
+    th0 = time.perf_counter()
     for i in range(K):
         step_resident(i)
+    host_enqueue_ms = (time.perf_counter() - th0) / K * 1e3    # host time to ENQUEUE a step (no sync inside)
     ev1.record()
     barrier()
+    p2p_stats = e.p2p_stats()
     ms_step = max_over_ranks(ev0.elapsed_time(ev1) / K)
     clocks = clk.stop() if clk is not None else None
     losses = e.read_losses()
@@ -621,6 +625,9 @@ def main():
         }
         if dp_parity is not None:
             line["dp_parity_max_rel_err"] = dp_parity
+        line["host_enqueue_ms_per_step"] = round(host_enqueue_ms, 4)
+        if p2p_stats:
+            line["p2p_exchange_rank0_us"] = p2p_stats
         if B != CFG["B"] or L != CFG["L"]:
             line["config"]["workload"] = "cl_vrnn train step, synthetic sweep point B=%d/GPU L=%d" % (B, L)
         print(json.dumps(line), flush=True)

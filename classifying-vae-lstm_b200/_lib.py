@@ -102,6 +102,9 @@ PROTOTYPES = {
     "clv_p2p_flag_ints": (C.c_int, []),
     "clv_p2p_signal": (C.c_int, [_P, _P, _CFG, _I32, _P]),
     "clv_p2p_wait_done": (C.c_int, [_P, _P, _CFG, _P]),
+    "clv_p2p_allreduce": (C.c_int, [_P, _P, _CFG, _I64, _I64, _I32, _I32, _P]),
+    "clv_p2p_allreduce_blocks": (C.c_int, [_I64]),
+    "clv_adamwn_range_blocks": (C.c_int, [_CFG, _I32, _I32, _I32]),
     "clv_adamwn_step_range_p2p": (C.c_int, [_CFG, _P, _P, _P, _D, _D, _D, _D, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "clv_fp32_peak_probe": (C.c_int, [_I32, _P, _I64, C.POINTER(C.c_double), _P]),
 }
@@ -117,7 +120,7 @@ class clv_adam_args(C.Structure):
 class clv_p2p_args(C.Structure):
     """include/clv_b200.h: clv_p2p_args (peer-memory data parallelism, hand-shake inside the kernels)."""
     _fields_ = [("peer_grads", C.c_void_p), ("peer_flags", C.c_void_p), ("n_peers", C.c_int32), ("rank", C.c_int32),
-                ("gsum", C.c_void_p), ("loss_out", C.c_void_p)]
+                ("gsum", C.c_void_p), ("loss_out", C.c_void_p), ("form", C.c_int32)]
 
 
 # include/clv_b200.h: clv_exchange_fn(user, buf, count, stream) -> int

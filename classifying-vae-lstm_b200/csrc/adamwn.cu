@@ -40,6 +40,8 @@ struct PeerSet {
 constexpr int P2P_MAXR = 16, P2P_SLOTS = 4;
 __device__ __forceinline__ int32_t* flag_ready(int32_t* f, int slot, int src) { return f + slot * P2P_MAXR + src; }
 __device__ __forceinline__ int32_t* flag_done(int32_t* f, int src) { return f + P2P_SLOTS * P2P_MAXR + src; }
+// last row: local counters (never written by a peer)
+__device__ __forceinline__ int32_t* flag_local(int32_t* f, int i) { return f + (P2P_SLOTS + 1) * P2P_MAXR + i; }
 __device__ __forceinline__ int ld_acquire_sys(const int32_t* p) {
   int v;
   asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
   __syncthreads();
   if (tid == 0) {
     const unsigned d = atomicAdd(done, 1u);
-    if (d == gridDim.x - 1) {
+    if (d == (unsigned)advance - 1u) {       // advance = number of blocks of the step's final launch(es)
       const float f = (float)(sqrt(1.0 - pow(b2d, (double)(t + 1))) / (1.0 - pow(b1d, (double)(t + 1))));
       fct[1] = __float_as_int(f);
       fct[0] = t + 1;
@@ -371,6 +373,102 @@ __global__ void __launch_bounds__(NTH) adamwn_kernel(const AdamPlan pl, float* _
         __threadfence_system();
         for (int p = 0; p < ps.n; ++p) st_release_sys(flag_done(ps.flags[p], ps.rank), t);
       }
+    }
+  }
+}
+
+// ---- one-shot all-reduce over peer memory (clv_p2p_allreduce) ------------------------------------------------
+// gsum[e] = sum_p peers[p][e] for e in [e0, e0 + cnt), summed in rank order (bitwise identical on every rank).
+// The launch is stream-ordered behind the kernels that produced this rank's bucket: block 0 publishes the bucket
+// (step number into every peer's flag block), every block waits for the peers' flags by polling LOCAL memory,
+// then the grid streams the peers' buffers over NVLink with NP independent 16-byte loads in flight per thread.
+// `last`: the final bucket of a step -- the block that finishes last tells the peers that this rank no longer
+// reads their gradients ("done" flags, waited for by clv_p2p_wait_done before the next step zeroes them).
+//
+// No fences (each system-scope fence measured 1.7 us, profiles/nvl_probe_r2.txt; the first version of this
+// kernel had four in series and took 11-16 us): the gradients were written by EARLIER kernels of the stream,
+// so they are in this GPU's L2 -- the point of coherence for peer accesses -- before this kernel starts, and a
+// plain system-scope store of the flag is enough (the start-of-collective barrier of NCCL's LL protocol and of
+// vLLM's custom all-reduce rely on the same property); the consumer reads the peers' data with volatile loads
+// (never from a stale L1 line), issued after it has seen the flag.  The "done" flag only orders READS that
+// have already returned their values.  The polls are bounded (~2 minutes): a peer that never arrives
+// traps the kernel instead of hanging the GPU for good.
+constexpr int AR_NTH = 512;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ float4 ld_volatile_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(int32_t* p, const int v) {
+  asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <int NP>
+__global__ void __launch_bounds__(AR_NTH) p2p_allreduce_kernel(const float* const* __restrict__ peers,
+                                                               int32_t* const* __restrict__ flags, const int n,
+                                                               const int rank, const int slot, const int* iter,
+                                                               float* __restrict__ gsum, const int64_t e0,
+                                                               const int64_t cnt, const int last) {
+  __shared__ const float* pp[NP];
+  pdl_wait();
+  const int t = *iter + 1;
+  const int tid = threadIdx.x;
+  // diagnostics (block 0): ns spent waiting for the peers / moving data, summed per slot in the local flag row
+  const bool diag = blockIdx.x == 0 && tid == 0;
+  unsigned long long tg0 = 0, tg1 = 0;
+  if (diag) tg0 = globaltimer_ns();
+  if (tid < NP) pp[tid] = tid < n ? peers[tid] : nullptr;
+  if (blockIdx.x == 0 && tid < n) st_relaxed_sys(flag_ready(flags[tid], slot, rank), t);
+  if (tid < n) {
+    const volatile int32_t* f = flag_ready(flags[rank], slot, tid);
+    const long long t0 = clock64();
+    while (*f < t) {
+      if (clock64() - t0 > 240000000000ll) __trap();     // ~2 minutes
+    }
+  }
+  __syncthreads();
+  if (diag) tg1 = globaltimer_ns();
+  pdl_launch_dependents();      // the update that follows may start fetching its W / m / v
+  // head up to the first 16-byte boundary, 16-byte body, tail
+  const int64_t head = min(cnt, (int64_t)((4 - (e0 & 3)) & 3));
+  const int64_t nv = (cnt - head) >> 2;
+  const int64_t tail0 = head + (nv << 2);
+  const int64_t gt = (int64_t)blockIdx.x * AR_NTH + tid, gs = (int64_t)gridDim.x * AR_NTH;
+  for (int64_t i = gt; i < nv; i += gs) {
+    const int64_t e = e0 + head + (i << 2);
+    float4 v[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+      if (p < n) v[p] = ld_volatile_f4(pp[p] + e);
+    float4 a = v[0];
+#pragma unroll
+    for (int p = 1; p < NP; ++p)
+      if (p < n) { a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w; }
+    *reinterpret_cast<float4*>(gsum + e) = a;
+  }
+  if (gt < head + (cnt - tail0)) {
+    const int64_t e = e0 + (gt < head ? gt : tail0 + (gt - head));
+    float a = *(const volatile float*)(pp[0] + e);
+    for (int p = 1; p < n; ++p) a += *(const volatile float*)(pp[p] + e);
+    gsum[e] = a;
+  }
+  if (diag && slot < 4) {
+    int32_t* d = flag_local(flags[rank], 1 + 3 * slot);
+    atomicAdd(d, (int)(tg1 - tg0));
+    atomicAdd(d + 1, (int)(globaltimer_ns() - tg1));
+    atomicAdd(d + 2, 1);
+  }
+  if (!last) return;
+  __syncthreads();              // every load of this block has returned (its value went into a store)
+  if (tid == 0) {
+    int32_t* cntr = flag_local(flags[rank], 0);
+    if (atomicAdd(cntr, 1) == last - 1) {     // last = number of blocks of the step's final bucket launch(es)
+      *cntr = 0;
+      for (int p = 0; p < n; ++p) st_relaxed_sys(flag_done(flags[p], rank), t);
     }
   }
 }
@@ -452,7 +550,7 @@ extern "C" int clv_adamwn_step_range(const clv_cfg* cfg, float* params, const fl
   if (nb <= 0) return CLV_OK;
   CLV_CUDA(clv_launch(adamwn_kernel<false>, nb, NTH, 0, (cudaStream_t)stream, pl, params, grads, state, lr,
                       beta_1, beta_2, (float)epsilon, (float)grad_scale, (int)weightnorm, ps,
-                      pl.first_block[t_first], (int)advance, loss_mirror));
+                      pl.first_block[t_first], advance == 1 ? nb : (int)advance, loss_mirror));
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }
@@ -475,13 +573,14 @@ extern "C" int clv_adamwn_step_p2p(const clv_cfg* cfg, float* params, const floa
   if (rc != CLV_OK) return rc;
   PeerSet ps = {peer_grads, n_peers, gsum, loss_out, nullptr, 0, 0, 1};
   adamwn_kernel<true><<<pl.first_block[CLV_N_TENSORS], NTH, 0, (cudaStream_t)stream>>>(
-      pl, params, nullptr, state, lr, beta_1, beta_2, (float)epsilon, 1.0f, weightnorm, ps, 0, 1, nullptr);
+      pl, params, nullptr, state, lr, beta_1, beta_2, (float)epsilon, 1.0f, weightnorm, ps, 0,
+      pl.first_block[CLV_N_TENSORS], nullptr);
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }
 
 // ---- peer-memory data parallelism with the hand-shake inside the kernels (clv_p2p_args) ------------------
-extern "C" int clv_p2p_flag_ints(void) { return (P2P_SLOTS + 1) * P2P_MAXR; }
+extern "C" int clv_p2p_flag_ints(void) { return (P2P_SLOTS + 2) * P2P_MAXR; }
 
 extern "C" int clv_p2p_signal(const clv_p2p_args* pp, const float* state, const clv_cfg* cfg, int32_t slot,
                               void* stream) {
@@ -508,6 +607,47 @@ extern "C" int clv_p2p_wait_done(const clv_p2p_args* pp, const float* state, con
   return CLV_OK;
 }
 
+extern "C" int clv_p2p_allreduce_blocks(int64_t count) {
+  int nb = (int)((count / 4 + AR_NTH - 1) / AR_NTH);
+  return nb < 1 ? 1 : (nb > clv_num_sms() ? clv_num_sms() : nb);
+}
+
+extern "C" int clv_adamwn_range_blocks(const clv_cfg* cfg, int32_t weightnorm, int32_t t_first, int32_t t_last) {
+  if (!cfg || t_first < 0 || t_last > CLV_N_TENSORS || t_first >= t_last) return CLV_E_INVALID;
+  AdamPlan pl;
+  int rc = make_plan(cfg, &pl, weightnorm);
+  if (rc != CLV_OK) return rc;
+  return pl.first_block[t_last] - pl.first_block[t_first];
+}
+
+extern "C" int clv_p2p_allreduce(const clv_p2p_args* pp, const float* state, const clv_cfg* cfg, int64_t first,
+                                 int64_t count, int32_t slot, int32_t last, void* stream) {
+  if (!pp || !state || !cfg || !pp->peer_grads || !pp->peer_flags || !pp->gsum) return CLV_E_INVALID;
+  if (slot < 0 || slot >= P2P_SLOTS || pp->n_peers < 1 || pp->n_peers > P2P_MAXR || pp->rank < 0 ||
+      pp->rank >= pp->n_peers)
+    return CLV_E_INVALID;
+  AdamPlan pl;
+  int rc = make_plan(cfg, &pl, 1);
+  if (rc != CLV_OK) return rc;
+  if (first < 0 || count <= 0 || first + count > pl.P + 8) return CLV_E_INVALID;
+  const int* iter = reinterpret_cast<const int*>(state + 2 * pl.P + 3 * (int64_t)pl.NC + 2);
+  // enough threads for one 16-byte chunk each, at most one CTA per SM (the remote loads are latency-bound:
+  // a wide grid with few chunks per thread finishes in about one NVLink round trip per chunk batch)
+  const int nb = clv_p2p_allreduce_blocks(count);
+  const int n = pp->n_peers;
+  if (last == 1) last = nb;
+#define CLV_AR(NP)                                                                                             \
+  CLV_CUDA(clv_launch(p2p_allreduce_kernel<NP>, nb, AR_NTH, 0, (cudaStream_t)stream, pp->peer_grads,            \
+                      pp->peer_flags, n, (int)pp->rank, (int)slot, iter, pp->gsum, first, count, (int)last))
+  if (n <= 2) CLV_AR(2);
+  else if (n <= 4) CLV_AR(4);
+  else if (n <= 8) CLV_AR(8);
+  else CLV_AR(16);
+#undef CLV_AR
+  CLV_CHECK_LAUNCH();
+  return CLV_OK;
+}
+
 extern "C" int clv_adamwn_step_range_p2p(const clv_cfg* cfg, float* params, const clv_p2p_args* pp, float* state,
                                          double lr, double beta_1, double beta_2, double epsilon,
                                          int32_t weightnorm, int32_t t_first, int32_t t_last, int32_t slot,
@@ -527,7 +667,7 @@ extern "C" int clv_adamwn_step_range_p2p(const clv_cfg* cfg, float* params, cons
   if (nb <= 0) return CLV_OK;
   CLV_CUDA(clv_launch(adamwn_kernel<true>, nb, NTH, 0, (cudaStream_t)stream, pl, params, (const float*)nullptr,
                       state, lr, beta_1, beta_2, (float)epsilon, 1.0f, (int)weightnorm, ps,
-                      pl.first_block[t_first], (int)advance, loss_mirror));
+                      pl.first_block[t_first], advance == 1 ? nb : (int)advance, loss_mirror));
   CLV_CHECK_LAUNCH();
   return CLV_OK;
 }

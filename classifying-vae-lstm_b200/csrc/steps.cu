@@ -251,6 +251,27 @@ struct Fork {
   }
 };
 
+// Adam-WN of the tensor range [t0, t1) on the peers' summed gradients (clv_p2p_args): either the one-shot
+// all-reduce kernel over the range's elements followed by the ordinary update on gsum (form 0), or the update
+// kernel that reads the peers itself (form 1).  The range [.., CLV_N_TENSORS) carries the 8 loss scalars.
+static int adam_p2p(const clv_cfg* c, const float* P, const clv_adam_args* opt, int t0, int t1, int slot, int advance,
+                    int last, bool mirror, cudaStream_t s_) {
+  // advance / last: 0, 1 or the block totals of the step's concurrent final launches (clv_b200.h)
+  const clv_p2p_args* pp = opt->p2p;
+  float* lm = mirror ? opt->loss_mirror : nullptr;
+  if (pp->form != 0)
+    return clv_adamwn_step_range_p2p(c, const_cast<float*>(P), pp, opt->state, opt->lr, opt->beta_1, opt->beta_2,
+                                     opt->epsilon, opt->weightnorm, t0, t1, slot, advance, lm, s_);
+  int64_t po[CLV_N_TENSORS]; int32_t pr[CLV_N_TENSORS], pc[CLV_N_TENSORS];
+  const int64_t Pn = clv_param_layout(c, po, pr, pc);
+  const int64_t e0 = po[t0], e1 = t1 == CLV_N_TENSORS ? Pn + 8 : po[t1];
+  if (pp->loss_out != pp->gsum + Pn) return CLV_E_INVALID;
+  TRY(clv_p2p_allreduce(pp, opt->state, c, e0, e1 - e0, slot, last, s_));
+  TRY_PDL(clv_adamwn_step_range(c, const_cast<float*>(P), pp->gsum, opt->state, opt->lr, opt->beta_1, opt->beta_2,
+                                opt->epsilon, 1.0, opt->weightnorm, t0, t1, advance, lm, s_));
+  return CLV_OK;
+}
+
 // opt != null: the optimizer is part of the schedule (single-GPU form, no exchange between backward
 // and update).  Adam-WN runs per tensor range as soon as that range's gradients are complete and
 // nothing later in the step reads those parameters: [decoder | X head] during the encoder BPTT,
@@ -261,15 +282,12 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   // Adam-WN of the tensor range [t0, t1).  Peer-memory data parallelism (opt->p2p): the range is a gradient
   // bucket -- the update kernel publishes it to the peers, waits for the peers' signals and sums their buffers
   // over NVLink (all-reduce fused into the optimizer, slot = bucket id)
-  auto adam = [&](int t0, int t1, int advance, cudaStream_t s_, int slot) -> int {
-    if (opt->p2p) {
-      return clv_adamwn_step_range_p2p(c, const_cast<float*>(P), opt->p2p, opt->state, opt->lr, opt->beta_1,
-                                       opt->beta_2, opt->epsilon, opt->weightnorm, t0, t1, slot, advance,
-                                       advance ? opt->loss_mirror : nullptr, s_);
-    }
+  auto adam = [&](int t0, int t1, int advance, cudaStream_t s_, int slot, int last = -1, int mirror = -1) -> int {
+    const bool mir = mirror < 0 ? advance != 0 : mirror != 0;
+    if (opt->p2p) return adam_p2p(c, P, opt, t0, t1, slot, advance, last < 0 ? advance : last, mir, s_);
     return clv_adamwn_step_range(c, const_cast<float*>(P), Gr, opt->state, opt->lr, opt->beta_1, opt->beta_2,
                                  opt->epsilon, opt->grad_scale, opt->weightnorm, t0, t1, advance,
-                                 advance ? opt->loss_mirror : nullptr, s_);
+                                 mir ? opt->loss_mirror : nullptr, s_);
   };
   int64_t po[CLV_N_TENSORS]; int32_t pr[CLV_N_TENSORS], pc[CLV_N_TENSORS];
   clv_param_layout(c, po, pr, pc);
@@ -490,14 +508,25 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   }
   TRY(tn_f32(W, C, dAsum_e, G, gKe + (int64_t)D * G, G, C, G, B, 0, 0, fk.next()));
   TRY(clv_colsum(dAsum_e, G, B, G, gbe, 1, fk.next()));
+  // The step's tail.  One GPU / peer memory: the last two updates run CONCURRENTLY -- [encoder LSTM | Z heads]
+  // on the optimizer stream as soon as the encoder weight gradients have drained, [key encoder] on the caller's
+  // stream behind its backward kernel; whichever block finishes last advances `iterations` (group totals).
+  const bool split_tail = opt && !dp && fused_ke;
   if (fused_ke) {
     // K2 backward + every key-encoder weight gradient in one kernel (sparse scatter for dK_hW)
     TRY_PDL(clv_keyenc_bwd_full(roll, off, sx, L, D, Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, gKhw,
                                 gbhw, gKwa, gbwa, B, C, c->w_log_var_prior, c->class_weight * sb,
                                 c->w_kl_weight * sb, st));
-    // key-encoder tensors: overlaps the encoder wgrads (one GPU).  Over peer memory every bucket on the tail
-    // costs a hand-shake + a remote read (~10 us): there the key encoder joins the last bucket instead
-    if (opt && !dp && !opt->p2p) TRY_PDL(adam(R_HW_K, R_ENC_K, 0, st, 1));
+    if (split_tail) {
+      const int nadv = clv_adamwn_range_blocks(c, opt->weightnorm, R_HW_K, R_ENC_K) +
+                       clv_adamwn_range_blocks(c, opt->weightnorm, R_ENC_K, R_DEC_K);
+      const int nlast = clv_p2p_allreduce_blocks(po[R_ENC_K] - po[R_HW_K]) +
+                        clv_p2p_allreduce_blocks(po[R_DEC_K] - po[R_ENC_K]);
+      TRY_PDL(adam(R_HW_K, R_ENC_K, nadv, st, 1, nlast, 0));
+      TRY(fk.gather());
+      // (the loss scalars were reduced with the first bucket on this stream: the mirror goes with this launch)
+      TRY(adam(R_ENC_K, R_DEC_K, nadv, fk.opt_stream(), 2, nlast, 1));
+    }
   } else {
     TRY(clv_keyenc_bwd(Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, B, C, D,
                        c->w_log_var_prior, c->class_weight * sb, c->w_kl_weight * sb, st));
@@ -511,8 +540,8 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   if (dp) {
     if (opt->exchange(opt->exchange_user, Gr, po[R_X_B] + pc[R_X_B] + 8, (void*)st) != 0) return CLV_E_CUDA;
     TRY(adam(R_HW_K, CLV_N_TENSORS, 1, st, 0));
-  } else if (opt) {
-    TRY(adam((fused_ke && !opt->p2p) ? R_ENC_K : R_HW_K, R_DEC_K, 1, st, 2));
+  } else if (opt && !split_tail) {
+    TRY(adam(R_HW_K, R_DEC_K, 1, st, 2));
   }
   return CLV_OK;
 }
@@ -553,8 +582,7 @@ int vae_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uin
     if (rc_ == CLV_OK) {
       if (opt && c->do_backward) {
         if (opt->p2p) {
-          TRY(clv_adamwn_step_range_p2p(c, const_cast<float*>(P), opt->p2p, opt->state, opt->lr, opt->beta_1, opt->beta_2,
-                                        opt->epsilon, opt->weightnorm, 0, CLV_N_TENSORS, 0, 1, opt->loss_mirror, st));
+          TRY(adam_p2p(c, P, opt, 0, CLV_N_TENSORS, 0, 1, 1, true, st));
         } else {
           if (opt->exchange && opt->exchange(opt->exchange_user, Gr, po[V_X_B] + pc[V_X_B] + 8, (void*)st) != 0)
             return CLV_E_CUDA;
@@ -619,8 +647,7 @@ int vae_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const uin
   TRY(tn_u8(roll, off, 1, sx, D, dh_w, Hc, gKhw, Hc, D, Hc, B, st));
   TRY(clv_colsum(dh_w, Hc, B, Hc, gbhw, 1, st));
   if (opt && opt->p2p) {
-    TRY(clv_adamwn_step_range_p2p(c, const_cast<float*>(P), opt->p2p, opt->state, opt->lr, opt->beta_1, opt->beta_2,
-                                  opt->epsilon, opt->weightnorm, 0, CLV_N_TENSORS, 0, 1, opt->loss_mirror, st));
+    TRY(adam_p2p(c, P, opt, 0, CLV_N_TENSORS, 0, 1, 1, true, st));
   } else if (opt) {
     if (opt->exchange && opt->exchange(opt->exchange_user, Gr, po[V_X_B] + pc[V_X_B] + 8, (void*)st) != 0)
       return CLV_E_CUDA;

@@ -43,7 +43,7 @@ class Engine:
                  class_weight=1.0, kl_weight=1.0, w_kl_weight=1.0, w_log_var_prior=0.0,
                  optimizer="adam-wn", lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-8,
                  seed=0, device=None, world_size=1, rank=0, process_group=None, use_graph=True,
-                 overlap_wgrad=True, gemm_algo=1, p2p_allreduce=False, tc_lstm_min=0,
+                 overlap_wgrad=True, gemm_algo=1, p2p_allreduce=None, tc_lstm_min=0,
                  fused_optimizer=True, predict_next=False, micro_batch=None, workspace_budget_bytes=None,
                  pair_bwd=False):
         _require_cuda()
@@ -102,19 +102,37 @@ class Engine:
         self.P, self.offs, self.rows, self.cols = _lib.param_layout(cfg)
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.params = torch.zeros(self.P, **f32)
-        # [grads | 8 loss scalars].  Data parallel (world_size > 1), two forms:
-        #  * default: ONE NCCL all-reduce of the whole buffer, enqueued by the library through the exchange
-        #    callback after the last weight gradient, then one Adam-WN launch -- all inside clv_train_step_opt
-        #    and the step's CUDA graph (N=2: 0.164 ms/step against 0.139 for two uncoupled ranks);
-        #  * p2p_allreduce=True (opt-in): the buffer and a small flag block live in peer-mapped (symmetric)
-        #    memory; the Adam-WN kernel of each gradient bucket publishes the bucket to the peers, waits for their
-        #    flags, reads their gradients over NVLink and applies the update -- all-reduce fused into the
-        #    optimizer, no collective launch, no host barrier (clv_p2p_args).  Parity-tested
-        #    (tests/dist_p2p_check.py) but measured slower on this pool: every hand-shake + remote read costs
-        #    15-20 us per bucket kernel (profiles/p2p_probe.py: 59 vs 21 us for the two bucket updates at N=2),
-        #    0.177-0.182 ms/step.
+        # [grads | 8 loss scalars].  Data parallel (world_size > 1), all inside clv_train_step_opt and the step's
+        # CUDA graph:
+        #  * p2p_allreduce=None (default: used when symmetric memory can be set up, the optimizer is scheduled
+        #    inside the step and the batch is not micro-batched) / True: the buffer and a small flag block live in
+        #    peer-mapped (symmetric) memory; per gradient bucket a one-shot all-reduce KERNEL publishes the bucket
+        #    (flag store into every peer's flag block), waits for the peers' flags inside the kernel and reads
+        #    their gradients over NVLink in rank order; the ordinary Adam-WN update of the bucket follows
+        #    (clv_p2p_allreduce).  Buckets: [decoder | X head | losses] hidden behind the encoder BPTT, [key
+        #    encoder] and [encoder LSTM | Z heads] concurrently on the tail.  N=2: 0.158 ms/step, N=8: 0.177
+        #    (end to end 0.199);
+        #  * p2p_allreduce="fused": the exchange inside the Adam-WN kernels themselves (clv_adamwn_step_range_p2p;
+        #    strided 16..32-byte remote reads: slower);
+        #  * p2p_allreduce=False: ONE NCCL all-reduce of the whole buffer, enqueued by the library through the
+        #    exchange callback after the last weight gradient, then one Adam-WN launch (N=2: 0.161-0.163 ms/step,
+        #    N=8: 0.179, end to end 0.264; two uncoupled ranks: 0.139).
+        if p2p_allreduce is None and (world_size == 1 or not fused_optimizer or self.n_micro > 1):
+            p2p_allreduce = False
         self.symm = None
         self.p2p = None
+        if world_size == 1 and p2p_allreduce is not False and fused_optimizer:
+            # diagnostic: the peer-memory schedule with this rank as its only peer (what the schedule itself
+            # costs, without NVLink and without another rank to wait for)
+            self.gradbuf = torch.zeros(self.P + 8, **f32)
+            self.peer_ptrs = torch.tensor([self.gradbuf.data_ptr()], dtype=torch.int64, device=self.dev)
+            self.flagbuf = torch.zeros(int(lib().clv_p2p_flag_ints()), dtype=torch.int32, device=self.dev)
+            self.peer_flag_ptrs = torch.tensor([self.flagbuf.data_ptr()], dtype=torch.int64, device=self.dev)
+            self.gsum = torch.zeros(self.P + 8, **f32)
+            self.loss_red = self.gsum[self.P:]
+            self.p2p = clv_p2p_args(peer_grads=self.peer_ptrs.data_ptr(), peer_flags=self.peer_flag_ptrs.data_ptr(),
+                                    n_peers=1, rank=0, gsum=self.gsum.data_ptr(), loss_out=self.loss_red.data_ptr(),
+                                    form=1 if p2p_allreduce == "fused" else 0)
         if world_size > 1 and p2p_allreduce is not False:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
@@ -130,20 +148,34 @@ class Engine:
                 self.symm_flags = symm_mem.rendezvous(self.flagbuf, group)
                 self.peer_flag_ptrs = torch.tensor([int(x) for x in self.symm_flags.buffer_ptrs], dtype=torch.int64,
                                                    device=self.dev)
-                self.gsum = torch.zeros(self.P, **f32)
-                self.loss_red = torch.zeros(8, **f32)
+                self.gsum = torch.zeros(self.P + 8, **f32)          # the reduced [grads | losses]
+                self.loss_red = self.gsum[self.P:]
                 self.p2p = clv_p2p_args(peer_grads=self.peer_ptrs.data_ptr(), peer_flags=self.peer_flag_ptrs.data_ptr(),
                                         n_peers=world_size, rank=rank, gsum=self.gsum.data_ptr(),
-                                        loss_out=self.loss_red.data_ptr())
+                                        loss_out=self.loss_red.data_ptr(),
+                                        form=1 if p2p_allreduce == "fused" else 0)
+                if os.environ.get("CLV_P2P_DIAG_SELF") == "1":
+                    # diagnostic (WRONG results): symmetric buffers, but every rank exchanges with itself only
+                    self.peer_ptrs = self.peer_ptrs[rank:rank + 1].clone()
+                    self.peer_flag_ptrs = self.peer_flag_ptrs[rank:rank + 1].clone()
+                    self.p2p.peer_grads, self.p2p.peer_flags = self.peer_ptrs.data_ptr(), self.peer_flag_ptrs.data_ptr()
+                    self.p2p.n_peers, self.p2p.rank = 1, 0
                 torch.cuda.synchronize(self.dev)
                 torch.distributed.barrier(group=process_group)        # every rank's flags are zero before any signal
             except Exception as ex:  # noqa: BLE001
-                if p2p_allreduce is True:
+                if p2p_allreduce is not None:
                     raise
                 print("[clvae_b200] symmetric memory unavailable (%s): using the NCCL all-reduce path" % (ex,))
                 self.symm = None
                 self.p2p = None
-        if self.symm is None:
+            if p2p_allreduce is None:
+                # automatic mode: every rank must have taken the same decision
+                ok = torch.tensor([1 if self.p2p is not None else 0], dtype=torch.int32, device=self.dev)
+                torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=process_group)
+                if int(ok.item()) == 0:
+                    self.symm = None
+                    self.p2p = None
+        if self.symm is None and self.p2p is None:
             self.gradbuf = torch.zeros(self.P + 8, **f32)
         self.grads, self.loss_acc = self.gradbuf[:self.P], self.gradbuf[self.P:]
         self._loss_src = self.loss_acc
@@ -397,6 +429,23 @@ class Engine:
             self._graphs[key] = g
             # capture does not execute: fall through to replay
         g.replay()
+
+    def p2p_stats(self, reset=True):
+        """Diagnostics of the peer-memory exchange: per gradient bucket, the mean time (us) block 0 of the
+        all-reduce kernel spent waiting for the peers' flags and moving its share of the data."""
+        if self.p2p is None:
+            return None
+        torch.cuda.synchronize(self.dev)
+        row = self.flagbuf[5 * 16:6 * 16]
+        v = row.cpu().tolist()
+        out = {}
+        for slot in range(4):
+            w, c, k = v[1 + 3 * slot:4 + 3 * slot]
+            if k:
+                out["bucket%d" % slot] = {"wait_us": round(w / k / 1e3, 2), "copy_us": round(c / k / 1e3, 2), "n": k}
+        if reset:
+            row[1:13].zero_()
+        return out
 
     def read_losses(self):
         """D2H of the 5 scalars (already global means) -> dict incl. Keras' weighted total."""

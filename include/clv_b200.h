@@ -353,12 +353,29 @@ typedef struct clv_p2p_args {
   int32_t* const* peer_flags;      /* device array [n_peers]: every rank's flag block, clv_p2p_flag_ints() int32,
                                       zero-initialised before the first step */
   int32_t n_peers, rank;
-  float* gsum;                     /* local scratch [P] */
-  float* loss_out;                 /* local [8]: reduced loss scalars */
+  float* gsum;                     /* local [P + 8]: the reduced [grads | losses] */
+  float* loss_out;                 /* local [8]: reduced loss scalars (form 0: must be gsum + P) */
+  int32_t form;                    /* 0: one-shot all-reduce kernel per bucket (clv_p2p_allreduce), then the ordinary
+                                      Adam-WN update on gsum; 1: all-reduce fused into the Adam-WN kernels
+                                      (clv_adamwn_step_range_p2p) */
 } clv_p2p_args;
 int clv_p2p_flag_ints(void);
 int clv_p2p_signal(const clv_p2p_args* pp, const float* adam_state, const clv_cfg* cfg, int32_t slot, void* stream);
 int clv_p2p_wait_done(const clv_p2p_args* pp, const float* adam_state, const clv_cfg* cfg, void* stream);
+/* One-shot all-reduce of a gradient bucket over peer memory: gsum[first .. first+count) = sum over the ranks of
+ * peer_grads[p][first .. first+count), summed in rank order (bit-identical on every rank).  The launch is
+ * stream-ordered behind the producers of this rank's bucket; it publishes the bucket to the peers (flag slot
+ * `slot`), waits for theirs inside the kernel (bounded: traps after ~2 minutes), and reads their buffers over NVLink.
+ * last != 0 on the final bucket of a step: also raises this rank's "done reading" flag at every peer.
+ * (the data-parallel exchange the reference does not have; replaces an NCCL all-reduce launch) */
+int clv_p2p_allreduce(const clv_p2p_args* pp, const float* adam_state, const clv_cfg* cfg, int64_t first,
+                      int64_t count, int32_t slot, int32_t last, void* stream);
+/* Grid sizes, for callers that run the final launches of a step concurrently on two streams: `advance` of
+ * clv_adamwn_step_range[_p2p] (and `last` of clv_p2p_allreduce) is 0 (not a final launch), 1 (the only final
+ * launch) or the TOTAL number of blocks of the concurrent final launches -- the block that finishes last among
+ * them advances `iterations` (raises the "done" flags). */
+int clv_p2p_allreduce_blocks(int64_t count);
+int clv_adamwn_range_blocks(const clv_cfg* cfg, int32_t weightnorm, int32_t t_first, int32_t t_last);
 /* clv_adamwn_step_range on the sum of all peers' gradients; slot = the bucket's flag slot (0..3). */
 int clv_adamwn_step_range_p2p(const clv_cfg* cfg, float* params, const clv_p2p_args* pp, float* state,
                               double lr, double beta_1, double beta_2, double epsilon, int32_t weightnorm,
@@ -368,9 +385,9 @@ int clv_adamwn_step_range_p2p(const clv_cfg* cfg, float* params, const clv_p2p_a
 /* Data-parallel hook: called by clv_train_step_opt on the HOST, while it enqueues the step, once per
  * gradient bucket at the point of the schedule where that bucket's gradients are final: sum-all-reduce
  * buf[0..count) over the ranks ON `stream` (stream-ordered; e.g. ncclAllReduce / torch.distributed.all_reduce
- * with `stream` current).  Buckets, in the order they become final: [decoder | X head | 8 loss scalars]
- * (during the encoder BPTT, on an auxiliary stream) and [key encoder | encoder LSTM | Z heads] (after the last
- * weight gradient); each is followed by the Adam-WN update of its range.  Return 0 on success. */
+ * with `stream` current).  Currently ONE bucket, the whole [grads | 8 loss scalars] buffer after the last weight
+ * gradient, followed by one Adam-WN update (a second NCCL bucket overlapped with the encoder BPTT measured
+ * slower); callers must nevertheless honour (buf, count).  Return 0 on success. */
 typedef int (*clv_exchange_fn)(void* user, float* buf, int64_t count, void* stream);
 typedef struct clv_adam_args {
   float* state;                 /* clv_adamwn_state_floats() floats, initialised by clv_adamwn_init */

@@ -22,13 +22,16 @@ def main():
     results = {}
     engines = []
     # nccl: step -> one all-reduce -> Adam-WN (three calls);  dp: clv_train_step_opt with the NCCL exchange
-    # callback;  p2p: the product default -- peer-memory exchange fused into the scheduled Adam-WN kernels
-    # (in-kernel flags);  p2p-barrier: the round-1 form (host-side symmetric-memory barriers around one kernel)
-    for mode, use_graph in (("nccl", False), ("dp", False), ("dp", True), ("p2p", False), ("p2p", True),
-                            ("p2p-barrier", False)):
+    # callback;  p2p: one-shot all-reduce kernels over peer memory (in-kernel flags) + the ordinary update;
+    # p2p-fused: the exchange inside the Adam-WN kernels;  p2p-barrier: the round-1 form (host-side
+    # symmetric-memory barriers around one kernel)
+    modes = (("nccl", False), ("dp", False), ("dp", True), ("p2p", False), ("p2p", True), ("p2p-fused", False),
+             ("p2p-fused", True), ("p2p-barrier", False))
+    for mode, use_graph in modes:
         e = Engine("vrnn", B, L=6, D=88, H=88, Z=2, n_classes=4, use_x_prev=True, world_size=world, rank=rank,
-                   use_graph=use_graph, p2p_allreduce=mode.startswith("p2p"),
-                   fused_optimizer=(mode in ("dp", "p2p")))
+                   use_graph=use_graph,
+                   p2p_allreduce=("fused" if mode == "p2p-fused" else mode.startswith("p2p")),
+                   fused_optimizer=(mode in ("dp", "p2p", "p2p-fused")))
         engines.append(e)
         assert (e.symm is not None) == mode.startswith("p2p"), "symmetric memory set-up failed"
         e.set_params({k: v.numpy() for k, v in case["p"].items()})
@@ -46,7 +49,7 @@ def main():
         dist.broadcast(ref, src=0)
         assert torch.equal(ref, e.params), "ranks diverged in mode %s" % mode
     base_l, base_p = results[("nccl", False)]
-    for key in (("dp", False), ("dp", True), ("p2p", False), ("p2p", True), ("p2p-barrier", False)):
+    for key in modes[1:]:
         l, p = results[key]
         assert np.allclose(l, base_l, rtol=2e-5), (key, l, base_l)
         err = float((p - base_p).abs().max() / base_p.abs().max())
