@@ -180,6 +180,13 @@ static int pair_disabled() {
   if (v < 0) { const char* e = getenv("CLV_NO_PAIR"); v = (e && e[0] == '1') ? 1 : 0; }
   return v;
 }
+// profiling aid (profiles/skip_probe.sh): CLV_DIAG_SKIP=<bitmask> drops launches from the B=200 schedule so that
+// differential timing shows which ones are on the critical path.  Results are WRONG with any bit set.
+static int diag_skip() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CLV_DIAG_SKIP"); v = e ? atoi(e) : 0; }
+  return v;
+}
 static int pdl_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("CLV_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -464,7 +471,13 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   }
   TRY(fk.fork());
   const bool tcw = tc && H == 88 && Z <= 8;   // tcgen05 weight gradients
-  if (tcw) {
+  const int dsk = diag_skip();
+  if (dsk & 64) {
+  } else if (tcw) {
+    // (beside the encoder BPTT: 100 weight-gradient CTAs and 100 one-per-SM BPTT CTAs share 148 SMs, which costs
+    //  the critical path 8.6 us -- profiles/skip_probe_r2.txt -- but capping this grid to the 48 free SMs, or
+    //  folding the update that follows into the final launch, measured 1-3 us WORSE: the update chain behind
+    //  this kernel has no slack either)
     TRY(clv_lstm_wgrad_tc(gates_d, roll, off, L, 0, D, h_d, Zs, Z, c->use_x_prev ? gKd : nullptr, gUd,
                           gKd + (int64_t)xo * G, BL, H, fk.next()));
   } else {
@@ -490,7 +503,7 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
                // stay out of this range: the encoder BPTT below still reads their kernels
     TRY(fk.fork());
     TRY(fk.gather());
-    if (!dp) TRY(adam(R_DEC_K, CLV_N_TENSORS, 0, fk.opt_stream(), 0));
+    if (!dp && !(dsk & 32)) TRY(adam(R_DEC_K, CLV_N_TENSORS, 0, fk.opt_stream(), 0));
   }
   if (pairb) {
     // (the encoder BPTT ran inside the wavefront launch above)
@@ -500,31 +513,40 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   else
     TRY_PDL(clv_lstm_bwd_fused(gates_e, Ue, c_e, dh, dAsum_e, Ke_w, C, dW_ext, 1, nullptr, 0, nullptr, B, L, H, st));
   TRY(fk.fork());
-  if (tcw) {
+  if (dsk & 8) {
+  } else if (tcw) {
     TRY(clv_lstm_wgrad_tc(gates_e, roll, off, L, sx, D, h_e, nullptr, 0, gKe, gUe, nullptr, BL, H, fk.next()));
   } else {
     TRY(tn_u8(roll, off, L, sx, D, gates_e, G, gKe, G, D, G, BL, fk.next()));
     TRY(tn_f32(h_e, H, gates_e, G, gUe, G, H, G, BL, -1, L, fk.next()));
   }
-  TRY(tn_f32(W, C, dAsum_e, G, gKe + (int64_t)D * G, G, C, G, B, 0, 0, fk.next()));
-  TRY(clv_colsum(dAsum_e, G, B, G, gbe, 1, fk.next()));
+  if (!(dsk & 16)) {
+    TRY(tn_f32(W, C, dAsum_e, G, gKe + (int64_t)D * G, G, C, G, B, 0, 0, fk.next()));
+    TRY(clv_colsum(dAsum_e, G, B, G, gbe, 1, fk.next()));
+  }
   // The step's tail.  One GPU / peer memory: the last two updates run CONCURRENTLY -- [encoder LSTM | Z heads]
   // on the optimizer stream as soon as the encoder weight gradients have drained, [key encoder] on the caller's
   // stream behind its backward kernel; whichever block finishes last advances `iterations` (group totals).
   const bool split_tail = opt && !dp && fused_ke;
   if (fused_ke) {
     // K2 backward + every key-encoder weight gradient in one kernel (sparse scatter for dK_hW)
+    if (!(dsk & 4))
     TRY_PDL(clv_keyenc_bwd_full(roll, off, sx, L, D, Wargs, eps_w, labels, W, dW_ext, Kwa, hW, dWargs, dhW, gKhw,
                                 gbhw, gKwa, gbwa, B, C, c->w_log_var_prior, c->class_weight * sb,
                                 c->w_kl_weight * sb, st));
-    if (split_tail) {
+    if (split_tail && (dsk & 3)) {
+      // (one of the two final launches dropped: the other advances alone)
+      if (!(dsk & 1)) TRY_PDL(adam(R_HW_K, R_ENC_K, 1, st, 1, 1, 1));
+      TRY(fk.gather());
+      if (!(dsk & 2)) TRY(adam(R_ENC_K, R_DEC_K, 1, fk.opt_stream(), 2, 1, 1));
+    } else if (split_tail) {
       const int nadv = clv_adamwn_range_blocks(c, opt->weightnorm, R_HW_K, R_ENC_K) +
                        clv_adamwn_range_blocks(c, opt->weightnorm, R_ENC_K, R_DEC_K);
       const int nlast = clv_p2p_allreduce_blocks(po[R_ENC_K] - po[R_HW_K]) +
                         clv_p2p_allreduce_blocks(po[R_DEC_K] - po[R_ENC_K]);
       TRY_PDL(adam(R_HW_K, R_ENC_K, nadv, st, 1, nlast, 0));
-      TRY(fk.gather());
       // (the loss scalars were reduced with the first bucket on this stream: the mirror goes with this launch)
+      TRY(fk.gather());
       TRY(adam(R_ENC_K, R_DEC_K, nadv, fk.opt_stream(), 2, nlast, 1));
     }
   } else {
