@@ -187,7 +187,7 @@ def workload_config(n):
                         "D=H=88, C=10, z=2, use_x_prev, adam-wn",
             "global_batch": CFG["B"] * n, "seq_len": CFG["L"], "parallelism": "dp%d" % n,
             "l2": "inputs drawn from a 176 MB resident roll pool (> 126 MB L2), fresh windows every step",
-            "noise": "in-kernel Philox", "graph": "one CUDA graph per step (fwd+bwd, Adam-WN scheduled inside at N=1; all-reduce then Adam-WN at N>1), programmatic dependent launches on the critical path"}
+            "noise": "in-kernel Philox", "graph": "one CUDA graph per step (fwd+bwd, Adam-WN per tensor range scheduled inside; N>1: per gradient bucket a one-shot all-reduce kernel over NVLink peer memory before its Adam-WN range, or NCCL with --p2p 0), programmatic dependent launches on the critical path"}
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -626,6 +626,9 @@ def main():
         if dp_parity is not None:
             line["dp_parity_max_rel_err"] = dp_parity
         line["host_enqueue_ms_per_step"] = round(host_enqueue_ms, 4)
+        if world > 1:
+            line["exchange"] = ("one-shot all-reduce kernels over peer memory (clv_p2p_allreduce)" if (e.p2p is not None and e.p2p.form == 0)
+                                else "fused into Adam-WN over peer memory" if e.p2p is not None else "NCCL all-reduce in the step graph")
         if p2p_stats:
             line["p2p_exchange_rank0_us"] = p2p_stats
         if B != CFG["B"] or L != CFG["L"]:
