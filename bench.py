@@ -627,7 +627,9 @@ def main():
             line["dp_parity_max_rel_err"] = dp_parity
         line["host_enqueue_ms_per_step"] = round(host_enqueue_ms, 4)
         if world > 1:
-            line["exchange"] = ("one-shot all-reduce kernels over peer memory (clv_p2p_allreduce)" if (e.p2p is not None and e.p2p.form == 0)
+            line["exchange"] = ("two-shot all-reduce kernels through the NVSwitch multicast mapping (clv_p2p_allreduce, multimem)"
+                                if (e.p2p is not None and e.p2p.form == 0 and e.p2p.mc_grads)
+                                else "one-shot all-reduce kernels over peer memory (clv_p2p_allreduce)" if (e.p2p is not None and e.p2p.form == 0)
                                 else "fused into Adam-WN over peer memory" if e.p2p is not None else "NCCL all-reduce in the step graph")
         if p2p_stats:
             line["p2p_exchange_rank0_us"] = p2p_stats

@@ -120,7 +120,8 @@ class clv_adam_args(C.Structure):
 class clv_p2p_args(C.Structure):
     """include/clv_b200.h: clv_p2p_args (peer-memory data parallelism, hand-shake inside the kernels)."""
     _fields_ = [("peer_grads", C.c_void_p), ("peer_flags", C.c_void_p), ("n_peers", C.c_int32), ("rank", C.c_int32),
-                ("gsum", C.c_void_p), ("loss_out", C.c_void_p), ("form", C.c_int32)]
+                ("gsum", C.c_void_p), ("loss_out", C.c_void_p), ("form", C.c_int32),
+                ("mc_grads", C.c_void_p), ("mc_gsum", C.c_void_p)]
 
 
 # include/clv_b200.h: clv_exchange_fn(user, buf, count, stream) -> int

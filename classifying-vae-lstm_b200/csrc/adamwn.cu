@@ -39,9 +39,11 @@ struct PeerSet {
 // finished writing; done[src] = step number after which `src` no longer reads anyone's gradients
 constexpr int P2P_MAXR = 16, P2P_SLOTS = 4;
 __device__ __forceinline__ int32_t* flag_ready(int32_t* f, int slot, int src) { return f + slot * P2P_MAXR + src; }
-__device__ __forceinline__ int32_t* flag_done(int32_t* f, int src) { return f + P2P_SLOTS * P2P_MAXR + src; }
+// landed[slot][src] = step number for which rank `src` has delivered its slice of bucket `slot` (two-shot form)
+__device__ __forceinline__ int32_t* flag_landed(int32_t* f, int slot, int src) { return f + (P2P_SLOTS + slot) * P2P_MAXR + src; }
+__device__ __forceinline__ int32_t* flag_done(int32_t* f, int src) { return f + 2 * P2P_SLOTS * P2P_MAXR + src; }
 // last row: local counters (never written by a peer)
-__device__ __forceinline__ int32_t* flag_local(int32_t* f, int i) { return f + (P2P_SLOTS + 1) * P2P_MAXR + i; }
+__device__ __forceinline__ int32_t* flag_local(int32_t* f, int i) { return f + (2 * P2P_SLOTS + 1) * P2P_MAXR + i; }
 __device__ __forceinline__ int ld_acquire_sys(const int32_t* p) {
   int v;
   asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -473,6 +475,107 @@ __global__ void __launch_bounds__(AR_NTH) p2p_allreduce_kernel(const float* cons
   }
 }
 
+// ---- two-shot all-reduce through the NVSwitch multicast mapping (NVLS); opt-in (clv_p2p_args.mc_*) ------------
+// The one-shot kernel above makes every rank read all N-1 peers' buckets (N=8: copy 11-13 us per bucket).  Here
+// rank r owns 1/N of the bucket: one multimem.ld_reduce per 16 bytes fetches that chunk from EVERY rank's
+// gradient buffer and adds it in the switch, one multimem.st writes the sum into every rank's gsum -- a rank
+// moves 1/N of a bucket in and out, whatever N is.  Every element has exactly one reducer, so the replicas stay
+// bit-identical.  Two hand-shakes: "bucket ready" before the reads (as above, fence-free) and "slice landed"
+// after the writes: each block fences its multicast stores at system scope, the block that finishes last tells
+// every peer, and stays until every peer's slice has landed here -- so the kernel completes only when this
+// rank's gsum is whole and the Adam-WN update behind it needs no further check.
+// Measured: 7-9 us per bucket whatever N (one-shot: 4.5 us at N=2, 11-13 us at N=8); step time equal at N=8
+// (0.178 vs 0.177 ms), worse at N=2 (0.176 vs 0.158) -- the two fences and the second hand-shake cost what the
+// smaller transfer saves, so the one-shot form stays the default.
+__device__ __forceinline__ float4 multimem_ld_reduce_f4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_f4(float* mc, const float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float multimem_ld_reduce_f1(const float* mc) {
+  float v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_f1(float* mc, const float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(AR_NTH) p2p_allreduce_mc_kernel(const float* __restrict__ mc_grads,
+                                                                  float* __restrict__ mc_gsum,
+                                                                  int32_t* const* __restrict__ flags, const int n,
+                                                                  const int rank, const int slot, const int* iter,
+                                                                  const int64_t e0, const int64_t cnt, const int last) {
+  pdl_wait();
+  const int t = *iter + 1;
+  const int tid = threadIdx.x;
+  const bool diag = blockIdx.x == 0 && tid == 0;
+  unsigned long long tg0 = 0, tg1 = 0;
+  if (diag) tg0 = globaltimer_ns();
+  if (blockIdx.x == 0 && tid < n) st_relaxed_sys(flag_ready(flags[tid], slot, rank), t);
+  if (tid < n) {
+    const volatile int32_t* f = flag_ready(flags[rank], slot, tid);
+    const long long t0 = clock64();
+    while (*f < t) {
+      if (clock64() - t0 > 240000000000ll) __trap();
+    }
+  }
+  __syncthreads();
+  if (diag) tg1 = globaltimer_ns();
+  pdl_launch_dependents();
+  const int64_t head = min(cnt, (int64_t)((4 - (e0 & 3)) & 3));
+  const int64_t nv = (cnt - head) >> 2;
+  const int64_t tail0 = head + (nv << 2);
+  const int64_t lo = nv * rank / n, hi = nv * (rank + 1) / n;      // this rank's 16-byte chunks
+  const int64_t gt = (int64_t)blockIdx.x * AR_NTH + tid, gs = (int64_t)gridDim.x * AR_NTH;
+  for (int64_t i = lo + gt; i < hi; i += gs) {
+    const int64_t e = e0 + head + (i << 2);
+    multimem_st_f4(mc_gsum + e, multimem_ld_reduce_f4(mc_grads + e));
+  }
+  if (rank == 0 && gt < head + (cnt - tail0)) {                      // unaligned ends: rank 0, one float each
+    const int64_t e = e0 + (gt < head ? gt : tail0 + (gt - head));
+    multimem_st_f1(mc_gsum + e, multimem_ld_reduce_f1(mc_grads + e));
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();                 // this block's multicast stores are performed everywhere
+    int32_t* cl = flag_local(flags[rank], 13 + slot);
+    const bool last_block = atomicAdd(cl, 1) == (int)gridDim.x - 1;
+    if (diag && slot < 3) {
+      int32_t* d = flag_local(flags[rank], 1 + 3 * slot);
+      atomicAdd(d, (int)(tg1 - tg0));
+      atomicAdd(d + 1, (int)(globaltimer_ns() - tg1));
+      atomicAdd(d + 2, 1);
+    }
+    if (last_block) {
+      *cl = 0;
+      __threadfence_system();
+      for (int p = 0; p < n; ++p) st_relaxed_sys(flag_landed(flags[p], slot, rank), t);
+      const long long t0 = clock64();
+      for (int p = 0; p < n; ++p) {
+        const volatile int32_t* f = flag_landed(flags[rank], slot, p);
+        while (*f < t) {
+          if (clock64() - t0 > 240000000000ll) __trap();
+        }
+      }
+      __threadfence_system();               // (the peers' slices are in this rank's memory before the kernel ends)
+    }
+    if (last) {
+      // every read of the peers' gradients by this block has returned (its value went into a store)
+      int32_t* cntr = flag_local(flags[rank], 0);
+      if (atomicAdd(cntr, 1) == last - 1) {
+        *cntr = 0;
+        for (int p = 0; p < n; ++p) st_relaxed_sys(flag_done(flags[p], rank), t);
+      }
+    }
+  }
+}
+
 // bucket `slot` of this rank's gradient buffer is final: publish the step number to every peer's flag block
 __global__ void p2p_signal_kernel(int32_t* const* flags, const int n, const int rank, const int slot,
                                   const int* iter) {
@@ -580,7 +683,7 @@ extern "C" int clv_adamwn_step_p2p(const clv_cfg* cfg, float* params, const floa
 }
 
 // ---- peer-memory data parallelism with the hand-shake inside the kernels (clv_p2p_args) ------------------
-extern "C" int clv_p2p_flag_ints(void) { return (P2P_SLOTS + 2) * P2P_MAXR; }
+extern "C" int clv_p2p_flag_ints(void) { return (2 * P2P_SLOTS + 2) * P2P_MAXR; }
 
 extern "C" int clv_p2p_signal(const clv_p2p_args* pp, const float* state, const clv_cfg* cfg, int32_t slot,
                               void* stream) {
@@ -636,6 +739,12 @@ extern "C" int clv_p2p_allreduce(const clv_p2p_args* pp, const float* state, con
   const int nb = clv_p2p_allreduce_blocks(count);
   const int n = pp->n_peers;
   if (last == 1) last = nb;
+  if (pp->mc_grads && pp->mc_gsum && slot < 3) {
+    CLV_CUDA(clv_launch(p2p_allreduce_mc_kernel, nb, AR_NTH, 0, (cudaStream_t)stream, pp->mc_grads, pp->mc_gsum,
+                        pp->peer_flags, n, (int)pp->rank, (int)slot, iter, first, count, (int)last));
+    CLV_CHECK_LAUNCH();
+    return CLV_OK;
+  }
 #define CLV_AR(NP)                                                                                             \
   CLV_CUDA(clv_launch(p2p_allreduce_kernel<NP>, nb, AR_NTH, 0, (cudaStream_t)stream, pp->peer_grads,            \
                       pp->peer_flags, n, (int)pp->rank, (int)slot, iter, pp->gsum, first, count, (int)last))

@@ -358,6 +358,10 @@ typedef struct clv_p2p_args {
   int32_t form;                    /* 0: one-shot all-reduce kernel per bucket (clv_p2p_allreduce), then the ordinary
                                       Adam-WN update on gsum; 1: all-reduce fused into the Adam-WN kernels
                                       (clv_adamwn_step_range_p2p) */
+  const float* mc_grads;           /* nullable: NVSwitch multicast address of the ranks' [grads | losses] buffers */
+  float* mc_gsum;                  /* nullable: multicast address of the ranks' gsum buffers (gsum then lives in
+                                      symmetric memory too).  Both set: clv_p2p_allreduce runs the two-shot form
+                                      (multimem.ld_reduce of this rank's 1/N slice, multimem.st of the sum to all) */
 } clv_p2p_args;
 int clv_p2p_flag_ints(void);
 int clv_p2p_signal(const clv_p2p_args* pp, const float* adam_state, const clv_cfg* cfg, int32_t slot, void* stream);

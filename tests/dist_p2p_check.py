@@ -25,15 +25,19 @@ def main():
     # callback;  p2p: one-shot all-reduce kernels over peer memory (in-kernel flags) + the ordinary update;
     # p2p-fused: the exchange inside the Adam-WN kernels;  p2p-barrier: the round-1 form (host-side
     # symmetric-memory barriers around one kernel)
-    modes = (("nccl", False), ("dp", False), ("dp", True), ("p2p", False), ("p2p", True), ("p2p-fused", False),
-             ("p2p-fused", True), ("p2p-barrier", False))
+    # p2p-mc: the two-shot form through the NVSwitch multicast mapping (multimem.ld_reduce / multimem.st)
+    modes = (("nccl", False), ("dp", False), ("dp", True), ("p2p", False), ("p2p", True), ("p2p-mc", False),
+             ("p2p-mc", True), ("p2p-fused", False), ("p2p-fused", True), ("p2p-barrier", False))
     for mode, use_graph in modes:
+        os.environ["CLV_P2P_MC"] = "1" if mode == "p2p-mc" else "0"
         e = Engine("vrnn", B, L=6, D=88, H=88, Z=2, n_classes=4, use_x_prev=True, world_size=world, rank=rank,
                    use_graph=use_graph,
                    p2p_allreduce=("fused" if mode == "p2p-fused" else mode.startswith("p2p")),
                    fused_optimizer=(mode in ("dp", "p2p", "p2p-fused")))
         engines.append(e)
         assert (e.symm is not None) == mode.startswith("p2p"), "symmetric memory set-up failed"
+        if mode == "p2p-mc":
+            assert e.p2p.mc_grads and e.p2p.mc_gsum, "no multicast mapping on this system"
         e.set_params({k: v.numpy() for k, v in case["p"].items()})
         e.stage_windows(torch.tensor(case["win"][sl]).cuda(), torch.tensor(case["labels"][sl]).cuda())
         e.eps_w.copy_(torch.tensor(case["eps_w"][sl], dtype=torch.float32).reshape(-1))
