@@ -24,6 +24,9 @@ extern "C" int clv_lstm_fwd_tc(float*, const float*, const float*, const float*,
 extern "C" int clv_xhead_fwd_bwd(const float*, const float*, const float*, const uint8_t*, const int32_t*,
                                  int32_t, int32_t, float*, float*, float*, int64_t, int32_t, int32_t,
                                  float, int32_t, void*);
+extern "C" int64_t clv_xhead_tc_scratch_bytes(void);
+extern "C" int clv_xhead_tc(const float*, const float*, const float*, const uint8_t*, const int32_t*, int32_t,
+                            int32_t, float*, float*, float*, void*, int64_t, int32_t, int32_t, float, void*);
 extern "C" int clv_keyenc_fwd(const uint8_t*, const int32_t*, int32_t, int32_t, int32_t, const float*,
                               const float*, const float*, const float*, float*, const int32_t*, float*,
                               float*, float*, float*, int32_t, int32_t, float, float, int32_t, uint64_t,
@@ -97,6 +100,7 @@ Ws carve(const clv_cfg* c) {
     w.add("dW_ext", B * C); w.add("dWargs", B * 2 * C1); w.add("dhW", B * D);
     w.add("wimg_e", clv_inproj_tc_scratch_bytes() / 4); w.add("wimg_d", clv_inproj_tc_scratch_bytes() / 4);
     w.add("uimg_e", clv_lstm_fwd_tc_scratch_bytes() / 4); w.add("uimg_d", clv_lstm_fwd_tc_scratch_bytes() / 4);
+    w.add("ximg", clv_xhead_tc_scratch_bytes() / 4);
   } else {
     const int64_t Hc = c->Hc;
     w.add("h_w", B * Hc); w.add("Wargs", B * 2 * C1); w.add("W", B * C);
@@ -173,6 +177,12 @@ int tn_u8(const uint8_t* roll, const int32_t* off, int grp, int shift, int64_t l
 static int vae_fused_max_rows() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("CLV_VAE_FUSED_MAX_ROWS"); v = e ? atoi(e) : 4096; }
+  return v;
+}
+// rows from which the tensor-core X head replaces the SIMT one (two tiles per SM); CLV_XHEAD_TC_MIN overrides
+static int64_t xhead_tc_min_rows() {
+  static int64_t v = -1;
+  if (v < 0) { const char* e = getenv("CLV_XHEAD_TC_MIN"); v = e ? atoll(e) : 2LL * 128 * clv_num_sms(); }
   return v;
 }
 static int pair_disabled() {
@@ -311,7 +321,7 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
         *c_d = WSP("c_d"), *logits = WSP("logits"), *dh = WSP("dh"), *dAsum_d = WSP("dAsum_d"),
         *dAsum_e = WSP("dAsum_e"), *dZ = WSP("dZ"), *dZa = WSP("dZa"), *dW_ext = WSP("dW_ext"),
         *dWargs = WSP("dWargs"), *dhW = WSP("dhW"), *wimg_e = WSP("wimg_e"), *wimg_d = WSP("wimg_d"),
-        *uimg_e = WSP("uimg_e"), *uimg_d = WSP("uimg_d");
+        *uimg_e = WSP("uimg_e"), *uimg_d = WSP("uimg_d"), *WSP_X = WSP("ximg");
 #undef WSP
   // hoisted input projections on tensor cores (tcgen05) when asked for and the shape is the built one
   const bool tc = c->gemm_algo == 1 && G == 352 && D <= 96 && (D % 8) == 0;
@@ -432,7 +442,10 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   else TRY_PDL(clv_lstm_fwd_fused(gates_d, c->use_x_prev, Ud, bd, W, Kd_w, C, Zs, Kd_z, Z, h_d, c_d, B, L, H, st));
   }
   // ---- X head + Bernoulli loss + dlogits + dgrad to h_d in one pass (model.py:229-234,241-242)
-  if (H == 88 && D == 88) {
+  if (H == 88 && D == 88 && tc && c->do_backward && BL >= xhead_tc_min_rows()) {
+    // large batches: two chained tcgen05 GEMMs per 128-row tile (xhead_tc.cu)
+    TRY(clv_xhead_tc(h_d, Kx, bx, roll, off, L, sy, loss, logits, dh, WSP_X, BL, H, D, sbl, st));
+  } else if (H == 88 && D == 88) {
     TRY_PDL(clv_xhead_fwd_bwd(h_d, Kx, bx, roll, off, L, sy, loss, logits, dh, BL, H, D, sbl,
                               c->do_backward, st));
   } else {

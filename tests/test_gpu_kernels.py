@@ -311,6 +311,44 @@ def test_xhead_fused_matches_gemm_plus_bernoulli(R, grp):
     assert util.rel_err(dh.cpu().numpy(), dh_ref) < TOL
 
 
+@pytest.mark.parametrize("R,grp", [(3200, 16), (45, 5), (128 * 150 * 3 + 33, 33), (77 * 7, 7)])
+def test_xhead_tensor_core_matches_gemm_plus_bernoulli(R, grp):
+    """clv_xhead_tc (two chained tcgen05 GEMMs, bf16 hi+mid operand splits) against float64 numpy: partial last
+    tile, more tiles than SMs (both pipeline stages of every CTA reused), sequence groups crossing tiles."""
+    _lib, L, check, ptr, st = _env()
+    rng = np.random.default_rng(R + 1)
+    D = H = 88
+    h = rng.uniform(-1, 1, size=(R, H)); Kx = rng.normal(0, 0.3, size=(H, D)); bx = rng.normal(0, 0.3, D)
+    nseq = (R + grp - 1) // grp
+    roll = (rng.random((nseq * (grp + 1) + 40, D)) < 0.1).astype(np.uint8)
+    off = (np.arange(nseq) * (grp + 1)).astype(np.int32)
+    rows = (off[:, None] + 1 + np.arange(grp)[None, :]).reshape(-1)[:R]
+    x = roll[rows].astype(np.float32)
+    logits = (h @ Kx + bx)
+    loss_ref, dl_ref = M.bernoulli_fwd_bwd(logits.astype(np.float32), x, np.float32(1.0 / R))
+    dh_ref = dl_ref.astype(np.float64) @ Kx.T
+    dl = torch.full((R, D), 7.0, device="cuda"); dh = torch.full((R, H), 7.0, device="cuda")
+    loss = torch.zeros(8, device="cuda")
+    scratch = torch.zeros(int(L.clv_xhead_tc_scratch_bytes()), dtype=torch.uint8, device="cuda")
+    hd, Kd, bd, rd, od = dev(h), dev(Kx), dev(bx), dev(roll, torch.uint8), dev(off, torch.int32)
+    for _ in range(2):          # twice: the second call reuses the barriers' phases from scratch
+        loss.zero_()
+        check(L.clv_xhead_tc(ptr(hd), ptr(Kd), ptr(bd), ptr(rd), ptr(od), grp, 1, ptr(loss), ptr(dl), ptr(dh),
+                             ptr(scratch), R, H, D, 1.0 / R, st))
+        torch.cuda.synchronize()
+    assert abs(loss.cpu().numpy()[0] - loss_ref.astype(np.float64).mean()) < TOL * loss_ref.mean()
+    assert util.rel_err(dl.cpu().numpy(), dl_ref) < TOL
+    assert util.rel_err(dh.cpu().numpy(), dh_ref) < TOL
+    # and against the SIMT kernel it replaces, much tighter than the parity tolerance
+    dl2 = torch.zeros(R, D, device="cuda"); dh2 = torch.zeros(R, H, device="cuda"); loss2 = torch.zeros(8, device="cuda")
+    check(L.clv_xhead_fwd_bwd(ptr(hd), ptr(Kd), ptr(bd), ptr(rd), ptr(od), grp, 1, ptr(loss2), ptr(dl2), ptr(dh2),
+                              R, H, D, 1.0 / R, 1, st))
+    torch.cuda.synchronize()
+    assert util.rel_err(dl.cpu().numpy(), dl2.cpu().numpy()) < 2e-5
+    assert util.rel_err(dh.cpu().numpy(), dh2.cpu().numpy()) < 2e-5
+    assert abs(float(loss[0]) - float(loss2[0])) < 1e-5 * abs(float(loss2[0]))
+
+
 @pytest.mark.parametrize("B_,Lq,Cc,dens", [(200, 16, 10, 0.05), (7, 3, 2, 0.5), (3, 64, 16, 0.0), (5, 128, 10, 0.004)])   # last: 34 KB dynamic + 17 KB static smem (opt-in path)
 def test_keyenc_fused_fwd_bwd(B_, Lq, Cc, dens):
     _lib, L, check, ptr, st = _env()
