@@ -10,7 +10,7 @@
 // (hi*hi + hi*mid + mid*hi): relative error ~2^-16 per operand pair, 2e-6 of max|dlogits| on the results
 // (tested at 1e-4 like every other kernel).  Warp-specialised persistent CTAs: 4 producer warps load and
 // split the h tile (double-buffered; the same buffer then receives the dlogits tile), one MMA thread issues
-// 2 x 18 MMAs per tile, 8 epilogue warps; both accumulators double-buffered in TMEM, so the MMA of tile i+1
+// 2 x 18 MMAs per tile, 12 epilogue warps (the loss epilogue of tile i+1 runs during GEMM2 of tile i); both accumulators double-buffered in TMEM, so the MMA of tile i+1
 // runs under the epilogues of tile i.  Replaces clv_xhead_fwd_bwd's SIMT kernels from 256 tiles up.
 #include <cuda_bf16.h>
 #include "common.cuh"
@@ -27,10 +27,10 @@ constexpr int A_SPLIT = TM * KP * 2;           // 24 576
 constexpr int A_STAGE = 2 * A_SPLIT;           // hi + mid
 constexpr int B_SPLIT = NP * KP * 2;           // 18 432
 constexpr int B_IMG = 2 * B_SPLIT;             // hi + mid of one matrix
-constexpr int NEPI = 8;
-constexpr int STAGE_FLOATS = 32 * 36;
+constexpr int NEPI = 12;            // epilogue warps: 4 TMEM quadrants x 3 column parts of 32
+constexpr int STAGE_FLOATS = 32 * 20;
 constexpr int SMEM_BYTES = 2 * A_STAGE + 2 * B_IMG + NEPI * STAGE_FLOATS * 4 + 512 + 1024;
-constexpr int THREADS = 13 * 32;
+constexpr int THREADS = 17 * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -134,7 +134,7 @@ struct XArgs {
 };
 
 //   warps 0-3        producers : h tile fp32 -> bf16 hi/mid, canonical A tile [stage]
-//   warps 4-7, 9-12  epilogue  : quadrant q = warp & 3 (TMEM lanes 32q..32q+31), column half cpart
+//   warps 4-7, 9-16  epilogue  : quadrant q = warp & 3 (TMEM lanes 32q..32q+31), column part cpart (32 columns)
 //   warp  8          MMA       : weight images by bulk copy, then the MMAs of both GEMMs
 __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -183,26 +183,30 @@ __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
     for (int it = 0; it < ntile; ++it) {
       const int s = it & 1, ph = (it >> 1) & 1;
       const int64_t m = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TM + row;
-      float4 v[22];
-      if (m < a.R) {
-        const float4* src = reinterpret_cast<const float4*>(a.h + m * XD);
+      // (the row in two halves of 44 floats: 22 float4 in flight at once cost registers the 12 epilogue warps need)
+      const bool mv = m < a.R;
+      const float4* src = reinterpret_cast<const float4*>(a.h + (mv ? m : 0) * XD);
+      float4 v[12];
 #pragma unroll
-        for (int j = 0; j < 22; ++j) v[j] = __ldg(src + j);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 22; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int j = 0; j < 12; ++j) v[j] = mv ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
       mbar_wait(BAR(A_EMPTY + s), ph ^ 1);       // GEMM2 of the tile that used this stage is done
       uint8_t* dst = a_s + s * A_STAGE + (row >> 3) * SBO + (row & 7) * 16;
 #pragma unroll
-      for (int j = 0; j < 11; ++j) {
-        uint4 hi, mid;
-        split2(v[2 * j].x, v[2 * j].y, hi.x, mid.x);
-        split2(v[2 * j].z, v[2 * j].w, hi.y, mid.y);
-        split2(v[2 * j + 1].x, v[2 * j + 1].y, hi.z, mid.z);
-        split2(v[2 * j + 1].z, v[2 * j + 1].w, hi.w, mid.w);
-        *reinterpret_cast<uint4*>(dst + j * LBO) = hi;
-        *reinterpret_cast<uint4*>(dst + A_SPLIT + j * LBO) = mid;
+      for (int hf = 0; hf < 2; ++hf) {
+        if (hf == 1) {
+#pragma unroll
+          for (int j = 0; j < 10; ++j) v[j] = mv ? __ldg(src + 12 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < (hf == 0 ? 6 : 5); ++j) {
+          uint4 hi, mid;
+          split2(v[2 * j].x, v[2 * j].y, hi.x, mid.x);
+          split2(v[2 * j].z, v[2 * j].w, hi.y, mid.y);
+          split2(v[2 * j + 1].x, v[2 * j + 1].y, hi.z, mid.z);
+          split2(v[2 * j + 1].z, v[2 * j + 1].w, hi.w, mid.w);
+          *reinterpret_cast<uint4*>(dst + (6 * hf + j) * LBO) = hi;
+          *reinterpret_cast<uint4*>(dst + A_SPLIT + (6 * hf + j) * LBO) = mid;
+        }
       }
       *reinterpret_cast<uint4*>(dst + 11 * LBO) = make_uint4(0u, 0u, 0u, 0u);            // k = 88..95
       *reinterpret_cast<uint4*>(dst + A_SPLIT + 11 * LBO) = make_uint4(0u, 0u, 0u, 0u);
@@ -212,9 +216,9 @@ __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
     }
   } else if (warp != 8) {
     // ================= epilogue warps
-    const int q = warp & 3, cpart = (warp > 8) ? 1 : 0;
+    const int q = warp & 3, cpart = warp < 8 ? 0 : (warp < 13 ? 1 : 2);
     float* stage = stage_all + (q + 4 * cpart) * STAGE_FLOATS;
-    const int cbase = 48 * cpart;                 // this warp's 48 columns: [cbase, cbase + 48)
+    const int cbase = 32 * cpart;                 // this warp's 32 columns: [cbase, cbase + 32)
     float lsum = 0.f;
     const float hi_p = 1.0f - CLV_EPS;
     const float lo_l = logf(CLV_EPS / (1.0f - CLV_EPS)), hi_l = logf(hi_p / (1.0f - hi_p));
@@ -238,30 +242,29 @@ __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
       }
       __syncwarp();
     };
-    for (int it = 0; it < ntile; ++it) {
+    auto epi1 = [&](const int it) {
       const int s = it & 1, ph = (it >> 1) & 1;
       const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TM + q * 32;
       const int rows_valid = (int)max((int64_t)0, min((int64_t)32, a.R - m0));
       const int64_t m = m0 + lane;
       const bool rv = m < a.R;
-      // this row's target bits (48 bytes of the roll row, 8-byte aligned)
-      uint2 xb[6];
+      // this row's target bits (32 bytes of the roll row, 8-byte aligned)
+      uint2 xb[4];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) xb[i] = make_uint2(0u, 0u);
+      for (int i = 0; i < 4; ++i) xb[i] = make_uint2(0u, 0u);
       if (rv) {
         const uint32_t mu = (uint32_t)m, g = mu / (uint32_t)a.x_grp;
         const uint8_t* xr = a.roll + ((int64_t)__ldg(a.x_off + g) + a.x_shift + (mu - g * a.x_grp)) * XD + cbase;
 #pragma unroll
-        for (int i = 0; i < 6; ++i)
+        for (int i = 0; i < 4; ++i)
           if (cbase + 8 * i < XD) xb[i] = __ldg(reinterpret_cast<const uint2*>(xr + 8 * i));
       }
-      // ---------- epilogue 1: logits -> loss, dlogits
       mbar_wait(BAR(ACC1_FULL + s), ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t t1 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 128) + (uint32_t)cbase;
       uint8_t* adst = a_s + s * A_STAGE + ((q * 32 + lane) >> 3) * SBO + ((q * 32 + lane) & 7) * 16;
 #pragma unroll 1
-      for (int ch = 0; ch < 3; ++ch) {             // 3 chunks of 16 columns
+      for (int ch = 0; ch < 2; ++ch) {             // 2 chunks of 16 columns
         uint32_t r[16];
         tmem_ld16(t1 + 16 * ch, r);
         float dl[16];
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
             // Keras-BCE of the clipped sigmoid, written on the LOGIT: clip(p, eps, 1-eps) <=> clip(z, lo, hi) with
             // lo/hi the logits of the bounds, so one exponential serves the sigmoid and the softplus term
             // (ex2/rcp/lg2.approx: abs. error < 3e-7 on p and on the loss term; the SIMT kernel's expf/logf/
-            // log1pf chain cost ~100 instructions per element and made the 8 epilogue warps the bottleneck)
+            // log1pf chain cost ~100 instructions per element and made the epilogue warps the bottleneck)
             const float z = __uint_as_float(r[i]) + bias_s[d];
             const float l = fminf(fmaxf(z, lo_l), hi_l);
             const float e = ex2_approx(-fabsf(l) * 1.4426950408889634f);
@@ -300,29 +303,40 @@ __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
           *reinterpret_cast<uint4*>(adst + A_SPLIT + j * LBO) = mid;
         }
         const int c0 = cbase + 16 * ch;
-        store_chunk16(dl, a.dlogits, m0, rows_valid, c0, min(16, XD - c0));
+        if (c0 < XD) store_chunk16(dl, a.dlogits, m0, rows_valid, c0, min(16, XD - c0));
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) { mbar_arrive(BAR(ACC1_EMPTY + s)); mbar_arrive(BAR(A2_FULL + s)); }
-      // ---------- epilogue 2: dh
+    };
+    auto epi2 = [&](const int it) {
+      const int s = it & 1, ph = (it >> 1) & 1;
+      const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TM + q * 32;
+      const int rows_valid = (int)max((int64_t)0, min((int64_t)32, a.R - m0));
       mbar_wait(BAR(ACC2_FULL + s), ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t t2 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 + s * 128) + (uint32_t)cbase;
 #pragma unroll 1
-      for (int ch = 0; ch < 3; ++ch) {
+      for (int ch = 0; ch < 2; ++ch) {
+        const int c0 = cbase + 16 * ch;
+        if (c0 >= XD) break;
         uint32_t r[16];
         tmem_ld16(t2 + 16 * ch, r);
         float vals[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) vals[i] = __uint_as_float(r[i]);
-        const int c0 = cbase + 16 * ch;
         store_chunk16(vals, a.dh, m0, rows_valid, c0, min(16, XD - c0));
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(ACC2_EMPTY + s));
+    };
+    // software pipeline: the loss epilogue of tile i+1 runs while GEMM2 of tile i is in flight
+    if (ntile > 0) epi1(0);
+    for (int it = 0; it < ntile; ++it) {
+      if (it + 1 < ntile) epi1(it + 1);
+      epi2(it);
     }
     lsum = warp_sum(lsum);
     if (lane == 0) atomicAdd(a.loss_acc, lsum * a.scale);

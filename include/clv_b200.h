@@ -259,7 +259,7 @@ int clv_xhead_fwd_bwd(const float* h, const float* Kx, const float* bx, const ui
                       float* dlogits, float* dh, int64_t R, int32_t H, int32_t D, float scale,
                       int32_t do_backward, void* stream);
 
-/* The same head on 5th-gen tensor cores for large batches (R >= 2 x 128 rows per SM in clv_train_step): two
+/* The same head on 5th-gen tensor cores for large batches (R >= 128 rows per SM in clv_train_step): two
  * chained tcgen05 GEMMs per 128-row tile (logits = h @ Kx in TMEM -> loss / dlogits epilogue -> dh = dlogits @
  * Kx^T in TMEM), fp32 operands as bf16 hi + mid splits (three products, ~2^-16 relative).  Always computes the
  * backward.  scratch: clv_xhead_tc_scratch_bytes() bytes, 16-byte aligned (split weight images, rebuilt per

@@ -52,6 +52,16 @@ def test_vrnn_step_with_the_backward_wavefront_matches_oracle(B, L, C, Z, xp):
     assert util.rel_err(e2.params.cpu().numpy(), e.params.cpu().numpy()) < 1e-5
 
 
+def test_vrnn_step_with_the_tensor_core_x_head_matches_oracle():
+    """B * L = 38 400 rows >= 2 x 128 x 148: the step takes the tcgen05 X head (clv_xhead_tc)."""
+    B, L = 2400, 16
+    case = util.make_vrnn_case(B + L + 5, B, L, C=10, Z=2, use_x_prev=True)
+    out, g = util.oracle_vrnn(case, **KW)
+    e = util.engine_for(case, "vrnn", use_graph=False, **KW)
+    check_step(e, out, g)
+    assert util.rel_err(e.ws_view("h_d", (B, L, 88)).cpu().numpy(), out["h_d"].numpy()) < TOL
+
+
 @pytest.mark.parametrize("B,C,Z,xp", [(100, 2, 4, True), (100, 10, 2, False), (5, 3, 16, True)])
 def test_vae_step_matches_oracle(B, C, Z, xp):
     case = util.make_vae_case(B + C, B, C=C, Z=Z, use_x_prev=xp)
