@@ -435,6 +435,22 @@ def main():
         ptr(Kd[D:D + Z]), Z, ptr(dZb), B, L, H, st)))
     t_tc = time_kernel(lambda: check(lib().clv_inproj_tc(
         ptr(e.roll), ptr(e.win_off), L, 1, D, ptr(Ke), G, G, ptr(scratch), ptr(gates), G, B * L, None, 0, 0, st)))
+    # X head: the form the step uses at this row count (tcgen05 from 128 rows per SM, SIMT below)
+    xtc = B * L >= 128 * torch.cuda.get_device_properties(local).multi_processor_count
+    Kxv, bxv = e.view("X_decoded_mean.kernel"), e.view("X_decoded_mean.bias")
+    dlb = torch.zeros(B * L, D, device=devn)
+    if xtc:
+        xscr = torch.zeros(int(lib().clv_xhead_tc_scratch_bytes()), dtype=torch.uint8, device=devn)
+        gKxb, gbxb = torch.zeros(H, D, device=devn), torch.zeros(D, device=devn)
+        t_x = time_kernel(lambda: check(lib().clv_xhead_tc(
+            ptr(hbuf), ptr(Kxv), ptr(bxv), ptr(e.roll), ptr(e.win_off), L, 1, ptr(lacc), ptr(dlb), ptr(dh),
+            ptr(gKxb), ptr(gbxb), ptr(xscr), B * L, H, D, 1.0 / (B * L), st)))
+    else:
+        t_x = time_kernel(lambda: check(lib().clv_xhead_fwd_bwd(
+            ptr(hbuf), ptr(Kxv), ptr(bxv), ptr(e.roll), ptr(e.win_off), L, 1, ptr(lacc), ptr(dlb), ptr(dh),
+            B * L, H, D, 1.0 / (B * L), 1, st)))
+    bytes_x = (3 * 4 * H + D) * B * L                           # read h + target bytes, write dlogits + dh
+    flop_x = 2 * 2 * H * D * B * L
     # algorithmic bytes / flops per launch: streamed operands only, weights excluded
     bytes_fwd = 4 * L * (2 * G + 2 * H + Z) * B                 # read xproj+Zs, write gates+h+c
     bytes_bwd = 4 * L * (2 * G + 3 * H + Z) * B + 4 * (G + Cc) * B   # read gates,c,dh; write dA,dZ,dAsum,dW
@@ -457,6 +473,9 @@ def main():
                                      "replaced in the step by clv_lstm_pair_fwd when Z <= 2" if pair_ok else None),
         "clv_inproj_tc (tcgen05)": kentry(t_tc, bytes_tc, 0, 2, "hbm"),
     }
+    kern["clv_xhead_tc (tcgen05)" if xtc else "clv_xhead_fwd_bwd"] = kentry(
+        t_x, bytes_x, flop_x, 1, "hbm" if xtc else "fp32 FFMA / LSU",
+        "three chained tcgen05 GEMMs per 128-row tile (logits, dh, weight gradient), loss epilogue between them" if xtc else None)
     if pair_ok:
         kern["clv_lstm_pair_fwd"] = kentry(t_pair, bytes_pair, 2 * flop_rec + 2 * H * 2 * Z * L * B, 1, lat,
                                            "encoder + Z heads + decoder forward as one wavefront launch")

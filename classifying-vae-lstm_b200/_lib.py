@@ -78,7 +78,7 @@ PROTOTYPES = {
     "clv_lstm_fwd_tc": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _I32, _I32, _I32, _P]),
     "clv_xhead_fwd_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _I64, _I32, _I32, _F, _I32, _P]),
     "clv_xhead_tc_scratch_bytes": (C.c_int64, []),
-    "clv_xhead_tc": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P]),
+    "clv_xhead_tc": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P]),
     "clv_keyenc_fwd": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32,
                                  _F, _F, _I32, _U64, _P, _P]),
     "clv_keyenc_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _F, _F, _F, _P]),

@@ -26,7 +26,8 @@ extern "C" int clv_xhead_fwd_bwd(const float*, const float*, const float*, const
                                  float, int32_t, void*);
 extern "C" int64_t clv_xhead_tc_scratch_bytes(void);
 extern "C" int clv_xhead_tc(const float*, const float*, const float*, const uint8_t*, const int32_t*, int32_t,
-                            int32_t, float*, float*, float*, void*, int64_t, int32_t, int32_t, float, void*);
+                            int32_t, float*, float*, float*, float*, float*, void*, int64_t, int32_t, int32_t, float,
+                            void*);
 extern "C" int clv_keyenc_fwd(const uint8_t*, const int32_t*, int32_t, int32_t, int32_t, const float*,
                               const float*, const float*, const float*, float*, const int32_t*, float*,
                               float*, float*, float*, int32_t, int32_t, float, float, int32_t, uint64_t,
@@ -443,9 +444,12 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   else TRY_PDL(clv_lstm_fwd_fused(gates_d, c->use_x_prev, Ud, bd, W, Kd_w, C, Zs, Kd_z, Z, h_d, c_d, B, L, H, st));
   }
   // ---- X head + Bernoulli loss + dlogits + dgrad to h_d in one pass (model.py:229-234,241-242)
-  if (H == 88 && D == 88 && tc && c->do_backward && BL >= xhead_tc_min_rows()) {
-    // large batches: two chained tcgen05 GEMMs per 128-row tile (xhead_tc.cu)
-    TRY(clv_xhead_tc(h_d, Kx, bx, roll, off, L, sy, loss, logits, dh, WSP_X, BL, H, D, sbl, st));
+  const bool xtc = H == 88 && D == 88 && tc && c->do_backward && BL >= xhead_tc_min_rows();
+  if (xtc) {
+    // large batches: chained tcgen05 GEMMs per 128-row tile (xhead_tc.cu); the head's weight and bias
+    // gradients come out of the same pass (third GEMM over the two tiles already in shared memory)
+    TRY(clv_xhead_tc(h_d, Kx, bx, roll, off, L, sy, loss, logits, dh, Gr + po[R_X_K], Gr + po[R_X_B], WSP_X, BL, H,
+                     D, sbl, st));
   } else if (H == 88 && D == 88) {
     TRY_PDL(clv_xhead_fwd_bwd(h_d, Kx, bx, roll, off, L, sy, loss, logits, dh, BL, H, D, sbl,
                               c->do_backward, st));
@@ -464,8 +468,10 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
         *gUd = Gr + po[R_DEC_U], *gbd = Gr + po[R_DEC_B], *gKx = Gr + po[R_X_K],
         *gbx = Gr + po[R_X_B];
   TRY(fk.fork());
-  TRY(tn_f32(h_d, H, logits, D, gKx, D, H, D, BL, 0, 0, fk.next()));
-  TRY(clv_colsum(logits, D, BL, D, gbx, 1, fk.next()));
+  if (!xtc) {
+    TRY(tn_f32(h_d, H, logits, D, gKx, D, H, D, BL, 0, 0, fk.next()));
+    TRY(clv_colsum(logits, D, BL, D, gbx, 1, fk.next()));
+  }
   // Z-head exchange fused into the two BPTT kernels (Z <= 2): the decoder BPTT also emits
   // dLoss/d(Z_mean|Z_log_var), the encoder BPTT turns it into dLoss/dh_e per cell, and the head
   // weight gradients move to a side stream -- no kernel between the two recurrences

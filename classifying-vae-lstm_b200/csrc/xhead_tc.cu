@@ -6,11 +6,15 @@
 //                            segments) AND -> the A-operand tile in shared memory, as bf16 hi + mid
 //   GEMM2  dh[128,88]      = dlogits[128,88] * Kx^T    accumulator 2 in TMEM
 //   epilogue 2             : TMEM -> registers -> smem transpose -> global
+//   GEMM3  gKx[88,88] (+ the bias gradient) += h^T * dlogits over the tile's 128 rows: both tiles are already in
+//          shared memory and are read a second time MN-major; accumulator 3 stays in TMEM across all tiles of the
+//          CTA and is added to the gradient buffer with red.add at the end (replaces a 0.68 ms SIMT GEMM + a 0.06
+//          ms column sum at 524 k rows)
 // fp32 operands are split into bf16 hi + mid (2 x 8 mantissa bits) and three products are accumulated in fp32
 // (hi*hi + hi*mid + mid*hi): relative error ~2^-16 per operand pair, 2e-6 of max|dlogits| on the results
 // (tested at 1e-4 like every other kernel).  Warp-specialised persistent CTAs: 4 producer warps load and
-// split the h tile (double-buffered; the same buffer then receives the dlogits tile), one MMA thread issues
-// 2 x 18 MMAs per tile, 12 epilogue warps (the loss epilogue of tile i+1 runs during GEMM2 of tile i); both accumulators double-buffered in TMEM, so the MMA of tile i+1
+// split the h tile (its first half prefetched in registers while the previous tile owns the buffer), one MMA
+// thread issues 2 x 18 + 24 MMAs per tile, 12 epilogue warps (the loss epilogue of tile i+1 runs during GEMM2 of tile i); both accumulators double-buffered in TMEM, so the MMA of tile i+1
 // runs under the epilogues of tile i.  Replaces clv_xhead_fwd_bwd's SIMT kernels from 256 tiles up.
 #include <cuda_bf16.h>
 #include "common.cuh"
@@ -129,35 +133,49 @@ __global__ void xsplit_kernel(const float* __restrict__ Kx, __nv_bfloat16* __res
 struct XArgs {
   const float* h; const float* bx; const __nv_bfloat16* img;
   const uint8_t* roll; const int32_t* x_off; int x_grp, x_shift;
-  float* loss_acc; float* dlogits; float* dh;
+  float* loss_acc; float* dlogits; float* dh; float* gKx; float* gbx;
   int64_t R; float scale; int tiles;
 };
 
-//   warps 0-3        producers : h tile fp32 -> bf16 hi/mid, canonical A tile [stage]
+// MN-major view of a canonical K-major tile (GEMM3 reduces over the ROWS of both tiles): element (mn, k = row)
+// sits at (row / 8) * SBO + (mn / 8) * LBO + (row % 8) * 16 + (mn % 8) * 2, i.e. the MN-major canonical form
+// with the two strides swapped: "leading" (between k-groups) = SBO, "stride" (between mn-groups) = LBO.
+__device__ __forceinline__ constexpr uint32_t umma_idesc_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+//   warps 0-3        producers : h tile fp32 -> bf16 hi/mid, canonical A tile
 //   warps 4-7, 9-16  epilogue  : quadrant q = warp & 3 (TMEM lanes 32q..32q+31), column part cpart (32 columns)
-//   warp  8          MMA       : weight images by bulk copy, then the MMAs of both GEMMs
+//   warp  8          MMA       : weight images by bulk copy, then the MMAs of the three GEMMs
+// TMEM columns: accumulator 1 (logits) at 0 / 96, accumulator 2 (dh) at 192 / 288 (both ping-pong), accumulator 3
+// (the weight gradient, summed over all tiles of the CTA) at 384.
 __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* a_s = smem;                                   // 2 stages x (hi | mid)
+  uint8_t* a1_s = smem;                                  // h tile       (hi | mid)
+  uint8_t* a2_s = smem + A_STAGE;                        // dlogits tile (hi | mid)
   uint8_t* b_s = smem + 2 * A_STAGE;                     // image 0 (hi | mid), image 1 (hi | mid)
   float* stage_all = reinterpret_cast<float*>(smem + 2 * A_STAGE + 2 * B_IMG);
   float* bias_s = stage_all + NEPI * STAGE_FLOATS;       // [96]
-  __shared__ __align__(8) uint64_t bars[15];
+  __shared__ __align__(8) uint64_t bars[16];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = smem_u32(&bars[0]);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  enum { B_FULL = 0, A_FULL = 1, A_EMPTY = 3, ACC1_FULL = 5, ACC1_EMPTY = 7, A2_FULL = 9, ACC2_FULL = 11,
-         ACC2_EMPTY = 13 };
+  enum { B_FULL = 0, A1_FULL = 1, A1_EMPTY = 2, A2_FULL = 3, A2_EMPTY = 4, ACC1_FULL = 5, ACC1_EMPTY = 7,
+         ACC2_FULL = 9, ACC2_EMPTY = 11, ACC3_FULL = 13 };
+  const bool wg = a.gKx != nullptr;                       // GEMM3: weight and bias gradients
 
   if (tid == 0) {
     mbar_init(BAR(B_FULL), 1);
+    mbar_init(BAR(A1_FULL), 4);
+    mbar_init(BAR(A1_EMPTY), 1);
+    mbar_init(BAR(A2_FULL), NEPI);
+    mbar_init(BAR(A2_EMPTY), 1);
+    mbar_init(BAR(ACC3_FULL), 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(BAR(A_FULL + s), 4);
-      mbar_init(BAR(A_EMPTY + s), 1);
       mbar_init(BAR(ACC1_FULL + s), 1);
       mbar_init(BAR(ACC1_EMPTY + s), NEPI);
-      mbar_init(BAR(A2_FULL + s), NEPI);
       mbar_init(BAR(ACC2_FULL + s), 1);
       mbar_init(BAR(ACC2_EMPTY + s), NEPI);
     }
@@ -181,16 +199,16 @@ __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
     // ================= producers: thread = row of the tile
     const int row = tid;
     for (int it = 0; it < ntile; ++it) {
-      const int s = it & 1, ph = (it >> 1) & 1;
       const int64_t m = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TM + row;
-      // (the row in two halves of 44 floats: 22 float4 in flight at once cost registers the 12 epilogue warps need)
+      // (the row in two halves of 44 floats: 22 float4 in flight at once cost registers the 12 epilogue warps
+      //  need; the first half is in flight while the previous tile still owns the buffer)
       const bool mv = m < a.R;
       const float4* src = reinterpret_cast<const float4*>(a.h + (mv ? m : 0) * XD);
       float4 v[12];
 #pragma unroll
       for (int j = 0; j < 12; ++j) v[j] = mv ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      mbar_wait(BAR(A_EMPTY + s), ph ^ 1);       // GEMM2 of the tile that used this stage is done
-      uint8_t* dst = a_s + s * A_STAGE + (row >> 3) * SBO + (row & 7) * 16;
+      mbar_wait(BAR(A1_EMPTY), (it & 1) ^ 1);     // GEMM1 and GEMM3 of the previous tile have read the buffer
+      uint8_t* dst = a1_s + (row >> 3) * SBO + (row & 7) * 16;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         if (hf == 1) {
@@ -208,11 +226,13 @@ __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
           *reinterpret_cast<uint4*>(dst + A_SPLIT + (6 * hf + j) * LBO) = mid;
         }
       }
-      *reinterpret_cast<uint4*>(dst + 11 * LBO) = make_uint4(0u, 0u, 0u, 0u);            // k = 88..95
+      // k = 88..95: zero padding, except k = 88 := 1.0 (bf16 0x3F80) -- GEMM1 multiplies it with a zero weight
+      // row, GEMM3 turns it into the column sums of dlogits (the bias gradient) as row 88 of its result
+      *reinterpret_cast<uint4*>(dst + 11 * LBO) = make_uint4(0x3F80u, 0u, 0u, 0u);
       *reinterpret_cast<uint4*>(dst + A_SPLIT + 11 * LBO) = make_uint4(0u, 0u, 0u, 0u);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(A_FULL + s));
+      if (lane == 0) mbar_arrive(BAR(A1_FULL));
     }
   } else if (warp != 8) {
     // ================= epilogue warps
@@ -225,7 +245,6 @@ __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
     // transposed store of a 16-column chunk held row-per-lane: 4 lanes per 64-byte row segment
     auto store_chunk16 = [&](const float* vals, float* gbase, const int64_t m0, const int rows_valid, const int c0,
                              const int nvalid) {
-      // stage[lane][0..15] <- vals; then lane (rs = lane >> 2, cc = (lane & 3) * 4) stores rows rs, rs+8, ...
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         *reinterpret_cast<float4*>(stage + lane * 20 + 4 * i) =
@@ -260,9 +279,10 @@ __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
           if (cbase + 8 * i < XD) xb[i] = __ldg(reinterpret_cast<const uint2*>(xr + 8 * i));
       }
       mbar_wait(BAR(ACC1_FULL + s), ph);
+      mbar_wait(BAR(A2_EMPTY), (it & 1) ^ 1);     // GEMM2 and GEMM3 of the previous tile have read the dlogits tile
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t t1 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 128) + (uint32_t)cbase;
-      uint8_t* adst = a_s + s * A_STAGE + ((q * 32 + lane) >> 3) * SBO + ((q * 32 + lane) & 7) * 16;
+      const uint32_t t1 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 96) + (uint32_t)cbase;
+      uint8_t* adst = a2_s + ((q * 32 + lane) >> 3) * SBO + ((q * 32 + lane) & 7) * 16;
 #pragma unroll 1
       for (int ch = 0; ch < 2; ++ch) {             // 2 chunks of 16 columns
         uint32_t r[16];
@@ -290,7 +310,7 @@ __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
           }
           dl[i] = v;
         }
-        // A-operand tile of GEMM2: k = d, 8 values per 16-byte store
+        // A-operand tile of GEMM2 (and B operand of GEMM3): k = d, 8 values per 16-byte store
 #pragma unroll
         for (int g8 = 0; g8 < 2; ++g8) {
           uint4 hi, mid;
@@ -308,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) { mbar_arrive(BAR(ACC1_EMPTY + s)); mbar_arrive(BAR(A2_FULL + s)); }
+      if (lane == 0) { mbar_arrive(BAR(ACC1_EMPTY + s)); mbar_arrive(BAR(A2_FULL)); }
     };
     auto epi2 = [&](const int it) {
       const int s = it & 1, ph = (it >> 1) & 1;
@@ -316,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
       const int rows_valid = (int)max((int64_t)0, min((int64_t)32, a.R - m0));
       mbar_wait(BAR(ACC2_FULL + s), ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t t2 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 + s * 128) + (uint32_t)cbase;
+      const uint32_t t2 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(192 + s * 96) + (uint32_t)cbase;
 #pragma unroll 1
       for (int ch = 0; ch < 2; ++ch) {
         const int c0 = cbase + 16 * ch;
@@ -332,7 +352,7 @@ __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(ACC2_EMPTY + s));
     };
-    // software pipeline: the loss epilogue of tile i+1 runs while GEMM2 of tile i is in flight
+    // software pipeline: the loss epilogue of tile i+1 runs while GEMM2 / GEMM3 of tile i are in flight
     if (ntile > 0) epi1(0);
     for (int it = 0; it < ntile; ++it) {
       if (it + 1 < ntile) epi1(it + 1);
@@ -340,6 +360,29 @@ __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
     }
     lsum = warp_sum(lsum);
     if (lane == 0) atomicAdd(a.loss_acc, lsum * a.scale);
+    // ---------- weight / bias gradient: accumulator 3, lane = row of gKx (k), lane 88 = the bias gradient
+    if (wg && ntile > 0) {
+      mbar_wait(BAR(ACC3_FULL), 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int k = q * 32 + lane;
+      const uint32_t t3 = tmem + ((uint32_t)(q * 32) << 16) + 384u + (uint32_t)cbase;
+      if (q < 3) {                                  // (lanes 96..127 hold nothing)
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+          const int c0 = cbase + 16 * ch;
+          if (c0 >= XD) break;
+          uint32_t r[16];
+          tmem_ld16(t3 + 16 * ch, r);
+          float* dstp = k < XD ? a.gKx + (int64_t)k * XD : (k == XD ? a.gbx : nullptr);
+          if (dstp) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < XD) atomicAdd(dstp + c0 + i, __uint_as_float(r[i]));
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
   } else {
     // ================= MMA warp (one elected thread)
     if (lane == 0) {
@@ -349,8 +392,8 @@ __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
       for (int i = 0; i < 4; ++i)
         bulk_g2s(smem_u32(b_s) + i * B_SPLIT, src + (size_t)i * B_SPLIT, B_SPLIT, BAR(B_FULL));
       mbar_wait(BAR(B_FULL), 0);
-      const uint32_t idesc = umma_idesc(TM, NP);
-      const uint32_t b_addr = smem_u32(b_s);
+      const uint32_t idesc = umma_idesc(TM, NP), idesc3 = umma_idesc_mn(TM, NP);
+      const uint32_t b_addr = smem_u32(b_s), a1 = smem_u32(a1_s), a2 = smem_u32(a2_s);
       // three products: (A hi, B hi), (A hi, B mid), (A mid, B hi)
       auto gemm = [&](const uint32_t a_addr, const uint32_t bimg, const uint32_t tacc) {
         uint32_t acc = 0;
@@ -365,28 +408,46 @@ __global__ void __launch_bounds__(THREADS, 1) xhead_tc_kernel(const XArgs a) {
           }
         }
       };
+      uint32_t acc3 = 0;
       auto issue1 = [&](const int it) {
         const int s = it & 1, ph = (it >> 1) & 1;
-        mbar_wait(BAR(A_FULL + s), ph);
+        mbar_wait(BAR(A1_FULL), it & 1);
         mbar_wait(BAR(ACC1_EMPTY + s), ph ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        gemm(smem_u32(a_s + s * A_STAGE), b_addr, tmem + (uint32_t)(s * 128));
+        gemm(a1, b_addr, tmem + (uint32_t)(s * 96));
         umma_commit(BAR(ACC1_FULL + s));
       };
-      auto issue2 = [&](const int it) {
+      auto issue23 = [&](const int it) {
         const int s = it & 1, ph = (it >> 1) & 1;
-        mbar_wait(BAR(A2_FULL + s), ph);
+        mbar_wait(BAR(A2_FULL), it & 1);
         mbar_wait(BAR(ACC2_EMPTY + s), ph ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        gemm(smem_u32(a_s + s * A_STAGE), b_addr + B_IMG, tmem + (uint32_t)(256 + s * 128));
-        umma_commit(BAR(A_EMPTY + s));
+        gemm(a2, b_addr + B_IMG, tmem + (uint32_t)(192 + s * 96));
         umma_commit(BAR(ACC2_FULL + s));
+        if (wg) {
+          // GEMM3: gKx[k][d] += sum_rows h[row][k] * dlogits[row][d] -- both tiles read MN-major (strides swapped),
+          // K = the 128 rows of the tile in 8 steps of 16; M = 128 covers k = 0..95 (+ 32 don't-care rows)
+#pragma unroll
+          for (int pr = 0; pr < 3; ++pr) {
+            const uint32_t ao = a1 + (pr == 2 ? A_SPLIT : 0);
+            const uint32_t bo = a2 + (pr == 1 ? A_SPLIT : 0);
+#pragma unroll
+            for (int kk = 0; kk < TM / 16; ++kk) {
+              umma_bf16(tmem + 384u, umma_desc(ao + kk * 2 * SBO, SBO, LBO), umma_desc(bo + kk * 2 * SBO, SBO, LBO),
+                        idesc3, acc3);
+              acc3 = 1;
+            }
+          }
+        }
+        umma_commit(BAR(A1_EMPTY));
+        umma_commit(BAR(A2_EMPTY));
       };
       if (ntile > 0) issue1(0);
       for (int it = 0; it < ntile; ++it) {
+        issue23(it);
         if (it + 1 < ntile) issue1(it + 1);
-        issue2(it);
       }
+      if (wg && ntile > 0) umma_commit(BAR(ACC3_FULL));
     }
     __syncwarp();
   }
@@ -403,12 +464,13 @@ extern "C" int64_t clv_xhead_tc_scratch_bytes(void) { return 2 * (int64_t)B_IMG;
 
 extern "C" int clv_xhead_tc(const float* h, const float* Kx, const float* bx, const uint8_t* roll,
                             const int32_t* x_off, int32_t x_grp, int32_t x_shift, float* loss_acc,
-                            float* dlogits, float* dh, void* scratch, int64_t R, int32_t H, int32_t D,
-                            float scale, void* stream) {
+                            float* dlogits, float* dh, float* gKx, float* gbx, void* scratch, int64_t R, int32_t H,
+                            int32_t D, float scale, void* stream) {
   if (!h || !Kx || !bx || !roll || !x_off || !loss_acc || !dlogits || !dh || !scratch || x_grp <= 0)
     return CLV_E_INVALID;
+  if ((gKx == nullptr) != (gbx == nullptr)) return CLV_E_INVALID;
   if (H != XD || D != XD || R >= (1LL << 32) || (((uintptr_t)h | (uintptr_t)dlogits | (uintptr_t)dh |
-                                                       (uintptr_t)scratch) & 15) || ((uintptr_t)roll & 7))
+                                                   (uintptr_t)scratch) & 15) || ((uintptr_t)roll & 7))
     return CLV_E_UNSUPPORTED;
   if (R <= 0) return CLV_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -423,7 +485,7 @@ extern "C" int clv_xhead_tc(const float* h, const float* Kx, const float* bx, co
   }
   XArgs a;
   a.h = h; a.bx = bx; a.img = img; a.roll = roll; a.x_off = x_off; a.x_grp = x_grp; a.x_shift = x_shift;
-  a.loss_acc = loss_acc; a.dlogits = dlogits; a.dh = dh; a.R = R; a.scale = scale;
+  a.loss_acc = loss_acc; a.dlogits = dlogits; a.dh = dh; a.gKx = gKx; a.gbx = gbx; a.R = R; a.scale = scale;
   a.tiles = (int)((R + TM - 1) / TM);
   int gx = clv_num_sms();
   if (gx > a.tiles) gx = a.tiles;

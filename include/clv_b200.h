@@ -262,12 +262,13 @@ int clv_xhead_fwd_bwd(const float* h, const float* Kx, const float* bx, const ui
 /* The same head on 5th-gen tensor cores for large batches (R >= 128 rows per SM in clv_train_step): two
  * chained tcgen05 GEMMs per 128-row tile (logits = h @ Kx in TMEM -> loss / dlogits epilogue -> dh = dlogits @
  * Kx^T in TMEM), fp32 operands as bf16 hi + mid splits (three products, ~2^-16 relative).  Always computes the
- * backward.  scratch: clv_xhead_tc_scratch_bytes() bytes, 16-byte aligned (split weight images, rebuilt per
+ * backward.  gKx[H,D] / gbx[D] (both or neither; pre-zeroed or accumulating): the head's weight and bias gradients
+ * h^T @ dlogits and colsum(dlogits), a third GEMM over the two tiles already in shared memory, added with red.add.  scratch: clv_xhead_tc_scratch_bytes() bytes, 16-byte aligned (split weight images, rebuilt per
  * call).  (cl_vrnn/model.py:229-234,241-242 and their backward) */
 int64_t clv_xhead_tc_scratch_bytes(void);
 int clv_xhead_tc(const float* h, const float* Kx, const float* bx, const uint8_t* roll, const int32_t* x_off,
-                 int32_t x_grp, int32_t x_shift, float* loss_acc, float* dlogits, float* dh, void* scratch,
-                 int64_t R, int32_t H, int32_t D, float scale, void* stream);
+                 int32_t x_grp, int32_t x_shift, float* loss_acc, float* dlogits, float* dh, float* gKx, float* gbx,
+                 void* scratch, int64_t R, int32_t H, int32_t D, float scale, void* stream);
 
 /* ---------------------------------------------------------------- key encoder (fused) ------ */
 /* hW = relu(flat(window) @ Khw + b) as a gather-sum over the SET keys of the binary window (exact

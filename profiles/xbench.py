@@ -23,10 +23,11 @@ for R, grp in ((32768, 32), (131072, 32), (524288, 32), (2097152, 32)):
     off = (torch.arange(nseq, device=dev, dtype=torch.int32) * (grp + 1)).contiguous()
     dl = torch.zeros(R, D, device=dev); dh = torch.zeros(R, H, device=dev); loss = torch.zeros(8, device=dev)
     scratch = torch.zeros(int(L.clv_xhead_tc_scratch_bytes()), dtype=torch.uint8, device=dev)
+    gK = torch.zeros(H, D, device=dev); gb = torch.zeros(D, device=dev)
 
     def tc():
         check(L.clv_xhead_tc(ptr(h), ptr(Kx), ptr(bx), ptr(roll), ptr(off), grp, 1, ptr(loss), ptr(dl), ptr(dh),
-                             ptr(scratch), R, H, D, 1.0 / R, st))
+                             ptr(gK), ptr(gb), ptr(scratch), R, H, D, 1.0 / R, st))
 
     def simt():
         check(L.clv_xhead_fwd_bwd(ptr(h), ptr(Kx), ptr(bx), ptr(roll), ptr(off), grp, 1, ptr(loss), ptr(dl), ptr(dh),

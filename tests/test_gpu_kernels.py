@@ -331,11 +331,15 @@ def test_xhead_tensor_core_matches_gemm_plus_bernoulli(R, grp):
     loss = torch.zeros(8, device="cuda")
     scratch = torch.zeros(int(L.clv_xhead_tc_scratch_bytes()), dtype=torch.uint8, device="cuda")
     hd, Kd, bd, rd, od = dev(h), dev(Kx), dev(bx), dev(roll, torch.uint8), dev(off, torch.int32)
+    gK = torch.zeros(H, D, device="cuda"); gb = torch.zeros(D, device="cuda")
     for _ in range(2):          # twice: the second call reuses the barriers' phases from scratch
-        loss.zero_()
+        loss.zero_(); gK.zero_(); gb.zero_()
         check(L.clv_xhead_tc(ptr(hd), ptr(Kd), ptr(bd), ptr(rd), ptr(od), grp, 1, ptr(loss), ptr(dl), ptr(dh),
-                             ptr(scratch), R, H, D, 1.0 / R, st))
+                             ptr(gK), ptr(gb), ptr(scratch), R, H, D, 1.0 / R, st))
         torch.cuda.synchronize()
+    # the head's weight / bias gradients from the third GEMM
+    assert util.rel_err(gK.cpu().numpy(), h.T @ dl_ref.astype(np.float64)) < TOL
+    assert util.rel_err(gb.cpu().numpy(), dl_ref.astype(np.float64).sum(0)) < TOL
     assert abs(loss.cpu().numpy()[0] - loss_ref.astype(np.float64).mean()) < TOL * loss_ref.mean()
     assert util.rel_err(dl.cpu().numpy(), dl_ref) < TOL
     assert util.rel_err(dh.cpu().numpy(), dh_ref) < TOL
