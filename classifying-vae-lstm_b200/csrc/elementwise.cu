@@ -305,6 +305,166 @@ __global__ void chunk_mean_kernel(const float* __restrict__ in, float* __restric
   out[i] = acc / (float)n_chunks;
 }
 
+// ------------------------------------------------------------------------------ K2b, H = 88 and Z <= 2 (the CL-VRNN heads)
+// Large-batch forms.  The general kernels above give a warp to every row: 2Z warp reductions (20 shuffles) per
+// row forward, and backward every lane repeats the row's scalar loads and exponentials -- 232 / 195 us at
+// 524 k rows against a 30 us read of h.  Forward here: 8 lanes per row (coalesced float4 loads, the head kernels
+// in registers, 3 shuffle steps for all 2Z sums).  Weight gradients: lane = row for the per-row scalars
+// (exponentials once per row), then the warp's 32 rows are broadcast one by one with lane = unit.
+template <int Z>
+__global__ void __launch_bounds__(256) gauss_heads_fwd88_kernel(
+    const float* __restrict__ h, const float* __restrict__ Km, const float* __restrict__ bm,
+    const float* __restrict__ Kv, const float* __restrict__ bv, float* __restrict__ eps,
+    float* __restrict__ Zargs, float* __restrict__ Zs, float* __restrict__ loss_acc, const int64_t R,
+    const float scale, const int gen_noise, const uint64_t seed, const uint64_t* ctr) {
+  constexpr int H = 88;
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, l8 = lane & 7, grp = lane >> 3;
+  float4 w[2 * Z][3];
+#pragma unroll
+  for (int j = 0; j < 2 * Z; ++j)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int k4 = l8 + 8 * i;
+      const float* K = j < Z ? Km : Kv;
+      const int jj = j < Z ? j : j - Z;
+      w[j][i] = k4 < 22 ? make_float4(__ldg(K + (4 * k4 + 0) * Z + jj), __ldg(K + (4 * k4 + 1) * Z + jj),
+                                      __ldg(K + (4 * k4 + 2) * Z + jj), __ldg(K + (4 * k4 + 3) * Z + jj))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  const float bmu = l8 < Z ? __ldg(bm + l8) : 0.f, blv = l8 < Z ? __ldg(bv + l8) : 0.f;
+  pdl_wait();                 // everything above reads parameters only
+  pdl_launch_dependents();
+  float kl_local = 0.f;
+  for (int64_t quad = (int64_t)blockIdx.x * 8 + wid; quad * 4 < R; quad += (int64_t)gridDim.x * 8) {
+    const int64_t row = quad * 4 + grp;
+    const bool valid = row < R;
+    const float4* hp = reinterpret_cast<const float4*>(h + (valid ? row : 0) * H);
+    float4 v[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      v[i] = (valid && l8 + 8 * i < 22) ? __ldg(hp + l8 + 8 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float p[2 * Z];
+#pragma unroll
+    for (int j = 0; j < 2 * Z; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        a = fmaf(v[i].x, w[j][i].x, fmaf(v[i].y, w[j][i].y, fmaf(v[i].z, w[j][i].z, fmaf(v[i].w, w[j][i].w, a))));
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      p[j] = a;
+    }
+    if (valid && l8 < Z) {
+      const float mu = (l8 == 0 ? p[0] : p[Z - 1]) + bmu;
+      const float lv = (l8 == 0 ? p[Z] : p[2 * Z - 1]) + blv;
+      float e;
+      if (gen_noise) {
+        e = philox_normal2(seed, *ctr, 2u, (uint64_t)row * Z + l8).x;
+        eps[row * Z + l8] = e;
+      } else {
+        e = eps[row * Z + l8];
+      }
+      Zargs[row * 2 * Z + l8] = mu;
+      Zargs[row * 2 * Z + Z + l8] = lv;
+      Zs[row * Z + l8] = mu + expf(lv * 0.5f) * e;
+      kl_local += -0.5f * (1.0f + lv - mu * mu - expf(lv));
+    }
+  }
+  const float t = block_sum(kl_local, red);
+  if (threadIdx.x == 0) atomicAdd(loss_acc + 3, t * scale);
+}
+
+template <int Z>
+__global__ void __launch_bounds__(256) gauss_heads_wgrad88_kernel(
+    const float* __restrict__ h, const float* __restrict__ eps, const float* __restrict__ Zargs,
+    const float* __restrict__ dZ, float* __restrict__ dKm, float* __restrict__ dbm, float* __restrict__ dKv,
+    float* __restrict__ dbv, const int64_t R, const float klw_scale) {
+  constexpr int H = 88;
+  __shared__ float red_s[2 * Z * H + 2 * Z];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 2 * Z * H + 2 * Z; i += blockDim.x) red_s[i] = 0.f;
+  float accm[3][Z], accv[3][Z], accb[2 * Z];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < Z; ++j) { accm[i][j] = 0.f; accv[i][j] = 0.f; }
+#pragma unroll
+  for (int j = 0; j < 2 * Z; ++j) accb[j] = 0.f;
+  pdl_wait();
+  pdl_launch_dependents();
+  for (int64_t r0 = ((int64_t)blockIdx.x * 8 + wid) * 32; r0 < R; r0 += (int64_t)gridDim.x * 8 * 32) {
+    // lane = row: the per-row scalars
+    const int64_t myrow = r0 + lane;
+    float dmu[Z], dlv[Z];
+#pragma unroll
+    for (int j = 0; j < Z; ++j) {
+      dmu[j] = 0.f; dlv[j] = 0.f;
+      if (myrow < R) {
+        const float mu = __ldg(Zargs + myrow * 2 * Z + j), lv = __ldg(Zargs + myrow * 2 * Z + Z + j);
+        const float dz = __ldg(dZ + myrow * Z + j), e = __ldg(eps + myrow * Z + j);
+        dmu[j] = dz + klw_scale * mu;
+        dlv[j] = dz * e * 0.5f * expf(lv * 0.5f) + klw_scale * 0.5f * (expf(lv) - 1.0f);
+      }
+      accb[j] += dmu[j];
+      accb[Z + j] += dlv[j];
+    }
+    // lane = unit: the warp's rows one by one (4 rows of loads in flight)
+    const int nrow = (int)min((int64_t)32, R - r0);
+#pragma unroll 1
+    for (int rr = 0; rr < nrow; rr += 4) {
+      float hk[4][3];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int k = lane + 32 * i;
+          hk[u][i] = (rr + u < nrow && k < H) ? __ldg(h + (r0 + rr + u) * H + k) : 0.f;
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < Z; ++j) {
+          const float dm = __shfl_sync(0xffffffffu, dmu[j], (rr + u) & 31);
+          const float dl = __shfl_sync(0xffffffffu, dlv[j], (rr + u) & 31);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            accm[i][j] = fmaf(hk[u][i], dm, accm[i][j]);
+            accv[i][j] = fmaf(hk[u][i], dl, accv[i][j]);
+          }
+        }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < Z; ++j) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int k = lane + 32 * i;
+      if (k < H) {
+        atomicAdd(red_s + j * H + k, accm[i][j]);
+        atomicAdd(red_s + (Z + j) * H + k, accv[i][j]);
+      }
+    }
+    const float bm_ = warp_sum(accb[j]), bv_ = warp_sum(accb[Z + j]);
+    if (lane == 0) {
+      atomicAdd(red_s + 2 * Z * H + j, bm_);
+      atomicAdd(red_s + 2 * Z * H + Z + j, bv_);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Z * H; i += blockDim.x) {
+    const int j = i / H, k = i - j * H;
+    atomicAdd(dKm + k * Z + j, red_s[j * H + k]);
+    atomicAdd(dKv + k * Z + j, red_s[(Z + j) * H + k]);
+  }
+  if (threadIdx.x < Z) {
+    atomicAdd(dbm + threadIdx.x, red_s[2 * Z * H + threadIdx.x]);
+    atomicAdd(dbv + threadIdx.x, red_s[2 * Z * H + Z + threadIdx.x]);
+  }
+}
+
 int rows_grid(int64_t R, int warps_per_block) {
   int64_t blocks = (R + warps_per_block - 1) / warps_per_block;
   const int64_t cap = 8LL * clv_num_sms();
@@ -352,6 +512,20 @@ extern "C" int clv_gauss_heads_fwd(const float* h, const float* Km, const float*
   if (H < 1 || H > 32 * KMAX || Z < 1 || Z > 16) return CLV_E_UNSUPPORTED;
   if (gen_noise && !ctr) return CLV_E_INVALID;
   if (R <= 0) return CLV_OK;
+  if (H == 88 && Z <= 2 && (((uintptr_t)h) & 15) == 0) {
+    // 8 lanes per row; enough blocks for 3 per SM, grid-stride beyond
+    int64_t blocks = (R + 31) / 32;
+    const int64_t cap = 6LL * clv_num_sms();
+    if (blocks > cap) blocks = cap;
+    if (Z == 1)
+      CLV_CUDA(clv_launch(gauss_heads_fwd88_kernel<1>, (int)blocks, 256, 0, (cudaStream_t)stream, h, Km, bm, Kv, bv,
+                          eps, Zargs, Zs, loss_acc, R, scale, gen_noise, seed, ctr));
+    else
+      CLV_CUDA(clv_launch(gauss_heads_fwd88_kernel<2>, (int)blocks, 256, 0, (cudaStream_t)stream, h, Km, bm, Kv, bv,
+                          eps, Zargs, Zs, loss_acc, R, scale, gen_noise, seed, ctr));
+    CLV_CHECK_LAUNCH();
+    return CLV_OK;
+  }
   const size_t smem = sizeof(float) * 2 * Z * H;
   CLV_CUDA(clv_launch(gauss_heads_fwd_kernel, rows_grid(R, 8), 256, smem, (cudaStream_t)stream,
                       h, Km, bm, Kv, bv, eps, Zargs, Zs, loss_acc, R, H, Z, scale, gen_noise, seed, ctr));
@@ -368,6 +542,21 @@ extern "C" int clv_gauss_heads_bwd(const float* h, const float* Km, const float*
     return CLV_E_INVALID;
   if (H < 1 || H > 32 * KMAX || Z < 1 || Z > 16) return CLV_E_UNSUPPORTED;
   if (R <= 0) return CLV_OK;
+  cudaStream_t st0 = (cudaStream_t)stream;
+  if (H == 88 && Z <= 2 && !dh && !relu_input) {
+    // weight gradients only (the CL-VRNN step: dh is produced inside the encoder BPTT)
+    int64_t blocks = (R + 255) / 256;
+    const int64_t cap = 2LL * clv_num_sms();
+    if (blocks > cap) blocks = cap;
+    if (Z == 1)
+      CLV_CUDA(clv_launch(gauss_heads_wgrad88_kernel<1>, (int)blocks, 256, 0, st0, h, eps, Zargs, dZ, dKm, dbm, dKv,
+                          dbv, R, klw_scale));
+    else
+      CLV_CUDA(clv_launch(gauss_heads_wgrad88_kernel<2>, (int)blocks, 256, 0, st0, h, eps, Zargs, dZ, dKm, dbm, dKv,
+                          dbv, R, klw_scale));
+    CLV_CHECK_LAUNCH();
+    return CLV_OK;
+  }
   const size_t smem = sizeof(float) * (2 * Z * H + 2 * Z);
   // each warp walks its rows serially (a global-load latency chain per row) and every block ends
   // with H*2Z global atomics: 4 rows per warp balances the two at small R, the cap at large R

@@ -1,0 +1,5 @@
+timeout 200 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_step.py tests/test_gpu_golden.py -m gpu -x -q --timeout=120 2>&1 | tail -4
+for cfg in "16384 32" "4096 32"; do set -- $cfg
+timeout 120 python bench.py --batch $1 --seq-len $2 --steps 10 --warmup 3 --no-sampler --no-vae --no-cpu 2>/dev/null | python -c "import sys,json
+d=json.loads(sys.stdin.readlines()[-1]); print('B=$1 L=$2', d['ms_per_step'], d['launches_per_step'], d['final_losses']['loss'])"
+done

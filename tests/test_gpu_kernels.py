@@ -152,7 +152,7 @@ def test_logitnormal_fwd_bwd(B_, Cc):
     assert util.rel_err(dWa.cpu().numpy(), np.concatenate([dWm, dWlv], -1)) < TOL
 
 
-@pytest.mark.parametrize("R,Z,relu_in", [(3200, 2, 0), (100, 4, 1), (17, 16, 0)])
+@pytest.mark.parametrize("R,Z,relu_in", [(3200, 2, 0), (100, 4, 1), (17, 16, 0), (4099, 1, 0), (33, 2, 0)])
 def test_gauss_heads_fwd_bwd(R, Z, relu_in):
     _lib, L, check, ptr, st = _env()
     rng = np.random.default_rng(R + Z)
@@ -190,6 +190,17 @@ def test_gauss_heads_fwd_bwd(R, Z, relu_in):
     assert util.rel_err(gKv.cpu().numpy(), h.T @ dlv) < TOL
     assert util.rel_err(gbm.cpu().numpy(), dmu.sum(0)) < TOL
     assert util.rel_err(gbv.cpu().numpy(), dlv.sum(0)) < TOL
+    if not relu_in:
+        # weight gradients only (dh = NULL): the form the CL-VRNN step uses; H = 88, Z <= 2 takes the large-batch kernel
+        for t_ in (gKm, gKv, gbm, gbv):
+            t_.zero_()
+        check(L.clv_gauss_heads_bwd(ptr(hd), ptr(Kmd), ptr(Kvd), ptr(epsd), ptr(Za), ptr(dev(dZ)), None,
+                                    ptr(gKm), ptr(gbm), ptr(gKv), ptr(gbv), R, H, Z, klw, 0, st))
+        torch.cuda.synchronize()
+        assert util.rel_err(gKm.cpu().numpy(), h.T @ dmu) < TOL
+        assert util.rel_err(gKv.cpu().numpy(), h.T @ dlv) < TOL
+        assert util.rel_err(gbm.cpu().numpy(), dmu.sum(0)) < TOL
+        assert util.rel_err(gbv.cpu().numpy(), dlv.sum(0)) < TOL
 
 
 @pytest.mark.parametrize("B_,L", [(200, 16), (3, 5), (1, 1), (19, 33), (1200, 4)])
