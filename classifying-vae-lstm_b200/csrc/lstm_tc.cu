@@ -6,11 +6,11 @@
 // U's two fp16 images (UMMA canonical K-major) stay resident in shared memory for the whole kernel;
 // h_{t-1} is re-written into the A tiles by the epilogue every step; the cell state lives in TMEM
 // (88 more columns) and never touches registers between steps.
-//   warps 0-7 : epilogue = the LSTM cell: tcgen05.ld gates + c, add the hoisted input projection (read
+//   warps 0-11: epilogue = the LSTM cell (8 warps left the loads of the hoisted projection latency-bound): tcgen05.ld gates + c, add the hoisted input projection (read
 //               from HBM, bias and W term already folded in, Z term added here), hard-sigmoid / tanh,
 //               write the stash (activated gates, c, h), c -> TMEM, h -> fp16 hi/lo A tiles
-//   warp  8   : one thread issues 36 tcgen05.mma per step (2 N-halves x 3 products x 6 k-steps)
-// Used by clv_train_step for B >= 1024 (the register-resident FFMA kernel of lstm.cu wins below
+//   warp  12  : one thread issues 36 tcgen05.mma per step (2 N-halves x 3 products x 6 k-steps)
+// Used by clv_train_step for B >= 16 384 (the register-resident FFMA kernel of lstm.cu wins below
 // that, where a step is latency-bound).  Keras-2.0.0 cell semantics as in lstm.cu.
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -22,7 +22,7 @@ constexpr int LBO = 128, SBO = (KP / 8) * 128;          // K-major, no swizzle (
 constexpr int U_IMG = G * KP * 2;                       // 67 584 B per split
 constexpr int A_IMG = TM * KP * 2;                      // 24 576 B per split
 constexpr int COL_C = 352;                              // TMEM column of the cell state
-constexpr int NEPI = 8;                                 // epilogue warps
+constexpr int NEPI = 12;                                // epilogue warps: 4 TMEM quadrants x 3 unit ranges
 constexpr int LT_THREADS = (NEPI + 1) * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_fwd_tc_kernel(const LtArgs
     const int q = warp & 3, uh = warp >> 2;
     const int row = q * 32 + lane, b = b0 + row;
     const bool rv = b < a.B;
-    const int u_beg = uh ? 48 : 0, u_end = uh ? H : 48;            // 8-aligned split of the 88 units
+    const int u_beg = 32 * uh, u_end = uh == 2 ? H : 32 * uh + 32;   // 8-aligned split of the 88 units: 32 | 32 | 24
     const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
     {  // c_0 = 0 in TMEM
       float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};

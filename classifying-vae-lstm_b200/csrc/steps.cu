@@ -331,7 +331,7 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
   // register-resident FFMA kernel is latency-optimal
   // measured crossover on B200: 128-row CTAs are latency-bound (~30 us/step), so the chip must be
   // filled (>= 64 CTAs) before tensor cores beat the 2..8-row FFMA kernel
-  const bool tcl = tc && c->use_x_prev && B >= (c->gemm_algo_tc_lstm_min > 0 ? c->gemm_algo_tc_lstm_min : 8192) && Z <= 16;
+  const bool tcl = tc && c->use_x_prev && B >= (c->gemm_algo_tc_lstm_min > 0 ? c->gemm_algo_tc_lstm_min : 16384) && Z <= 16;
   const float *Khw = P + po[R_HW_K], *bhw = P + po[R_HW_B], *Kwa = P + po[R_WA_K],
               *bwa = P + po[R_WA_B], *Ke = P + po[R_ENC_K], *Ue = P + po[R_ENC_U],
               *be = P + po[R_ENC_B], *Kzm = P + po[R_ZM_K], *bzm = P + po[R_ZM_B],

@@ -70,7 +70,7 @@ class Engine:
         self.seed = (int(seed) * 1000003 + rank * 7919 + 1) & 0xFFFFFFFFFFFFFFFF
         self.use_graph = use_graph
         self.overlap_wgrad = bool(overlap_wgrad)
-        self.tc_lstm_min = int(tc_lstm_min)        # 0 = library default (8192)
+        self.tc_lstm_min = int(tc_lstm_min)        # 0 = library default (16384)
         self.fused_optimizer = bool(fused_optimizer)   # world_size 1: clv_train_step_opt
         self.gemm_algo = int(gemm_algo)            # 0: exact-fp32 SIMT GEMMs, 1: tcgen05 input projections
         if self.overlap_wgrad:
