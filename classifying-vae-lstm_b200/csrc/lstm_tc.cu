@@ -6,10 +6,10 @@
 // U's two fp16 images (UMMA canonical K-major) stay resident in shared memory for the whole kernel;
 // h_{t-1} is re-written into the A tiles by the epilogue every step; the cell state lives in TMEM
 // (88 more columns) and never touches registers between steps.
-//   warps 0-11: epilogue = the LSTM cell (8 warps left the loads of the hoisted projection latency-bound): tcgen05.ld gates + c, add the hoisted input projection (read
+//   warps 0-7 : epilogue = the LSTM cell: tcgen05.ld gates + c, add the hoisted input projection (read
 //               from HBM, bias and W term already folded in, Z term added here), hard-sigmoid / tanh,
 //               write the stash (activated gates, c, h), c -> TMEM, h -> fp16 hi/lo A tiles
-//   warp  12  : one thread issues 36 tcgen05.mma per step (2 N-halves x 3 products x 6 k-steps)
+//   warp  8   : one thread issues 36 tcgen05.mma per step (2 N-halves x 3 products x 6 k-steps)
 // Used by clv_train_step for B >= 16 384 (the register-resident FFMA kernel of lstm.cu wins below
 // that, where a step is latency-bound).  Keras-2.0.0 cell semantics as in lstm.cu.
 #include <cuda_fp16.h>
@@ -22,7 +22,7 @@ constexpr int LBO = 128, SBO = (KP / 8) * 128;          // K-major, no swizzle (
 constexpr int U_IMG = G * KP * 2;                       // 67 584 B per split
 constexpr int A_IMG = TM * KP * 2;                      // 24 576 B per split
 constexpr int COL_C = 352;                              // TMEM column of the cell state
-constexpr int NEPI = 12;                                // epilogue warps: 4 TMEM quadrants x 3 unit ranges
+constexpr int NEPI = 8;                                 // epilogue warps (12 measured the same: -0.3 %)
 constexpr int LT_THREADS = (NEPI + 1) * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_fwd_tc_kernel(const LtArgs
     const int q = warp & 3, uh = warp >> 2;
     const int row = q * 32 + lane, b = b0 + row;
     const bool rv = b < a.B;
-    const int u_beg = 32 * uh, u_end = uh == 2 ? H : 32 * uh + 32;   // 8-aligned split of the 88 units: 32 | 32 | 24
+    const int u_beg = uh ? 48 : 0, u_end = uh ? H : 48;            // 8-aligned split of the 88 units
     const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
     {  // c_0 = 0 in TMEM
       float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -162,6 +162,21 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_fwd_tc_kernel(const LtArgs
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_h);                              // h_0 tiles (zeros) are ready
     uint8_t* arow = a_s + (row >> 3) * SBO + (row & 7) * 16;
+    // The hoisted input projection of a chunk is fetched one chunk AHEAD (the first chunk of step t+1 before the
+    // wait for its MMA): it does not depend on the recurrence, and fetched at its point of use every chunk exposed
+    // a full global-load latency (22 % of the stall samples sat on the first add of the loaded values,
+    // profiles/ncu_stalls_lstm_fwd_tc_kernel_B16384_r1_final.txt).
+    float nxi[8], nxf[8], nxg[8], nxo[8];
+    auto fetch = [&](const int t_, const int u_) {
+      if (rv) {
+        const float* g_ = a.gates + ((size_t)b * a.L + t_) * G + u_;
+        ld8(g_, nxi); ld8(g_ + H, nxf); ld8(g_ + 2 * H, nxg); ld8(g_ + 3 * H, nxo);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nxi[i] = nxf[i] = nxg[i] = nxo[i] = 0.f;
+      }
+    };
+    fetch(0, u_beg);
     for (int t = 0; t < a.L; ++t) {
       mbar_wait(bar_acc, t & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -179,12 +194,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_fwd_tc_kernel(const LtArgs
         tmem_ld8(tq + 3 * H + u0, ao);
         tmem_ld8(tq + COL_C + u0, cc);
         float xi[8], xf[8], xg[8], xo[8];
-        if (rv) {
-          ld8(grow + u0, xi); ld8(grow + H + u0, xf); ld8(grow + 2 * H + u0, xg); ld8(grow + 3 * H + u0, xo);
-        } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) xi[i] = xf[i] = xg[i] = xo[i] = 0.f;
-        }
+        for (int i = 0; i < 8; ++i) { xi[i] = nxi[i]; xf[i] = nxf[i]; xg[i] = nxg[i]; xo[i] = nxo[i]; }
+        if (u0 + 8 < u_end) fetch(t, u0 + 8);
+        else if (t + 1 < a.L) fetch(t + 1, u_beg);
         if (a.Zs && rv) {
           for (int j = 0; j < a.Z; ++j) {
             const float* kz = a.Kz + (size_t)j * G + u0;
