@@ -468,7 +468,7 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
         *gUd = Gr + po[R_DEC_U], *gbd = Gr + po[R_DEC_B], *gKx = Gr + po[R_X_K],
         *gbx = Gr + po[R_X_B];
   TRY(fk.fork());
-  if (!xtc) {
+  if (!xtc && !(diag_skip() & 512)) {
     TRY(tn_f32(h_d, H, logits, D, gKx, D, H, D, BL, 0, 0, fk.next()));
     TRY(clv_colsum(logits, D, BL, D, gbx, 1, fk.next()));
   }
@@ -505,9 +505,12 @@ int vrnn_step(const clv_cfg* c, const float* P, float* Gr, float* loss, const ui
     TRY(tn_f32(Zs, Z, gates_d, G, gKd + (int64_t)xo * G, G, Z, G, BL, 0, 0, fk.next()));
     TRY(tn_f32(h_d, H, gates_d, G, gUd, G, H, G, BL, -1, L, fk.next()));
   }
-  TRY(tn_f32(W, C, dAsum_d, G, gKd + (int64_t)(xo + Z) * G, G, C, G, B, 0, 0, fk.next()));
-  TRY(clv_colsum(dAsum_d, G, B, G, gbd, 1, fk.next()));
-  if (fuse_heads) {
+  if (!(dsk & 1024)) {
+    TRY(tn_f32(W, C, dAsum_d, G, gKd + (int64_t)(xo + Z) * G, G, C, G, B, 0, 0, fk.next()));
+    TRY(clv_colsum(dAsum_d, G, B, G, gbd, 1, fk.next()));
+  }
+  if (fuse_heads && (dsk & 2048)) {
+  } else if (fuse_heads) {
     // head weight gradients only (dh = null), off the critical path
     TRY(clv_gauss_heads_bwd(h_e, Kzm, Kzv, eps_z, Zargs, dZ, nullptr, gKzm, gbzm, gKzv, gbzv, BL, H, Z, klw, 0,
                             fk.next()));
